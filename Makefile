@@ -1,0 +1,22 @@
+# Builds the C-ABI kernel library (sm_100a only) and the C oracle helpers.
+NVCC ?= nvcc
+PKG := stable-video-infinity_b200
+CSRC := $(PKG)/csrc
+LIB := $(PKG)/lib/libsvi_b200.so
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --use_fast_math
+SRCS := $(CSRC)/runtime.cu $(CSRC)/gemm_tcgen05.cu $(CSRC)/attn_tcgen05.cu $(CSRC)/elementwise.cu
+OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
+
+all: $(LIB)
+
+build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/svi_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJS)
+	@mkdir -p $(PKG)/lib
+	$(NVCC) -shared -o $@ $(OBJS) -cudart shared
+
+clean:
+	rm -rf build $(LIB)
+.PHONY: all clean

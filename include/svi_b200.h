@@ -1,0 +1,142 @@
+/*
+ * svi_b200.h — C ABI of the B200-native (sm_100a) kernel library for the SVI clip-denoising hot path.
+ *
+ * The reference (vita-epfl/Stable-Video-Infinity) has NO native boundary: its hot path is Python
+ * (diffsynth) calling torch library kernels.  This header therefore DEFINES the boundary a maintainer
+ * would bind with ctypes.  Every entry point cites the reference lines it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - all pointers are borrowed DEVICE pointers (row-major, contiguous unless a leading dimension
+ *     `ld*` in ELEMENTS is given); nothing is allocated or retained by the library;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued asynchronously;
+ *   - return value: 0 = ok, <0 = error (svi_last_error() gives the message of the calling thread);
+ *   - bf16 = __nv_bfloat16 (2 bytes), f32 = float.
+ */
+#ifndef SVI_B200_H_
+#define SVI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVI_ACT_NONE 0
+#define SVI_ACT_GELU_TANH 1
+#define SVI_ACT_SILU 2
+#define SVI_ACT_GELU_ERF 3 /* nn.GELU() default (img_emb MLP, wan_video_dit.py:381) */
+
+/* ABI version of this header / library pair. */
+int svi_abi_version(void);
+/* Message of the last failing call made by this thread (never NULL). */
+const char* svi_last_error(void);
+/* Number of SMs of the current device (148 on B200); <0 on error. */
+int svi_sm_count(void);
+
+/*
+ * Epilogue of svi_gemm_bf16:  v = acc[m,n] + bias[n];  v = act(v);
+ *                             sumsq[m, n / sumsq_group_cols] += v*v   (if sumsq != NULL)
+ *                             v = gate[n] * v                          (if gate != NULL)
+ *                             v = residual[m,n] + v                    (if residual != NULL)
+ *                             out[m,n] = v  (stored as f32 or bf16)
+ */
+typedef struct svi_gemm_epilogue {
+  void* out;             /* [M, ldo] f32 or bf16 */
+  int64_t ldo;           /* elements */
+  int32_t out_is_f32;    /* 1: out is float, 0: out is bf16 */
+  int32_t act;           /* SVI_ACT_* */
+  const float* bias;     /* [N] or NULL */
+  const float* gate;     /* [N] or NULL */
+  const float* residual; /* [M, ldr] f32 or NULL; may alias out when out_is_f32 */
+  int64_t ldr;
+  float* sumsq;          /* [M, sumsq_groups] f32, accumulated with atomicAdd; or NULL */
+  int32_t sumsq_groups;  /* number of column groups that are accumulated (columns beyond are skipped) */
+  int32_t sumsq_group_cols; /* width of one group in columns; multiple of 32 */
+} svi_gemm_epilogue;
+
+/*
+ * out = epilogue(A[M,K] @ W[N,K]^T), A and W bf16, fp32 accumulation on tcgen05 tensor cores (TMEM
+ * accumulators, TMA-fed 128B-swizzled operand tiles, persistent warp-specialised kernel).
+ * Replaces every nn.Linear / F.linear on the path: wan_video_dit.py:227-229,242 (q,k,v,o),
+ * :272-303 (cross-attn q,k,v,o,k_img,v_img), :334-335,372-373 (ffn.0/GELU/ffn.2 with gate+residual),
+ * :401-404 (head), :429-452 (patch/text/time embeddings as GEMMs), vram_management/layers.py:65-71.
+ * Requirements: K % 8 == 0, N % 8 == 0, lda % 8 == 0, ldw % 8 == 0, 16-byte aligned bases.
+ */
+int svi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N,
+                  int32_t K, const svi_gemm_epilogue* ep, void* stream);
+
+/*
+ * Non-causal softmax(Q K^T * scale) V, head_dim 128, bf16 in / bf16 out, fp32 softmax.
+ * Q: [Lq, ldq] bf16 with head h at columns [h*128, h*128+128); K, V likewise with ldk / ldv;
+ * O: [Lq, ldo].  Any Lq, Lk >= 1 (ragged tails masked).  accumulate != 0: O += result
+ * (used for the image branch of cross-attention, wan_video_dit.py:300-301).
+ * Replaces flash_attention(), wan_video_dit.py:116-147 (the single attention entry point).
+ */
+int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                 void* O, int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale,
+                 int32_t accumulate, void* stream);
+
+/*
+ * y[m,:] = LayerNorm(x[m,:]; eps, no affine unless gamma/beta) * (1 + scale[:]) + shift[:]  -> bf16.
+ * x f32 [M, D]; gamma/beta/scale/shift f32 [D] or NULL.  D % 8 == 0, D <= 8192.
+ * Replaces nn.LayerNorm + modulate(): wan_video_dit.py:150-151,331-333,358,368-372,401-403.
+ */
+int svi_layernorm_modulate(const float* x, int32_t M, int32_t D, float eps, const float* gamma,
+                           const float* beta, const float* scale, const float* shift, void* y_bf16,
+                           void* stream);
+
+/*
+ * In place on bf16 rows t[m, 0:D] (leading dim ldt):  t = t * rsqrt(sumsq[m*sumsq_ld + sumsq_col]/D + eps) * w[:]
+ * then, if rope_cos != NULL, the interleaved-pair rotation of every head (head_dim 128):
+ *   (t[2i], t[2i+1]) <- (t[2i] c_i - t[2i+1] s_i,  t[2i] s_i + t[2i+1] c_i),  c,s = rope[(m + row_offset), i], i<64.
+ * Replaces RMSNorm (wan_video_dit.py:186-197, over the FULL width D) + rope_apply (:178-183).
+ */
+int svi_rmsnorm_rope(void* t_bf16, int64_t ldt, int32_t M, int32_t D, const float* sumsq,
+                     int32_t sumsq_ld, int32_t sumsq_col, float eps, const float* w,
+                     const float* rope_cos, const float* rope_sin, int32_t row_offset, void* stream);
+
+/*
+ * Patchify gather (im2col of the k=s=(1,2,2) Conv3d): x f32 [C, F, H, W] -> tokens bf16 [L, Kpad],
+ * L = F*(H/2)*(W/2), column index = c*4 + dy*2 + dx (matching Conv3d weight.reshape(d, C*4)),
+ * columns [C*4, Kpad) zero.  Replaces patchify's Conv3d input side, wan_video_dit.py:473-477.
+ * Up to two sources are concatenated on the channel axis (x: C0 channels, y: C1 channels; y may be NULL),
+ * replacing torch.cat([x, y], dim=1), svi_video.py:94.
+ */
+int svi_patchify_gather(const float* x, int32_t C0, const float* y, int32_t C1, int32_t F, int32_t H,
+                        int32_t W, void* tokens_bf16, int32_t Kpad, void* stream);
+
+/*
+ * Unpatchify scatter: head output f32 [L, ldh] (first 4*C columns = (dy, dx, c)) -> out f32 [C, F, H, W]
+ * ('b (f h w) (x y z c) -> b c (f x) (h y) (w z)', wan_video_dit.py:479-484).
+ */
+int svi_unpatchify(const float* head_out, int64_t ldh, int32_t C, int32_t F, int32_t H, int32_t W,
+                   float* out, void* stream);
+
+/*
+ * Classifier-free guidance + flow-matching Euler step, fused:
+ *   v = v_uncond + cfg * (v_cond - v_uncond);  latents += v * (sigma_next - sigma).
+ * v_uncond may be NULL (cfg == 1 path).  svi_video.py:410,420; flow_match.py:53-64.
+ */
+int svi_cfg_euler_step(float* latents, const float* v_cond, const float* v_uncond, int64_t n,
+                       float cfg, float sigma, float sigma_next, void* stream);
+
+/* dst_bf16[i] = bf16(src_f32[i]);  dst_f32[i] = float(src_bf16[i]) */
+int svi_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+int svi_cast_bf16_to_f32(const void* src_bf16, float* dst, int64_t n, void* stream);
+
+/* out[i] = act(in[i]) on f32 (SiLU in front of time_projection, wan_video_dit.py:441-442) -> bf16 */
+int svi_act_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, int32_t act, void* stream);
+
+/*
+ * mod[j, :] = table[j, :] + t[:] (j < rows) — AdaLN modulation rows (wan_video_dit.py:356-357, 402).
+ * table f32 [rows, D], t f32 [rows_t, D] with rows_t in {1, rows}; out f32 [rows, D].
+ */
+int svi_add_rows(const float* table, const float* t, int32_t rows, int32_t rows_t, int32_t D,
+                 float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVI_B200_H_ */

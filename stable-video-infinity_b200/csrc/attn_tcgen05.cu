@@ -1,0 +1,356 @@
+// Non-causal flash attention forward for sm_100a, head_dim 128, bf16 operands, fp32 softmax.
+//
+// One CTA owns TWO 128-row Q tiles of one head and streams K/V tiles of 128 rows past them:
+//
+//   warps 0-3 : softmax warpgroup for Q tile 0 (thread = row; TMEM lane quadrant = warp % 4)
+//   warps 4-7 : softmax warpgroup for Q tile 1
+//   warp  8   : TMA producer (Q once, then K_j / V_j into 2-stage rings, 128B-swizzled boxes)
+//   warp  9   : tcgen05.mma issuer + TMEM owner
+//
+// TMEM (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,384) | O1 [384,512); P_i (bf16, 64 columns)
+// aliases the front of S_i and is consumed straight from TMEM by the P*V MMA (A operand in TMEM).
+// The issue order  PV_i(j) ; QK_i(j+1)  per tile ping-pongs the two softmax warpgroups against the
+// tensor pipe: while warpgroup 0 exponentiates S0(j+1), the tensor core runs PV1(j) and QK1(j+1).
+// Online softmax uses the lazy-rescale rule (O is only rescaled when a row max grows by > 2^8).
+// Replaces flash_attention(), reference wan_video_dit.py:116-147.
+#include "common.cuh"
+#include "../../include/svi_b200.h"
+
+namespace svi {
+namespace attn {
+
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int HD = 128;
+constexpr int KV_STAGES = 2;
+constexpr int HALF_BYTES = 128 * 64 * 2;   // one 128-row x 64-col swizzled box (16 KB)
+constexpr int TILE_BYTES = 2 * HALF_BYTES;  // 128 x 128 bf16 (32 KB)
+constexpr int NUM_THREADS = 320;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct Params {
+  __nv_bfloat16* O;
+  long long ldo;
+  int Lq, Lk;
+  float scale_log2;  // softmax scale * log2(e)
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_q = smem;                               // [2][TILE_BYTES]
+  uint8_t* smem_k = smem + 2 * TILE_BYTES;              // [KV_STAGES][TILE_BYTES]
+  uint8_t* smem_v = smem_k + KV_STAGES * TILE_BYTES;    // [KV_STAGES][TILE_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + KV_STAGES * TILE_BYTES);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* k_full = bars + 2;     // [2]
+  uint64_t* k_empty = bars + 4;    // [2]
+  uint64_t* v_full = bars + 6;     // [2]
+  uint64_t* v_empty = bars + 8;    // [2]
+  uint64_t* s_full = bars + 10;    // [2]  MMA -> softmax_i : S_i(j) ready (and PV_i(j-1) retired)
+  uint64_t* p_ready = bars + 12;   // [2]  softmax_i -> MMA : P_i(j) in TMEM, O_i rescaled
+  uint64_t* o_full = bars + 14;    // [2]  MMA -> softmax_i : O_i final
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q_row0 = blockIdx.x * (2 * BQ);
+  const int n_kv = (p.Lk + BKV - 1) / BKV;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&q_full[i], 1);
+        mbar_init(&k_full[i], 1);
+        mbar_init(&k_empty[i], 1);
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_ready[i], 4);  // one arrive per softmax warp
+        mbar_init(&o_full[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 8) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (lane == 0) {
+      const int col0 = head * HD;
+      auto load_tile = [&](uint8_t* dst, const CUtensorMap* m, uint64_t* bar, int row) {
+        mbar_expect_tx(bar, TILE_BYTES);
+        tma_load_2d(dst, m, bar, col0, row);
+        tma_load_2d(dst + HALF_BYTES, m, bar, col0 + 64, row);
+      };
+      load_tile(smem_q, &tmap_q, &q_full[0], q_row0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        load_tile(smem_k + s * TILE_BYTES, &tmap_k, &k_full[s], j * BKV);
+        if (j == 0) load_tile(smem_q + TILE_BYTES, &tmap_q, &q_full[1], q_row0 + BQ);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        load_tile(smem_v + s * TILE_BYTES, &tmap_v, &v_full[s], j * BKV);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------ MMA issuer --------------------------------------
+    constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major (d contiguous)
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);   // P K-major (TMEM), V MN-major
+    auto issue_qk = [&](int i, int ks) {
+      const uint32_t qb = smem_u32(smem_q + i * TILE_BYTES);
+      const uint32_t kb = smem_u32(smem_k + ks * TILE_BYTES);
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
+        tc_mma_ss(tmem_base + i * 128, make_smem_desc(qb + off, 16, 1024, 2),
+                  make_smem_desc(kb + off, 16, 1024, 2), idesc_qk, kk != 0);
+      }
+    };
+    auto issue_pv = [&](int i, int vs, bool first_tile) {
+      const uint32_t vb = smem_u32(smem_v + vs * TILE_BYTES);
+#pragma unroll
+      for (int kk = 0; kk < BKV / 16; ++kk) {
+        // B = V tile, MN-major: 64-column atoms HALF_BYTES apart (LBO), 8-row groups 1024 B apart (SBO)
+        const uint64_t bdesc = make_smem_desc(vb + kk * 2048, HALF_BYTES, 1024, 2);
+        tc_mma_ts(tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8, bdesc, idesc_pv,
+                  !(first_tile && kk == 0));
+      }
+    };
+
+    // prologue: S_i(0) = Q_i K_0^T
+    mbar_wait(&k_full[0], 0);
+    for (int i = 0; i < 2; ++i) {
+      mbar_wait(&q_full[i], 0);
+      tc_fence_after();
+      if (lane == 0) {
+        issue_qk(i, 0);
+        tc_commit(&s_full[i]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) tc_commit(&k_empty[0]);
+    __syncwarp();
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int vs = j % KV_STAGES;
+      const int ks = (j + 1) % KV_STAGES;
+      const bool has_next = (j + 1) < n_kv;
+      mbar_wait(&v_full[vs], (j / KV_STAGES) & 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_wait(&p_ready[i], j & 1);
+        if (has_next && i == 0) mbar_wait(&k_full[ks], ((j + 1) / KV_STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_pv(i, vs, j == 0);
+          if (!has_next) tc_commit(&o_full[i]);
+          if (has_next) {
+            issue_qk(i, ks);
+            tc_commit(&s_full[i]);
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        tc_commit(&v_empty[vs]);
+        if (has_next) tc_commit(&k_empty[ks]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------ softmax warpgroups ------------------------------
+    const int i = warp >> 2;    // which Q tile
+    const int quad = warp & 3;  // TMEM lane quadrant
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + i * 128 + lane_sel;
+    const uint32_t tO = tmem_base + 256 + i * 128 + lane_sel;
+    const float c = p.scale_log2;
+    float m_cur = -INFINITY;  // running row max (scaled, log2 domain); reference point of P and O
+    float l = 0.f;            // running row sum of P
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[i], j & 1);
+      tc_fence_after();
+      const int limit = p.Lk - j * BKV;  // number of valid key columns in this tile (>=128: all)
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tS + cc * 32, r);
+        tmem_ld_wait();
+        if (limit >= BKV) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (cc * 32 + e < limit) mx = fmaxf(mx, __uint_as_float(r[e]));
+        }
+      }
+      mx *= c;
+      // lazy rescale (warp-uniform decision because tcgen05.ld/st are warp-collective)
+      const bool need = (j > 0) && (mx > m_cur + RESCALE_THRESHOLD);
+      if (j == 0) {
+        m_cur = mx;
+      } else if (__any_sync(0xffffffffu, need)) {
+        const float m_new = fmaxf(m_cur, mx);
+        const float alpha = ex2(m_cur - m_new);
+        l *= alpha;
+        m_cur = m_new;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(tO + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+          tmem_st32(tO + cc * 32, r);
+        }
+      }
+      // pass 2: P = exp2(S*c - m), row sum, bf16 pack into TMEM (aliasing consumed S columns)
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tS + cc * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = ex2(fmaf(__uint_as_float(r[e]), c, -m_cur));
+          float p1 = ex2(fmaf(__uint_as_float(r[e + 1]), c, -m_cur));
+          if (limit < BKV) {
+            if (cc * 32 + e >= limit) p0 = 0.f;
+            if (cc * 32 + e + 1 >= limit) p1 = 0.f;
+          }
+          l += p0 + p1;
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(tS + cc * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[i]);
+    }
+
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(&o_full[i], 0);
+    tc_fence_after();
+    const int row = q_row0 + i * BQ + quad * 32 + lane;
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* orow = p.O + (long long)row * p.ldo + head * HD;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(tO + cc * 32, r);
+      tmem_ld_wait();
+      if (row < p.Lq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]) * inv_l;
+          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + g * 8);
+          if (p.accumulate) {
+            const uint4 old = *dst;
+            const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(ob[e]);
+              v[2 * e] += f.x;
+              v[2 * e + 1] += f.y;
+            }
+          }
+          uint4 pk;
+          pk.x = pack_bf16x2(v[0], v[1]);
+          pk.y = pack_bf16x2(v[2], v[3]);
+          pk.z = pack_bf16x2(v[4], v[5]);
+          pk.w = pack_bf16x2(v[6], v[7]);
+          *dst = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace attn
+}  // namespace svi
+
+extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V,
+                            int64_t ldv, void* O, int64_t ldo, int32_t Lq, int32_t Lk,
+                            int32_t num_heads, float scale, int32_t accumulate, void* stream) {
+  using namespace svi;
+  using namespace svi::attn;
+  SVI_REQUIRE(Q && K && V && O, "svi_attn_fwd: null pointer");
+  SVI_REQUIRE(Lq > 0 && Lk > 0 && num_heads > 0, "svi_attn_fwd: Lq, Lk, num_heads must be positive");
+  const int64_t width = (int64_t)num_heads * HD;
+  SVI_REQUIRE(ldq >= width && ldk >= width && ldv >= width && ldo >= width,
+              "svi_attn_fwd: leading dimensions must be >= num_heads*128");
+  SVI_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+              "svi_attn_fwd: leading dimensions must be multiples of 8 elements");
+  SVI_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) |
+                reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(O)) & 15) == 0,
+              "svi_attn_fwd: pointers must be 16-byte aligned");
+  CUtensorMap tq, tk, tv;
+  int rc = make_tmap_2d(&tq, Q, 2, (uint64_t)width, (uint64_t)Lq, (uint64_t)ldq * 2, 64, BQ);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tk, K, 2, (uint64_t)width, (uint64_t)Lk, (uint64_t)ldk * 2, 64, BKV);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tv, V, 2, (uint64_t)width, (uint64_t)Lk, (uint64_t)ldv * 2, 64, BKV);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          SMEM_BYTES);
+    if (ce != cudaSuccess) {
+      set_last_error("svi_attn_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce));
+      return SVI_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  Params p;
+  p.O = reinterpret_cast<__nv_bfloat16*>(O);
+  p.ldo = ldo;
+  p.Lq = Lq;
+  p.Lk = Lk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.accumulate = accumulate;
+  dim3 grid((Lq + 2 * BQ - 1) / (2 * BQ), num_heads);
+  attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  SVI_CUDA_LAUNCH_CHECK("svi_attn_fwd");
+  return SVI_OK;
+}

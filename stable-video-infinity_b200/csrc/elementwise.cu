@@ -1,0 +1,344 @@
+// Memory-bound row / elementwise kernels of the DiT hot path (HBM-bound: vectorised 16-byte accesses,
+// one pass over the data, fp32 math).  Each replaces a chain of separate torch elementwise launches
+// in the reference (line map in include/svi_b200.h).
+#include "common.cuh"
+#include "../../include/svi_b200.h"
+
+namespace svi {
+namespace ew {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum for blockDim.x == 128 (4 warps); every thread gets the result
+__device__ __forceinline__ float block_sum_128(float v, float* red /*[4]*/) {
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` reuse
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (+affine) (+modulate) -> bf16.  One 128-thread block per row, row cached in registers.
+// ---------------------------------------------------------------------------------------------
+constexpr int LN_THREADS = 128;
+constexpr int LN_MAX_VEC = 16;  // float4 per thread -> D <= 8192
+
+__global__ void __launch_bounds__(LN_THREADS)
+layernorm_modulate_kernel(const float* __restrict__ x, int D, float eps, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const float* __restrict__ scale,
+                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ y) {
+  __shared__ float red[4];
+  const long long row = blockIdx.x;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  const int nvec = D >> 2;
+  float4 v[LN_MAX_VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int idx = threadIdx.x + i * LN_THREADS;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = block_sum_128(s, red) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int idx = threadIdx.x + i * LN_THREADS;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(block_sum_128(q, red) / (float)D + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + row * D);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int idx = threadIdx.x + i * LN_THREADS;
+    if (idx < nvec) {
+      float o[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd,
+                    (v[i].w - mean) * rstd};
+      if (gamma) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+        o[0] *= g.x; o[1] *= g.y; o[2] *= g.z; o[3] *= g.w;
+      }
+      if (beta) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+        o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+      }
+      if (scale) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + idx);
+        o[0] *= 1.f + sc.x; o[1] *= 1.f + sc.y; o[2] *= 1.f + sc.z; o[3] *= 1.f + sc.w;
+      }
+      if (shift) {
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + idx);
+        o[0] += sh.x; o[1] += sh.y; o[2] += sh.z; o[3] += sh.w;
+      }
+      uint2 pk;
+      pk.x = pack_bf16x2(o[0], o[1]);
+      pk.y = pack_bf16x2(o[2], o[3]);
+      yr[idx] = pk;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// full-width RMSNorm (row sum of squares supplied by the GEMM epilogue) + interleaved-pair RoPE,
+// in place on bf16.  One thread = 8 consecutive columns (4 rotation pairs).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D,
+                    const float* __restrict__ sumsq, int sumsq_ld, int sumsq_col, float eps,
+                    const float* __restrict__ w, const float* __restrict__ rope_cos,
+                    const float* __restrict__ rope_sin, int row_offset) {
+  const int vec_per_row = D >> 3;
+  const long long total = (long long)M * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / vec_per_row);
+    const int c0 = (int)(i % vec_per_row) * 8;
+    const float rs = rsqrtf(sumsq[(long long)m * sumsq_ld + sumsq_col] / (float)D + eps);
+    uint4* ptr = reinterpret_cast<uint4*>(t + (long long)m * ldt + c0);
+    const uint4 raw = *ptr;
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + c0 + 4));
+    float v[8];
+    {
+      const float2 a = __bfloat1622float2(b2[0]), b = __bfloat1622float2(b2[1]),
+                   c = __bfloat1622float2(b2[2]), d = __bfloat1622float2(b2[3]);
+      v[0] = a.x * rs * w0.x; v[1] = a.y * rs * w0.y; v[2] = b.x * rs * w0.z; v[3] = b.y * rs * w0.w;
+      v[4] = c.x * rs * w1.x; v[5] = c.y * rs * w1.y; v[6] = d.x * rs * w1.z; v[7] = d.y * rs * w1.w;
+    }
+    if (rope_cos) {
+      const int pair0 = (c0 & 127) >> 1;  // pair index inside the head (0..63), multiple of 4
+      const long long ro = (long long)(m + row_offset) * 64 + pair0;
+      const float4 cs = __ldg(reinterpret_cast<const float4*>(rope_cos + ro));
+      const float4 sn = __ldg(reinterpret_cast<const float4*>(rope_sin + ro));
+      const float cc[4] = {cs.x, cs.y, cs.z, cs.w};
+      const float ss[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+      for (int pidx = 0; pidx < 4; ++pidx) {
+        const float re = v[2 * pidx], im = v[2 * pidx + 1];
+        v[2 * pidx] = re * cc[pidx] - im * ss[pidx];
+        v[2 * pidx + 1] = re * ss[pidx] + im * cc[pidx];
+      }
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(v[0], v[1]);
+    pk.y = pack_bf16x2(v[2], v[3]);
+    pk.z = pack_bf16x2(v[4], v[5]);
+    pk.w = pack_bf16x2(v[6], v[7]);
+    *ptr = pk;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// patchify gather / unpatchify scatter
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patchify_gather_kernel(const float* __restrict__ x, int C0, const float* __restrict__ y, int C1, int F,
+                       int H, int W, __nv_bfloat16* __restrict__ tok, int Kpad) {
+  const int h2 = H >> 1, w2 = W >> 1;
+  const long long L = (long long)F * h2 * w2;
+  const int C = C0 + C1;
+  const int groups = Kpad >> 2;  // 4 columns (one channel's 2x2 patch) per thread
+  const long long total = L * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long tokn = i % L;  // token fastest -> coalesced reads along w
+    const int c = (int)(i / L);
+    uint2 pk = make_uint2(0u, 0u);
+    if (c < C) {
+      const int f = (int)(tokn / (h2 * w2));
+      const int rem = (int)(tokn % (h2 * w2));
+      const int hh = rem / w2, ww = rem % w2;
+      const float* src = (c < C0) ? (x + (long long)c * F * H * W) : (y + (long long)(c - C0) * F * H * W);
+      const float* p0 = src + ((long long)f * H + 2 * hh) * W + 2 * ww;
+      const float2 r0 = *reinterpret_cast<const float2*>(p0);
+      const float2 r1 = *reinterpret_cast<const float2*>(p0 + W);
+      pk.x = pack_bf16x2(r0.x, r0.y);
+      pk.y = pack_bf16x2(r1.x, r1.y);
+    }
+    *reinterpret_cast<uint2*>(tok + tokn * Kpad + c * 4) = pk;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+unpatchify_kernel(const float* __restrict__ ho, long long ldh, int C, int F, int H, int W,
+                  float* __restrict__ out) {
+  const int h2 = H >> 1, w2 = W >> 1;
+  const long long total = (long long)C * F * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W);
+    const int Y = (int)((i / W) % H);
+    const int f = (int)((i / ((long long)W * H)) % F);
+    const int c = (int)(i / ((long long)W * H * F));
+    const long long tokn = ((long long)f * h2 + (Y >> 1)) * w2 + (X >> 1);
+    const int col = (((Y & 1) << 1) | (X & 1)) * C + c;
+    out[i] = ho[tokn * ldh + col];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small elementwise kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restrict__ vc,
+                                 const float* __restrict__ vu, long long n, float cfg, float dsigma) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = vc[i];
+    if (vu) {
+      const float u = vu[i];
+      v = u + cfg * (v - u);
+    }
+    lat[i] += v * dsigma;
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d,
+                                     long long n, int act) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = s[i];
+    if (act == SVI_ACT_SILU) v = silu(v);
+    else if (act == SVI_ACT_GELU_TANH) v = gelu_tanh(v);
+    else if (act == SVI_ACT_GELU_ERF) v = gelu_erf(v);
+    d[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d,
+                                     long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    d[i] = __bfloat162float(s[i]);
+}
+__global__ void add_rows_kernel(const float* __restrict__ table, const float* __restrict__ t, int rows,
+                                int rows_t, int D, float* __restrict__ out) {
+  const long long n = (long long)rows * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / D), c = (int)(i % D);
+    out[i] = table[i] + t[(rows_t == 1 ? 0 : (long long)r * D) + c];
+  }
+}
+
+inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = 148LL * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace ew
+}  // namespace svi
+
+using namespace svi;
+using namespace svi::ew;
+
+extern "C" int svi_layernorm_modulate(const float* x, int32_t M, int32_t D, float eps, const float* gamma,
+                                      const float* beta, const float* scale, const float* shift,
+                                      void* y_bf16, void* stream) {
+  SVI_REQUIRE(x && y_bf16, "svi_layernorm_modulate: null pointer");
+  SVI_REQUIRE(M > 0 && D > 0 && D % 8 == 0 && D <= 4 * LN_THREADS * LN_MAX_VEC,
+              "svi_layernorm_modulate: need M>0, D %% 8 == 0, D <= 8192 (M=%d D=%d)", M, D);
+  SVI_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0,
+              "svi_layernorm_modulate: alignment");
+  layernorm_modulate_kernel<<<M, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, D, eps, gamma, beta, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16));
+  SVI_CUDA_LAUNCH_CHECK("svi_layernorm_modulate");
+  return SVI_OK;
+}
+
+extern "C" int svi_rmsnorm_rope(void* t_bf16, int64_t ldt, int32_t M, int32_t D, const float* sumsq,
+                                int32_t sumsq_ld, int32_t sumsq_col, float eps, const float* w,
+                                const float* rope_cos, const float* rope_sin, int32_t row_offset,
+                                void* stream) {
+  SVI_REQUIRE(t_bf16 && sumsq && w, "svi_rmsnorm_rope: null pointer");
+  SVI_REQUIRE(M > 0 && D > 0 && D % 8 == 0 && ldt >= D && ldt % 8 == 0,
+              "svi_rmsnorm_rope: need D %% 8 == 0, ldt %% 8 == 0, ldt >= D");
+  SVI_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "svi_rmsnorm_rope: cos/sin must both be given");
+  if (rope_cos) SVI_REQUIRE(D % 128 == 0, "svi_rmsnorm_rope: RoPE needs D %% 128 == 0 (head_dim 128)");
+  SVI_REQUIRE((reinterpret_cast<uintptr_t>(t_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+              "svi_rmsnorm_rope: alignment");
+  const long long total = (long long)M * (D / 8);
+  rmsnorm_rope_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(t_bf16), ldt, M, D, sumsq, sumsq_ld, sumsq_col, eps, w, rope_cos,
+      rope_sin, row_offset);
+  SVI_CUDA_LAUNCH_CHECK("svi_rmsnorm_rope");
+  return SVI_OK;
+}
+
+extern "C" int svi_patchify_gather(const float* x, int32_t C0, const float* y, int32_t C1, int32_t F,
+                                   int32_t H, int32_t W, void* tokens_bf16, int32_t Kpad, void* stream) {
+  SVI_REQUIRE(x && tokens_bf16, "svi_patchify_gather: null pointer");
+  SVI_REQUIRE(C0 > 0 && C1 >= 0 && (C1 == 0 || y), "svi_patchify_gather: bad channel split");
+  SVI_REQUIRE(F > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "svi_patchify_gather: H, W must be even");
+  SVI_REQUIRE(Kpad % 8 == 0 && Kpad >= 4 * (C0 + C1), "svi_patchify_gather: Kpad must be a multiple of 8 >= 4*C");
+  const long long total = (long long)F * (H / 2) * (W / 2) * (Kpad / 4);
+  patchify_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, C0, y, C1, F, H, W, reinterpret_cast<__nv_bfloat16*>(tokens_bf16), Kpad);
+  SVI_CUDA_LAUNCH_CHECK("svi_patchify_gather");
+  return SVI_OK;
+}
+
+extern "C" int svi_unpatchify(const float* head_out, int64_t ldh, int32_t C, int32_t F, int32_t H,
+                              int32_t W, float* out, void* stream) {
+  SVI_REQUIRE(head_out && out, "svi_unpatchify: null pointer");
+  SVI_REQUIRE(C > 0 && F > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && ldh >= 4 * C,
+              "svi_unpatchify: bad shape");
+  const long long total = (long long)C * F * H * W;
+  unpatchify_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(head_out, ldh, C, F,
+                                                                                         H, W, out);
+  SVI_CUDA_LAUNCH_CHECK("svi_unpatchify");
+  return SVI_OK;
+}
+
+extern "C" int svi_cfg_euler_step(float* latents, const float* v_cond, const float* v_uncond, int64_t n,
+                                  float cfg, float sigma, float sigma_next, void* stream) {
+  SVI_REQUIRE(latents && v_cond && n > 0, "svi_cfg_euler_step: null pointer / empty");
+  cfg_euler_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      latents, v_cond, v_uncond, n, cfg, sigma_next - sigma);
+  SVI_CUDA_LAUNCH_CHECK("svi_cfg_euler_step");
+  return SVI_OK;
+}
+
+extern "C" int svi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  SVI_REQUIRE(src && dst && n > 0, "svi_cast_f32_to_bf16: null pointer / empty");
+  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n, SVI_ACT_NONE);
+  SVI_CUDA_LAUNCH_CHECK("svi_cast_f32_to_bf16");
+  return SVI_OK;
+}
+extern "C" int svi_act_f32_to_bf16(const float* src, void* dst, int64_t n, int32_t act, void* stream) {
+  SVI_REQUIRE(src && dst && n > 0, "svi_act_f32_to_bf16: null pointer / empty");
+  SVI_REQUIRE(act >= 0 && act <= 3, "svi_act_f32_to_bf16: unknown activation %d", act);
+  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n, act);
+  SVI_CUDA_LAUNCH_CHECK("svi_act_f32_to_bf16");
+  return SVI_OK;
+}
+extern "C" int svi_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  SVI_REQUIRE(src && dst && n > 0, "svi_cast_bf16_to_f32: null pointer / empty");
+  cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+  SVI_CUDA_LAUNCH_CHECK("svi_cast_bf16_to_f32");
+  return SVI_OK;
+}
+extern "C" int svi_add_rows(const float* table, const float* t, int32_t rows, int32_t rows_t, int32_t D,
+                            float* out, void* stream) {
+  SVI_REQUIRE(table && t && out, "svi_add_rows: null pointer");
+  SVI_REQUIRE(rows > 0 && D > 0 && (rows_t == 1 || rows_t == rows), "svi_add_rows: rows_t must be 1 or rows");
+  add_rows_kernel<<<grid_for((long long)rows * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      table, t, rows, rows_t, D, out);
+  SVI_CUDA_LAUNCH_CHECK("svi_add_rows");
+  return SVI_OK;
+}

@@ -1,0 +1,223 @@
+"""ctypes binding of the C-ABI kernel library ``libsvi_b200.so`` (declared in ``include/svi_b200.h``).
+
+This is the only door between the Python host code and the hand-written sm_100a kernels.  There is no
+fallback: if the shared library is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsvi_b200.so")
+
+ACT_NONE, ACT_GELU_TANH, ACT_SILU, ACT_GELU_ERF = 0, 1, 2, 3
+
+_c = ctypes
+_vp, _i32, _i64, _f32 = _c.c_void_p, _c.c_int32, _c.c_int64, _c.c_float
+
+
+class GemmEpilogue(_c.Structure):
+    """Mirror of ``svi_gemm_epilogue`` (include/svi_b200.h)."""
+    _fields_ = [
+        ("out", _vp), ("ldo", _i64), ("out_is_f32", _i32), ("act", _i32),
+        ("bias", _vp), ("gate", _vp), ("residual", _vp), ("ldr", _i64),
+        ("sumsq", _vp), ("sumsq_groups", _i32), ("sumsq_group_cols", _i32),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol the header declares (checked by tests)
+SIGNATURES = {
+    "svi_abi_version": (_i32, []),
+    "svi_last_error": (_c.c_char_p, []),
+    "svi_sm_count": (_i32, []),
+    "svi_gemm_bf16": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _c.POINTER(GemmEpilogue), _vp]),
+    "svi_attn_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp]),
+    "svi_layernorm_modulate": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "svi_rmsnorm_rope": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _i32, _vp]),
+    "svi_patchify_gather": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "svi_unpatchify": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "svi_cfg_euler_step": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp]),
+    "svi_cast_f32_to_bf16": (_i32, [_vp, _vp, _i64, _vp]),
+    "svi_cast_bf16_to_f32": (_i32, [_vp, _vp, _i64, _vp]),
+    "svi_act_f32_to_bf16": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "svi_add_rows": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load the kernel library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"svi_b200: native kernel library not found at {_LIB_PATH}. Build it with "
+            f"`python -c 'import __graft_entry__ as g; g.build()'` (or `make`) — there is no CPU fallback.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc, name):
+    if rc != 0:
+        msg = load().svi_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{name} failed (status {rc}): {msg}")
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"svi_b200: {name} must be a CUDA tensor (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"svi_b200: {name} must be {dtype}, got {t.dtype}")
+    return _vp(t.data_ptr())
+
+
+def _rowmajor(t, name):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"svi_b200: {name} must be 2-D with unit inner stride, got {tuple(t.shape)} / {t.stride()}")
+    return t.stride(0)
+
+
+def sm_count():
+    return load().svi_sm_count()
+
+
+def gemm(a, w, out, bias=None, act=ACT_NONE, gate=None, residual=None, sumsq=None, sumsq_group_cols=0):
+    """out = epilogue(a[M,K] @ w[N,K]^T); a, w bf16; out f32 or bf16 (may be a column slice view)."""
+    lda, ldw, ldo = _rowmajor(a, "a"), _rowmajor(w, "w"), _rowmajor(out, "out")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or out.shape[0] != M or out.shape[1] != N:
+        raise RuntimeError(f"svi_b200.gemm: shape mismatch a{tuple(a.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
+    ep = GemmEpilogue()
+    ep.out = _ptr(out, name="out")
+    ep.ldo = ldo
+    if out.dtype == torch.float32:
+        ep.out_is_f32 = 1
+    elif out.dtype == torch.bfloat16:
+        ep.out_is_f32 = 0
+    else:
+        raise RuntimeError(f"svi_b200.gemm: out must be f32 or bf16, got {out.dtype}")
+    ep.act = act
+    ep.bias = _ptr(bias, torch.float32, "bias")
+    ep.gate = _ptr(gate, torch.float32, "gate")
+    if residual is not None:
+        ep.residual = _ptr(residual, torch.float32, "residual")
+        ep.ldr = _rowmajor(residual, "residual")
+    if sumsq is not None:
+        ep.sumsq = _ptr(sumsq, torch.float32, "sumsq")
+        ep.sumsq_groups = sumsq.shape[1]
+        ep.sumsq_group_cols = sumsq_group_cols
+    rc = load().svi_gemm_bf16(_ptr(a, torch.bfloat16, "a"), lda, _ptr(w, torch.bfloat16, "w"), ldw,
+                              M, N, K, ctypes.byref(ep), _stream())
+    _check(rc, "svi_gemm_bf16")
+    return out
+
+
+def attention(q, k, v, out, num_heads, scale=None, accumulate=False):
+    """out[Lq, H*128] (+)= softmax(q k^T * scale) v per head; q,k,v,out bf16 2-D (column-slice views allowed)."""
+    ldq, ldk, ldv, ldo = (_rowmajor(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")))
+    if scale is None:
+        scale = 128 ** -0.5
+    rc = load().svi_attn_fwd(_ptr(q, torch.bfloat16, "q"), ldq, _ptr(k, torch.bfloat16, "k"), ldk,
+                             _ptr(v, torch.bfloat16, "v"), ldv, _ptr(out, torch.bfloat16, "out"), ldo,
+                             q.shape[0], k.shape[0], num_heads, float(scale), int(bool(accumulate)), _stream())
+    _check(rc, "svi_attn_fwd")
+    return out
+
+
+def layernorm_modulate(x, out, eps, gamma=None, beta=None, scale=None, shift=None):
+    """out(bf16)[M,D] = LN(x f32 [M,D]) (*gamma + beta) * (1 + scale) + shift."""
+    M, D = x.shape
+    if not x.is_contiguous() or not out.is_contiguous():
+        raise RuntimeError("svi_b200.layernorm_modulate: x and out must be contiguous")
+    rc = load().svi_layernorm_modulate(_ptr(x, torch.float32, "x"), M, D, float(eps),
+                                       _ptr(gamma, torch.float32, "gamma"), _ptr(beta, torch.float32, "beta"),
+                                       _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"),
+                                       _ptr(out, torch.bfloat16, "out"), _stream())
+    _check(rc, "svi_layernorm_modulate")
+    return out
+
+
+def rmsnorm_rope(t, sumsq, sumsq_col, eps, weight, rope_cos=None, rope_sin=None, row_offset=0):
+    """In place on bf16 t[M, D] (row-strided view allowed): full-width RMSNorm + optional RoPE."""
+    ldt = _rowmajor(t, "t")
+    M, D = t.shape
+    rc = load().svi_rmsnorm_rope(_ptr(t, torch.bfloat16, "t"), ldt, M, D, _ptr(sumsq, torch.float32, "sumsq"),
+                                 sumsq.shape[1], sumsq_col, float(eps), _ptr(weight, torch.float32, "weight"),
+                                 _ptr(rope_cos, torch.float32, "rope_cos"), _ptr(rope_sin, torch.float32, "rope_sin"),
+                                 row_offset, _stream())
+    _check(rc, "svi_rmsnorm_rope")
+    return t
+
+
+def patchify_gather(x, y, tokens):
+    """x f32 [C0,F,H,W] (+ y f32 [C1,F,H,W]) -> tokens bf16 [L, Kpad]."""
+    C0, F, H, W = x.shape
+    C1 = 0 if y is None else y.shape[0]
+    if not x.is_contiguous() or (y is not None and not y.is_contiguous()) or not tokens.is_contiguous():
+        raise RuntimeError("svi_b200.patchify_gather: tensors must be contiguous")
+    rc = load().svi_patchify_gather(_ptr(x, torch.float32, "x"), C0, _ptr(y, torch.float32, "y"), C1, F, H, W,
+                                    _ptr(tokens, torch.bfloat16, "tokens"), tokens.shape[1], _stream())
+    _check(rc, "svi_patchify_gather")
+    return tokens
+
+
+def unpatchify(head_out, out):
+    """head_out f32 [L, ld>=4C] -> out f32 [C,F,H,W]."""
+    C, F, H, W = out.shape
+    rc = load().svi_unpatchify(_ptr(head_out, torch.float32, "head_out"), _rowmajor(head_out, "head_out"),
+                               C, F, H, W, _ptr(out, torch.float32, "out"), _stream())
+    _check(rc, "svi_unpatchify")
+    return out
+
+
+def cfg_euler_step(latents, v_cond, v_uncond, cfg, sigma, sigma_next):
+    rc = load().svi_cfg_euler_step(_ptr(latents, torch.float32, "latents"), _ptr(v_cond, torch.float32, "v_cond"),
+                                   _ptr(v_uncond, torch.float32, "v_uncond"), latents.numel(), float(cfg),
+                                   float(sigma), float(sigma_next), _stream())
+    _check(rc, "svi_cfg_euler_step")
+    return latents
+
+
+def cast_f32_to_bf16(src, dst, act=ACT_NONE):
+    if act == ACT_NONE:
+        rc = load().svi_cast_f32_to_bf16(_ptr(src, torch.float32, "src"), _ptr(dst, torch.bfloat16, "dst"),
+                                         src.numel(), _stream())
+    else:
+        rc = load().svi_act_f32_to_bf16(_ptr(src, torch.float32, "src"), _ptr(dst, torch.bfloat16, "dst"),
+                                        src.numel(), act, _stream())
+    _check(rc, "svi_cast_f32_to_bf16")
+    return dst
+
+
+def cast_bf16_to_f32(src, dst):
+    rc = load().svi_cast_bf16_to_f32(_ptr(src, torch.bfloat16, "src"), _ptr(dst, torch.float32, "dst"),
+                                     src.numel(), _stream())
+    _check(rc, "svi_cast_bf16_to_f32")
+    return dst
+
+
+def add_rows(table, t, out):
+    rows, D = table.shape
+    rc = load().svi_add_rows(_ptr(table, torch.float32, "table"), _ptr(t, torch.float32, "t"), rows, t.shape[0], D,
+                             _ptr(out, torch.float32, "out"), _stream())
+    _check(rc, "svi_add_rows")
+    return out

@@ -1,0 +1,173 @@
+"""Generate golden vectors by running the REAL reference modules (from /root/reference) on CPU.
+
+Runs only in the build container (the reference tree does not exist on the GPU box); its outputs,
+``tests/golden/*.npz``, are committed.  The reference ships no tests or golden vectors of its own
+(SURVEY.md §4), so these files are what pins the oracle (``oracle/``) to the reference's behaviour.
+
+Import recipe: pre-register bare ``diffsynth`` package modules pointing into the reference
+tree (skipping its heavy ``__init__``), stub the four missing third-party modules, force the flash-attn
+availability flags off so the SDPA branch runs on CPU.
+
+usage:  python tests/golden/make_golden.py [--ref /root/reference]
+"""
+import argparse
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from tools import synth  # noqa: E402
+
+
+def import_reference(ref_root):
+    def pkg(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+        return m
+
+    pkg("diffsynth", os.path.join(ref_root, "diffsynth"))
+    pkg("diffsynth.models", os.path.join(ref_root, "diffsynth", "models"))
+    pkg("diffsynth.utils", os.path.join(ref_root, "diffsynth", "utils"))
+    pkg("diffsynth.schedulers", os.path.join(ref_root, "diffsynth", "schedulers"))
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _Any:  # permissive placeholder
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            return None
+
+    stub("xfuser")
+    stub("xfuser.core")
+    stub("xfuser.core.distributed", get_sequence_parallel_rank=lambda: 0, get_sequence_parallel_world_size=lambda: 1,
+         get_sp_group=lambda: None)
+    stub("xformers")
+    stub("xformers.ops", memory_efficient_attention=None)
+    stub("imageio")
+
+    class ModelMixin(torch.nn.Module):
+        pass
+
+    class ConfigMixin:
+        pass
+
+    stub("diffusers", ModelMixin=ModelMixin, ConfigMixin=ConfigMixin)
+    stub("diffusers.configuration_utils", ConfigMixin=ConfigMixin, register_to_config=lambda f: f)
+    stub("diffusers.models", ModelMixin=ModelMixin)
+    stub("diffusers.models.modeling_utils", ModelMixin=ModelMixin)
+
+    dit = importlib.import_module("diffsynth.models.wan_video_dit")
+    dit.FLASH_ATTN_2_AVAILABLE = False
+    dit.FLASH_ATTN_3_AVAILABLE = False
+    dit.SAGE_ATTN_AVAILABLE = False
+    vae = importlib.import_module("diffsynth.models.wan_video_vae")
+    fm = importlib.import_module("diffsynth.schedulers.flow_match")
+    return dit, vae, fm
+
+
+def ref_model_fn(dit_mod, model, x, timestep, context, clip_feature=None, y=None):
+    """The reference's model_fn_wan_video (svi_video.py:74-137) is a free function in a pipeline module that
+    cannot be imported without the whole package; WanModel.forward (wan_video_dit.py:486-567) is its
+    documented training twin with identical arithmetic for the non-TeaCache / non-USP path."""
+    return model(x, timestep, context, clip_feature=clip_feature, y=y)
+
+
+def golden_dit(dit_mod, cfg, name, f, h, w, ctx_len, seed):
+    model = dit_mod.WanModel(**cfg).eval()
+    sd = synth.make_dit_state_dict(cfg, seed=seed)
+    missing, unexpected = model.load_state_dict(sd, strict=True), None
+    inp = synth.make_dit_inputs(cfg, f, h, w, seed=seed, ctx_len=ctx_len)
+    ts = torch.tensor([937.5])
+    with torch.no_grad():
+        out = ref_model_fn(dit_mod, model, inp["x"], ts, inp["context"], inp.get("clip_feature"), inp.get("y"))
+        # intermediate pins: one block, rope, rmsnorm
+        blk_x = torch.randn(1, f * (h // 2) * (w // 2), cfg["dim"], generator=torch.Generator().manual_seed(7))
+        t = model.time_embedding(dit_mod.sinusoidal_embedding_1d(cfg["freq_dim"], ts))
+        t_mod = model.time_projection(t).unflatten(1, (6, cfg["dim"]))
+        ctx = model.text_embedding(inp["context"])
+        if cfg["has_image_input"]:
+            ctx = torch.cat([model.img_emb(inp["clip_feature"]), ctx], dim=1)
+        fr = torch.cat([model.freqs[0][:f].view(f, 1, 1, -1).expand(f, h // 2, w // 2, -1),
+                        model.freqs[1][:h // 2].view(1, h // 2, 1, -1).expand(f, h // 2, w // 2, -1),
+                        model.freqs[2][:w // 2].view(1, 1, w // 2, -1).expand(f, h // 2, w // 2, -1)],
+                       dim=-1).reshape(f * (h // 2) * (w // 2), 1, -1)
+        blk_out = model.blocks[0](blk_x, ctx, t_mod, fr)
+        rope_out = dit_mod.rope_apply(blk_x, fr, cfg["num_heads"])
+        rms_out = model.blocks[0].self_attn.norm_q(blk_x)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"),
+                        out=out.numpy(), timestep=ts.numpy(), blk_x=blk_x.numpy(), blk_out=blk_out.numpy(),
+                        rope_out=rope_out.numpy(), rms_out=rms_out.numpy(), t=t.numpy(), t_mod=t_mod.numpy(),
+                        ctx=ctx.numpy(), weight_checksum=np.float64(sum(v.double().sum().item() for v in sd.values())),
+                        fhw=np.array([f, h, w]), ctx_len=np.int64(ctx_len), seed=np.int64(seed))
+    print(name, "out", tuple(out.shape), "std", out.std().item())
+
+
+def golden_scheduler(fm):
+    res = {}
+    for steps in (1, 4, 50):
+        s = fm.FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True)
+        s.set_timesteps(steps, denoising_strength=1.0, shift=5.0)
+        res[f"sigmas_{steps}"] = s.sigmas.numpy()
+        res[f"timesteps_{steps}"] = s.timesteps.numpy()
+    s = fm.FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True)
+    s.set_timesteps(4, shift=5.0)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, generator=g)
+    xs = [x.numpy()]
+    vs = []
+    for i, t in enumerate(s.timesteps):
+        v = torch.randn(2, 5, generator=g)
+        x = s.step(v, s.timesteps[i], x)
+        vs.append(v.numpy())
+        xs.append(x.numpy())
+    res["step_x"] = np.stack(xs)
+    res["step_v"] = np.stack(vs)
+    np.savez_compressed(os.path.join(HERE, "flow_match.npz"), **res)
+    print("flow_match timesteps_50[:3]", res["timesteps_50"][:3], "last", res["timesteps_50"][-1])
+
+
+def golden_vae(vae_mod):
+    sys.path.insert(0, ROOT)
+    from tools import synth_vae
+    model = vae_mod.WanVideoVAE().eval()
+    sd = synth_vae.make_vae_state_dict(seed=0)
+    model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(11)
+    video = torch.rand(3, 9, 32, 48, generator=g) * 2 - 1
+    with torch.no_grad():
+        lat = model.encode([video], device="cpu")          # [1,16,3,4,6]
+        z = torch.randn(1, 16, 3, 4, 6, generator=g)
+        dec = model.decode(z, device="cpu")                # [1,3,9,32,48]
+    np.savez_compressed(os.path.join(HERE, "vae_tiny.npz"), video=video.numpy(), lat=lat.numpy(), z=z.numpy(),
+                        dec=dec.numpy())
+    print("vae lat", tuple(lat.shape), "dec", tuple(dec.shape), "dec std", dec.std().item())
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    dit_mod, vae_mod, fm = import_reference(a.ref)
+    if a.only in ("", "dit"):
+        golden_dit(dit_mod, synth.CFG_TINY_T2V, "dit_tiny_t2v", f=3, h=8, w=12, ctx_len=40, seed=0)
+        golden_dit(dit_mod, synth.CFG_TINY_I2V, "dit_tiny_i2v", f=2, h=6, w=10, ctx_len=24, seed=1)
+    if a.only in ("", "sched"):
+        golden_scheduler(fm)
+    if a.only in ("", "vae") and os.path.exists(os.path.join(ROOT, "tools", "synth_vae.py")):
+        golden_vae(vae_mod)

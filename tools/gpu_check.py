@@ -1,0 +1,264 @@
+"""Kernel-level GPU checks with verbose diagnostics (development tool; the pytest -m gpu suite is the gate).
+
+usage: python tools/gpu_check.py <section> [...]   sections: gemm gemm_epi attn attn_cross ew perf_gemm perf_attn
+Each section prints one line per case: name, max abs err, reference scale, verdict.
+"""
+import math
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "stable-video-infinity_b200"))
+from diffsynth import _native as nv  # noqa: E402
+
+dev = "cuda"
+
+
+def report(name, got, ref, tol):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    mx = err.max().item()
+    scale = ref.abs().max().item()
+    bad = (err > tol * max(scale, 1e-6)).float().mean().item()
+    ok = math.isfinite(mx) and mx <= tol * max(scale, 1e-6)
+    print(f"[{'OK ' if ok else 'BAD'}] {name}: max_err={mx:.4e} ref_max={scale:.4e} frac_bad={bad:.4f}", flush=True)
+    if not ok:
+        # locate the error pattern to help debugging descriptor/layout mistakes
+        idx = (err > tol * max(scale, 1e-6)).nonzero()
+        if idx.numel():
+            rows = idx[:, 0].unique()
+            cols = idx[:, 1].unique() if idx.shape[1] > 1 else idx[:, 0]
+            print(f"      bad rows: n={rows.numel()} first={rows[:8].tolist()} | bad cols: n={cols.numel()} first={cols[:16].tolist()}")
+            r0, c0 = idx[0, 0].item(), (idx[0, 1].item() if idx.shape[1] > 1 else 0)
+            print(f"      sample got={got[r0, c0:c0+4].tolist()} ref={ref[r0, c0:c0+4].tolist()}")
+    return ok
+
+
+def time_ms(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def sec_gemm():
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for (M, N, K) in [(128, 256, 64), (128, 256, 256), (256, 512, 128), (100, 64, 64), (1, 1536, 256),
+                      (3200, 1536, 1536), (333, 4608, 1536), (512, 1536, 4096), (777, 8960, 1536), (640, 1536, 8960),
+                      (130, 264, 72)]:
+        a = (torch.randn(M, K, generator=g) * 0.5).to(dev, torch.bfloat16)
+        w = (torch.randn(N, K, generator=g) * 0.5).to(dev, torch.bfloat16)
+        out = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32)
+        nv.gemm(a, w, out)
+        torch.cuda.synchronize()
+        ref = a.float() @ w.float().t()
+        report(f"gemm f32out M={M} N={N} K={K}", out, ref, 2e-3)
+
+
+def sec_gemm_epi():
+    g = torch.Generator(device="cpu").manual_seed(1)
+    M, N, K = 300, 1536, 512
+    a = (torch.randn(M, K, generator=g) * 0.3).to(dev, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.1).to(dev, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(dev)
+    gate = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    acc = a.float() @ w.float().t()
+    # bf16 out + bias + gelu
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    nv.gemm(a, w, out, bias=bias, act=nv.ACT_GELU_TANH)
+    report("epi bias+gelu_tanh bf16", out, torch.nn.functional.gelu(acc + bias, approximate="tanh"), 1e-2)
+    nv.gemm(a, w, out, bias=bias, act=nv.ACT_SILU)
+    report("epi bias+silu bf16", out, torch.nn.functional.silu(acc + bias), 1e-2)
+    nv.gemm(a, w, out, bias=bias, act=nv.ACT_GELU_ERF)
+    report("epi bias+gelu_erf bf16", out, torch.nn.functional.gelu(acc + bias), 1e-2)
+    # f32 out, gate, residual in place
+    x = res.clone()
+    nv.gemm(a, w, x, bias=bias, gate=gate, residual=x)
+    report("epi bias+gate+residual(in place) f32", x, res + gate * (acc + bias), 2e-3)
+    # sumsq with 3 groups of 512 columns, 2 accumulated; output into a column-slice view (ld > N)
+    big = torch.zeros(M, 2 * N, device=dev, dtype=torch.bfloat16)
+    ss = torch.zeros(M, 2, device=dev, dtype=torch.float32)
+    nv.gemm(a, w, big[:, N:], bias=bias, sumsq=ss, sumsq_group_cols=512)
+    v = acc + bias
+    report("epi strided bf16 out", big[:, N:], v, 1e-2)
+    report("epi strided untouched half", big[:, :N], torch.zeros_like(v), 1e-6)
+    ref_ss = torch.stack([(v[:, :512] ** 2).sum(1), (v[:, 512:1024] ** 2).sum(1)], dim=1)
+    report("epi sumsq", ss, ref_ss, 2e-3)
+
+
+def attn_ref(q, k, v, H, scale):
+    Lq, Lk = q.shape[0], k.shape[0]
+    qh = q.float().view(Lq, H, 128).transpose(0, 1)
+    kh = k.float().view(Lk, H, 128).transpose(0, 1)
+    vh = v.float().view(Lk, H, 128).transpose(0, 1)
+    s = (qh @ kh.transpose(1, 2)) * scale
+    p = torch.softmax(s, dim=-1)
+    return (p @ vh).transpose(0, 1).reshape(Lq, H * 128)
+
+
+def sec_attn():
+    g = torch.Generator(device="cpu").manual_seed(2)
+    scale = 128 ** -0.5
+    for (Lq, Lk, H, amp) in [(256, 128, 1, 1.0), (256, 256, 1, 1.0), (256, 512, 2, 1.0), (128, 128, 1, 1.0),
+                             (300, 333, 2, 1.0), (1000, 1000, 3, 3.0), (257, 77, 1, 1.0), (3200, 3200, 2, 2.0)]:
+        q = (torch.randn(Lq, H * 128, generator=g) * amp).to(dev, torch.bfloat16)
+        k = (torch.randn(Lk, H * 128, generator=g) * amp).to(dev, torch.bfloat16)
+        v = torch.randn(Lk, H * 128, generator=g).to(dev, torch.bfloat16)
+        out = torch.full((Lq, H * 128), float("nan"), device=dev, dtype=torch.bfloat16)
+        nv.attention(q, k, v, out, H, scale)
+        torch.cuda.synchronize()
+        report(f"attn Lq={Lq} Lk={Lk} H={H} amp={amp}", out, attn_ref(q, k, v, H, scale), 2e-2)
+
+
+def sec_attn_cross():
+    g = torch.Generator(device="cpu").manual_seed(3)
+    scale = 128 ** -0.5
+    H, Lq = 2, 700
+    # fused qkv layout: q,k,v are column slices of one [L, 3*H*128] buffer
+    qkv = torch.randn(Lq, 3 * H * 128, generator=g).to(dev, torch.bfloat16)
+    d = H * 128
+    out = torch.empty(Lq, d, device=dev, dtype=torch.bfloat16)
+    nv.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, H, scale)
+    report("attn strided qkv slices", out, attn_ref(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], H, scale), 2e-2)
+    # cross attention: Lk=512 then accumulate Lk=257
+    q = torch.randn(Lq, d, generator=g).to(dev, torch.bfloat16)
+    k1 = torch.randn(512, d, generator=g).to(dev, torch.bfloat16)
+    v1 = torch.randn(512, d, generator=g).to(dev, torch.bfloat16)
+    k2 = torch.randn(257, d, generator=g).to(dev, torch.bfloat16)
+    v2 = torch.randn(257, d, generator=g).to(dev, torch.bfloat16)
+    nv.attention(q, k1, v1, out, H, scale)
+    r1 = attn_ref(q, k1, v1, H, scale)
+    report("cross Lk=512", out, r1, 2e-2)
+    nv.attention(q, k2, v2, out, H, scale, accumulate=True)
+    report("cross accumulate Lk=257", out, r1.bfloat16().float() + attn_ref(q, k2, v2, H, scale), 3e-2)
+
+
+def sec_ew():
+    g = torch.Generator(device="cpu").manual_seed(4)
+    for (M, D) in [(77, 1536), (5, 5120), (300, 256), (33, 1280)]:
+        x = (torch.randn(M, D, generator=g) * 2 + 0.3).to(dev)
+        scale = torch.randn(D, generator=g).to(dev) * 0.1
+        shift = torch.randn(D, generator=g).to(dev) * 0.1
+        gamma = torch.randn(D, generator=g).to(dev)
+        beta = torch.randn(D, generator=g).to(dev)
+        out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+        nv.layernorm_modulate(x, out, 1e-6, scale=scale, shift=shift)
+        ref = torch.nn.functional.layer_norm(x, (D,), eps=1e-6) * (1 + scale) + shift
+        report(f"ln_modulate M={M} D={D}", out, ref, 1e-2)
+        nv.layernorm_modulate(x, out, 1e-6, gamma=gamma, beta=beta)
+        ref = torch.nn.functional.layer_norm(x, (D,), gamma, beta, eps=1e-6)
+        report(f"ln_affine M={M} D={D}", out, ref, 1e-2)
+    # rmsnorm + rope
+    M, H = 200, 3
+    D = H * 128
+    t = torch.randn(M, 3 * D, generator=g).to(dev, torch.bfloat16)
+    w = (torch.randn(D, generator=g) * 0.2 + 1).to(dev)
+    tf = t.float()
+    ss = torch.stack([(tf[:, :D] ** 2).sum(1), (tf[:, D:2 * D] ** 2).sum(1)], 1).contiguous()
+    ang = torch.rand(M + 10, 64, generator=g, dtype=torch.float64) * 6.28
+    cos, sin = ang.cos().float().to(dev), ang.sin().float().to(dev)
+    ref_in = tf[:, D:2 * D]
+    ref = ref_in * torch.rsqrt(ss[:, 1:2] / D + 1e-6) * w
+    refc = torch.view_as_complex(ref.double().reshape(M, H, 64, 2))
+    fr = torch.polar(torch.ones(M, 64, dtype=torch.float64), ang[3:3 + M]).to(dev)
+    ref_r = torch.view_as_real(refc * fr[:, None, :]).reshape(M, D).float()
+    t2 = t.clone()
+    nv.rmsnorm_rope(t2[:, D:2 * D], ss, 1, 1e-6, w, cos, sin, row_offset=3)
+    report("rmsnorm+rope (strided k slice)", t2[:, D:2 * D], ref_r, 1e-2)
+    report("rmsnorm+rope left q slice untouched", t2[:, :D], tf[:, :D], 1e-6)
+    t3 = t.clone()
+    nv.rmsnorm_rope(t3[:, :D], ss, 0, 1e-6, w)
+    report("rmsnorm only", t3[:, :D], tf[:, :D] * torch.rsqrt(ss[:, 0:1] / D + 1e-6) * w, 1e-2)
+    # patchify / unpatchify
+    C0, C1, F, Hh, Ww = 16, 20, 3, 8, 12
+    x = torch.randn(C0, F, Hh, Ww, generator=g).to(dev)
+    y = torch.randn(C1, F, Hh, Ww, generator=g).to(dev)
+    L = F * (Hh // 2) * (Ww // 2)
+    tok = torch.empty(L, 4 * (C0 + C1), device=dev, dtype=torch.bfloat16)
+    nv.patchify_gather(x, y, tok)
+    xy = torch.cat([x, y], 0)
+    ref = xy.view(C0 + C1, F, Hh // 2, 2, Ww // 2, 2).permute(1, 2, 4, 0, 3, 5).reshape(L, (C0 + C1) * 4)
+    report("patchify_gather", tok, ref, 1e-2)
+    ho = torch.randn(L, 64, generator=g).to(dev)
+    out = torch.empty(16, F, Hh, Ww, device=dev)
+    nv.unpatchify(ho, out)
+    ref = ho.view(F, Hh // 2, Ww // 2, 2, 2, 16).permute(5, 0, 1, 3, 2, 4).reshape(16, F, Hh, Ww)
+    report("unpatchify", out.reshape(16, -1), ref.reshape(16, -1), 1e-6)
+    # cfg euler
+    lat = torch.randn(1000, 7, generator=g).to(dev)
+    vc = torch.randn(1000, 7, generator=g).to(dev)
+    vu = torch.randn(1000, 7, generator=g).to(dev)
+    l2 = lat.clone()
+    nv.cfg_euler_step(l2, vc, vu, 5.0, 0.9, 0.8)
+    report("cfg_euler", l2, lat + (vu + 5.0 * (vc - vu)) * (0.8 - 0.9), 1e-5)
+    tb = torch.randn(6, 1536, generator=g).to(dev)
+    tt = torch.randn(6, 1536, generator=g).to(dev)
+    oo = torch.empty_like(tb)
+    nv.add_rows(tb, tt, oo)
+    report("add_rows", oo, tb + tt, 1e-6)
+    nv.add_rows(tb[:2].contiguous(), tt[:1].contiguous(), oo[:2])
+    report("add_rows bcast", oo[:2], tb[:2] + tt[:1], 1e-6)
+
+
+def sec_perf_gemm():
+    g = torch.Generator(device="cpu").manual_seed(5)
+    L = 32760
+    for (M, N, K, name) in [(L, 4608, 1536, "qkv"), (L, 1536, 1536, "o"), (L, 8960, 1536, "ffn1"),
+                            (L, 1536, 8960, "ffn2"), (8192, 8192, 8192, "square8k")]:
+        a = torch.randn(M, K, generator=g).to(dev, torch.bfloat16)
+        w = (torch.randn(N, K, generator=g) * 0.02).to(dev, torch.bfloat16)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ms = time_ms(lambda: nv.gemm(a, w, out))
+        tf = 2.0 * M * N * K / ms / 1e9
+        ms_t = time_ms(lambda: torch.matmul(a, w.t()))
+        print(f"[PERF] gemm {name} M={M} N={N} K={K}: {ms:.3f} ms = {tf:.1f} TFLOP/s | cuBLAS {ms_t:.3f} ms = {2.0*M*N*K/ms_t/1e9:.1f}", flush=True)
+
+
+def sec_perf_attn():
+    g = torch.Generator(device="cpu").manual_seed(6)
+    scale = 128 ** -0.5
+    for (L, H) in [(8192, 12), (32760, 12)]:
+        q = torch.randn(L, H * 128, generator=g).to(dev, torch.bfloat16)
+        k = torch.randn(L, H * 128, generator=g).to(dev, torch.bfloat16)
+        v = torch.randn(L, H * 128, generator=g).to(dev, torch.bfloat16)
+        out = torch.empty(L, H * 128, device=dev, dtype=torch.bfloat16)
+        ms = time_ms(lambda: nv.attention(q, k, v, out, H, scale), iters=5, warm=2)
+        fl = 4.0 * L * L * H * 128
+        print(f"[PERF] attn L={L} H={H}: {ms:.3f} ms = {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+        try:
+            from flash_attn import flash_attn_func
+            q4, k4, v4 = (t.view(1, L, H, 128) for t in (q, k, v))
+            ms2 = time_ms(lambda: flash_attn_func(q4, k4, v4), iters=5, warm=2)
+            print(f"[PERF]   flash_attn2 (library, mma.sync) {ms2:.3f} ms = {fl/ms2/1e9:.1f} TFLOP/s", flush=True)
+        except Exception as ex:  # noqa: BLE001
+            print("[PERF]   flash_attn2 unavailable:", repr(ex)[:100])
+    # cross attention shape
+    L, H = 32760, 12
+    q = torch.randn(L, H * 128, generator=g).to(dev, torch.bfloat16)
+    k = torch.randn(512, H * 128, generator=g).to(dev, torch.bfloat16)
+    v = torch.randn(512, H * 128, generator=g).to(dev, torch.bfloat16)
+    out = torch.empty(L, H * 128, device=dev, dtype=torch.bfloat16)
+    ms = time_ms(lambda: nv.attention(q, k, v, out, H, scale))
+    print(f"[PERF] cross attn L={L} Lk=512: {ms:.3f} ms = {4.0*L*512*H*128/ms/1e9:.1f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__":
+    print("device:", torch.cuda.get_device_name(0), "SMs:", nv.sm_count(), flush=True)
+    for sec in sys.argv[1:]:
+        print(f"=== {sec} ===", flush=True)
+        t0 = time.time()
+        globals()["sec_" + sec]()
+        torch.cuda.synchronize()
+        print(f"=== {sec} done in {time.time()-t0:.1f}s ===", flush=True)

@@ -1,0 +1,117 @@
+"""Deterministic synthetic weights / inputs shared by the golden generator, the tests, smoke() and bench.py.
+
+No checkpoints exist in the build or GPU containers, so every parity and benchmark run uses random-init
+weights of the real architecture.  Generation is pure CPU torch.Generator arithmetic (identical on the build
+box and the GPU box); keys and shapes follow the reference's WanModel parameter names
+(reference diffsynth/models/wan_video_dit.py:408-452).
+"""
+import math
+
+import torch
+
+# tiny configs for goldens / fast tests (head_dim is always 128 like the real models)
+CFG_TINY_T2V = dict(has_image_input=False, patch_size=(1, 2, 2), in_dim=16, dim=256, ffn_dim=512,
+                    freq_dim=64, text_dim=96, out_dim=16, num_heads=2, num_layers=2, eps=1e-6)
+CFG_TINY_I2V = dict(has_image_input=True, patch_size=(1, 2, 2), in_dim=36, dim=256, ffn_dim=512,
+                    freq_dim=64, text_dim=96, out_dim=16, num_heads=2, num_layers=2, eps=1e-6)
+CFG_T2V_1_3B = dict(has_image_input=False, patch_size=(1, 2, 2), in_dim=16, dim=1536, ffn_dim=8960,
+                    freq_dim=256, text_dim=4096, out_dim=16, num_heads=12, num_layers=30, eps=1e-6)
+CFG_I2V_14B = dict(has_image_input=True, patch_size=(1, 2, 2), in_dim=36, dim=5120, ffn_dim=13824,
+                   freq_dim=256, text_dim=4096, out_dim=16, num_heads=40, num_layers=40, eps=1e-6)
+
+
+def dit_param_shapes(cfg):
+    d, ffn, L = cfg["dim"], cfg["ffn_dim"], cfg["num_layers"]
+    sh = {}
+
+    def lin(name, o, i):
+        sh[name + ".weight"] = (o, i)
+        sh[name + ".bias"] = (o,)
+
+    sh["patch_embedding.weight"] = (d, cfg["in_dim"], *cfg["patch_size"])
+    sh["patch_embedding.bias"] = (d,)
+    lin("text_embedding.0", d, cfg["text_dim"])
+    lin("text_embedding.2", d, d)
+    lin("time_embedding.0", d, cfg["freq_dim"])
+    lin("time_embedding.2", d, d)
+    lin("time_projection.1", 6 * d, d)
+    for i in range(L):
+        p = f"blocks.{i}"
+        for att in ("self_attn", "cross_attn"):
+            for n in "qkvo":
+                lin(f"{p}.{att}.{n}", d, d)
+            sh[f"{p}.{att}.norm_q.weight"] = (d,)
+            sh[f"{p}.{att}.norm_k.weight"] = (d,)
+        if cfg["has_image_input"]:
+            lin(f"{p}.cross_attn.k_img", d, d)
+            lin(f"{p}.cross_attn.v_img", d, d)
+            sh[f"{p}.cross_attn.norm_k_img.weight"] = (d,)
+        sh[f"{p}.norm3.weight"] = (d,)
+        sh[f"{p}.norm3.bias"] = (d,)
+        lin(f"{p}.ffn.0", ffn, d)
+        lin(f"{p}.ffn.2", d, ffn)
+        sh[f"{p}.modulation"] = (1, 6, d)
+    lin("head.head", cfg["out_dim"] * math.prod(cfg["patch_size"]), d)
+    sh["head.modulation"] = (1, 2, d)
+    if cfg["has_image_input"]:
+        sh["img_emb.proj.0.weight"] = (1280,)
+        sh["img_emb.proj.0.bias"] = (1280,)
+        lin("img_emb.proj.1", 1280, 1280)
+        lin("img_emb.proj.3", d, 1280)
+        sh["img_emb.proj.4.weight"] = (d,)
+        sh["img_emb.proj.4.bias"] = (d,)
+    return sh
+
+
+def make_dit_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
+    """Seeded random-init state dict.  Matrices ~ N(0, 1/fan_in), norm weights ~ 1 + 0.1 N, biases ~ 0.02 N,
+    modulation ~ N(0,1)/sqrt(dim) (as wan_video_dit.py:336,399).  Per-tensor generators keyed by name order so
+    that a subset (e.g. fewer layers) is reproducible."""
+    sd = {}
+    for idx, (name, shape) in enumerate(dit_param_shapes(cfg).items()):
+        g = torch.Generator(device="cpu").manual_seed(seed * 1000003 + idx)
+        if name.endswith("modulation"):
+            t = torch.randn(shape, generator=g) / cfg["dim"] ** 0.5
+        elif "norm" in name and name.endswith(".weight") or name in ("img_emb.proj.0.weight", "img_emb.proj.4.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        else:
+            fan_in = math.prod(shape[1:])
+            t = torch.randn(shape, generator=g) / math.sqrt(fan_in)
+        sd[name] = t.to(device=device, dtype=dtype)
+    return sd
+
+
+def make_dit_state_dict_fast(cfg, seed=0, device="cuda", dtype=torch.bfloat16):
+    """Same distribution as make_dit_state_dict but generated on `device` (for 1.3B / 14B benchmark models,
+    where CPU generation + upload would take minutes).  NOT bit-identical to the CPU version."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    for name, shape in dit_param_shapes(cfg).items():
+        if name.endswith("modulation"):
+            t = torch.randn(shape, generator=g, device=device) / cfg["dim"] ** 0.5
+        elif "norm" in name and name.endswith(".weight") or name in ("img_emb.proj.0.weight", "img_emb.proj.4.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
+        elif name.endswith(".bias"):
+            t = 0.02 * torch.randn(shape, generator=g, device=device)
+        else:
+            t = torch.randn(shape, generator=g, device=device) / math.sqrt(math.prod(shape[1:]))
+        sd[name] = t.to(dtype)
+    return sd
+
+
+def make_dit_inputs(cfg, f, h, w, seed=0, ctx_len=512, zero_ctx_after=None):
+    """Seeded latents [1,16,f,h,w], context [1,ctx_len,text_dim], and (I2V) y [1,20,f,h,w] with the SVI mask
+    pattern (svi_video.py:319-326) + clip_feature [1,257,1280].  h, w are LATENT sizes (even)."""
+    g = torch.Generator(device="cpu").manual_seed(1234 + seed)
+    out = {"x": torch.randn(1, 16, f, h, w, generator=g),
+           "context": torch.randn(1, ctx_len, cfg["text_dim"], generator=g)}
+    if zero_ctx_after is not None:  # real umT5 embeddings are zero-filled past the prompt (wan_prompter.py:107-108)
+        out["context"][:, zero_ctx_after:] = 0
+    if cfg["has_image_input"]:
+        msk = torch.zeros(1, 4, f, h, w)
+        msk[:, :, 0] = 1
+        out["y"] = torch.cat([msk, torch.randn(1, 16, f, h, w, generator=g)], dim=1)
+        out["clip_feature"] = torch.randn(1, 257, 1280, generator=g)
+    return out
