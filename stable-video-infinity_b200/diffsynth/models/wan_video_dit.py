@@ -1,0 +1,544 @@
+"""Wan DiT — host side of the B200-native hot path.
+
+Same module/parameter names as the reference (``diffsynth/models/wan_video_dit.py``: ``WanModel`` :407-567,
+``DiTBlock`` :321-374, ``SelfAttention`` :210-242, ``CrossAttention`` :245-303, ``Head`` :392-404,
+``RMSNorm`` :186-197) so that Wan checkpoints and SVI LoRA keys load unchanged, but the nn.Modules are only
+PARAMETER CONTAINERS: all arithmetic runs in ``WanDiTEngine`` which drives the hand-written sm_100a kernels
+of ``libsvi_b200.so`` through ``diffsynth._native`` (C ABI, ``include/svi_b200.h``).  There is no torch
+compute fallback: without a CUDA device + the built library every forward raises.
+
+Numerics policy (SURVEY.md §7 hard part 1): bf16 GEMM/attention operands, fp32 accumulation, fp32 residual
+stream / norms / softmax / modulation; RoPE in fp32 with an fp64-built (cos, sin) table.
+"""
+import math
+from collections import OrderedDict
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _native as nv
+
+HEAD_DIM = 128
+
+
+def sinusoidal_embedding_1d(dim, position):
+    """Reference wan_video_dit.py:154-158 (fp64 on the host: `position` holds one scalar per batch row)."""
+    pos = position.detach().to("cpu", torch.float64).reshape(-1)
+    inv = torch.pow(10000.0, -torch.arange(dim // 2, dtype=torch.float64) / (dim // 2))
+    ang = torch.outer(pos, inv)
+    return torch.cat([ang.cos(), ang.sin()], dim=1).to(position.dtype if position.is_floating_point() else torch.float32)
+
+
+def precompute_freqs_cis(dim: int, end: int = 1024, theta: float = 10000.0):
+    """Reference wan_video_dit.py:169-175 (complex128 table)."""
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].double() / dim))
+    ang = torch.outer(torch.arange(end, dtype=torch.float64), freqs)
+    return torch.polar(torch.ones_like(ang), ang)
+
+
+def precompute_freqs_cis_3d(dim: int, end: int = 1024, theta: float = 10000.0):
+    """Reference wan_video_dit.py:161-166: (frame | height | width) tables for head_dim `dim`."""
+    return (precompute_freqs_cis(dim - 2 * (dim // 3), end, theta), precompute_freqs_cis(dim // 3, end, theta),
+            precompute_freqs_cis(dim // 3, end, theta))
+
+
+def rope_table(freqs, f, h, w, device):
+    """(cos, sin) f32 [f*h*w, head_dim/2] from the complex tables (svi_video.py:106-110), built in fp64."""
+    fr = torch.cat([freqs[0][:f].view(f, 1, 1, -1).expand(f, h, w, -1),
+                    freqs[1][:h].view(1, h, 1, -1).expand(f, h, w, -1),
+                    freqs[2][:w].view(1, 1, w, -1).expand(f, h, w, -1)], dim=-1).reshape(f * h * w, -1)
+    return (fr.real.to(torch.float32).contiguous().to(device), fr.imag.to(torch.float32).contiguous().to(device))
+
+
+class RMSNorm(nn.Module):
+    """Parameter container for the full-width q/k RMSNorm (reference :186-197); applied by svi_rmsnorm_rope."""
+
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class SelfAttention(nn.Module):
+    def __init__(self, dim: int, num_heads: int, eps: float = 1e-6):
+        super().__init__()
+        self.dim, self.num_heads, self.head_dim = dim, num_heads, dim // num_heads
+        self.q, self.k, self.v, self.o = (nn.Linear(dim, dim) for _ in range(4))
+        self.norm_q = RMSNorm(dim, eps=eps)
+        self.norm_k = RMSNorm(dim, eps=eps)
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, dim: int, num_heads: int, eps: float = 1e-6, has_image_input: bool = False):
+        super().__init__()
+        self.dim, self.num_heads, self.head_dim = dim, num_heads, dim // num_heads
+        self.q, self.k, self.v, self.o = (nn.Linear(dim, dim) for _ in range(4))
+        self.norm_q = RMSNorm(dim, eps=eps)
+        self.norm_k = RMSNorm(dim, eps=eps)
+        self.has_image_input = has_image_input
+        if has_image_input:
+            self.k_img = nn.Linear(dim, dim)
+            self.v_img = nn.Linear(dim, dim)
+            self.norm_k_img = RMSNorm(dim, eps=eps)
+
+
+class DiTBlock(nn.Module):
+    def __init__(self, has_image_input: bool, dim: int, num_heads: int, ffn_dim: int, eps: float = 1e-6,
+                 enable_multitalk: bool = False):
+        super().__init__()
+        if enable_multitalk:
+            raise NotImplementedError("SVI-Talk audio cross-attention is outside the hot-path scope (SURVEY.md §8f)")
+        self.dim, self.num_heads, self.ffn_dim = dim, num_heads, ffn_dim
+        self.self_attn = SelfAttention(dim, num_heads, eps)
+        self.cross_attn = CrossAttention(dim, num_heads, eps, has_image_input=has_image_input)
+        self.norm1 = nn.LayerNorm(dim, eps=eps, elementwise_affine=False)
+        self.norm2 = nn.LayerNorm(dim, eps=eps, elementwise_affine=False)
+        self.norm3 = nn.LayerNorm(dim, eps=eps)
+        self.ffn = nn.Sequential(nn.Linear(dim, ffn_dim), nn.GELU(approximate="tanh"), nn.Linear(ffn_dim, dim))
+        self.modulation = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
+
+
+class MLP(nn.Module):
+    """CLIP-feature projector (reference :377-389)."""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.proj = nn.Sequential(nn.LayerNorm(in_dim), nn.Linear(in_dim, in_dim), nn.GELU(),
+                                  nn.Linear(in_dim, out_dim), nn.LayerNorm(out_dim))
+
+
+class Head(nn.Module):
+    def __init__(self, dim: int, out_dim: int, patch_size: Tuple[int, int, int], eps: float):
+        super().__init__()
+        self.dim, self.patch_size = dim, patch_size
+        self.norm = nn.LayerNorm(dim, eps=eps, elementwise_affine=False)
+        self.head = nn.Linear(dim, out_dim * math.prod(patch_size))
+        self.modulation = nn.Parameter(torch.randn(1, 2, dim) / dim ** 0.5)
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _bf16(t, device):
+    return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+
+class _BlockWeights:
+    """Kernel-ready copies of one DiTBlock's parameters (fused QKV / KV weights, fp32 vectors)."""
+
+    def __init__(self, blk: DiTBlock, device):
+        sa, ca = blk.self_attn, blk.cross_attn
+        self.w_qkv = _bf16(torch.cat([sa.q.weight, sa.k.weight, sa.v.weight], 0), device)
+        self.b_qkv = _f32(torch.cat([sa.q.bias, sa.k.bias, sa.v.bias], 0), device)
+        self.w_q, self.b_q = self.w_qkv[: blk.dim], self.b_qkv[: blk.dim]          # views (sequence-parallel split)
+        self.w_kv, self.b_kv = self.w_qkv[blk.dim:], self.b_qkv[blk.dim:]
+        self.w_o, self.b_o = _bf16(sa.o.weight, device), _f32(sa.o.bias, device)
+        self.nq, self.nk = _f32(sa.norm_q.weight, device), _f32(sa.norm_k.weight, device)
+        self.eps_qk = sa.norm_q.eps
+        self.w_cq, self.b_cq = _bf16(ca.q.weight, device), _f32(ca.q.bias, device)
+        self.w_ckv = _bf16(torch.cat([ca.k.weight, ca.v.weight], 0), device)
+        self.b_ckv = _f32(torch.cat([ca.k.bias, ca.v.bias], 0), device)
+        self.w_co, self.b_co = _bf16(ca.o.weight, device), _f32(ca.o.bias, device)
+        self.cnq, self.cnk = _f32(ca.norm_q.weight, device), _f32(ca.norm_k.weight, device)
+        if ca.has_image_input:
+            self.w_ckv_img = _bf16(torch.cat([ca.k_img.weight, ca.v_img.weight], 0), device)
+            self.b_ckv_img = _f32(torch.cat([ca.k_img.bias, ca.v_img.bias], 0), device)
+            self.cnk_img = _f32(ca.norm_k_img.weight, device)
+        self.n3w, self.n3b = _f32(blk.norm3.weight, device), _f32(blk.norm3.bias, device)
+        self.eps = blk.norm1.eps
+        self.w_f0, self.b_f0 = _bf16(blk.ffn[0].weight, device), _f32(blk.ffn[0].bias, device)
+        self.w_f2, self.b_f2 = _bf16(blk.ffn[2].weight, device), _f32(blk.ffn[2].bias, device)
+        self.mod = _f32(blk.modulation.reshape(6, blk.dim), device)
+
+
+class ContextState:
+    """Step-invariant conditioning of one prompt: embedded context rows and every layer's cross-attention K/V
+    (reference recomputes text_embedding + K/V projections on every forward, svi_video.py:92, wan_video_dit.py:273-274)."""
+
+    def __init__(self, n_img, n_txt):
+        self.n_img, self.n_txt = n_img, n_txt
+        self.kv_txt = []   # per layer bf16 [n_txt, 2d]  (k normalised | v)
+        self.kv_img = []   # per layer bf16 [257, 2d]
+
+
+class _CountingNative:
+    """Proxy over diffsynth._native that counts kernel launches (bench.py reports them as gpu_launches)."""
+
+    def __init__(self):
+        self.launches = 0
+
+    def __getattr__(self, name):
+        fn = getattr(nv, name)
+
+        def call(*a, **k):
+            self.launches += 1
+            return fn(*a, **k)
+        return call
+
+
+class WanDiTEngine:
+    """Runs WanModel's arithmetic on the native kernels.  One instance per (model, device)."""
+
+    def __init__(self, model: "WanModel", device):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("svi_b200: the Wan DiT runs only on a CUDA device (sm_100a kernels; no CPU fallback)")
+        nv.load()
+        self.device = torch.device(device)
+        self.model = model
+        self.dim, self.H = model.dim, model.num_heads
+        self.sig = model._param_signature()
+        d = self.dim
+        self.blocks = [_BlockWeights(b, self.device) for b in model.blocks]
+        pe = model.patch_embedding
+        self.kpatch = pe.weight.shape[1] * 4
+        self.w_patch = _bf16(pe.weight.reshape(d, self.kpatch), self.device)
+        self.b_patch = _f32(pe.bias, self.device)
+        self.w_te0, self.b_te0 = _bf16(model.text_embedding[0].weight, self.device), _f32(model.text_embedding[0].bias, self.device)
+        self.w_te2, self.b_te2 = _bf16(model.text_embedding[2].weight, self.device), _f32(model.text_embedding[2].bias, self.device)
+        self.w_t0, self.b_t0 = _bf16(model.time_embedding[0].weight, self.device), _f32(model.time_embedding[0].bias, self.device)
+        self.w_t2, self.b_t2 = _bf16(model.time_embedding[2].weight, self.device), _f32(model.time_embedding[2].bias, self.device)
+        self.w_tp, self.b_tp = _bf16(model.time_projection[1].weight, self.device), _f32(model.time_projection[1].bias, self.device)
+        self.w_head, self.b_head = _bf16(model.head.head.weight, self.device), _f32(model.head.head.bias, self.device)
+        self.head_mod = _f32(model.head.modulation.reshape(2, d), self.device)
+        self.eps = model.head.norm.eps
+        if model.has_image_input:
+            p = model.img_emb.proj
+            self.ie_ln0 = (_f32(p[0].weight, self.device), _f32(p[0].bias, self.device), p[0].eps)
+            self.ie_w1, self.ie_b1 = _bf16(p[1].weight, self.device), _f32(p[1].bias, self.device)
+            self.ie_w3, self.ie_b3 = _bf16(p[3].weight, self.device), _f32(p[3].bias, self.device)
+            self.ie_ln4 = (_f32(p[4].weight, self.device), _f32(p[4].bias, self.device), p[4].eps)
+        self._rope = {}
+        self._ws = {}
+        self._ctx_cache = OrderedDict()
+        self._time_cache = OrderedDict()
+        self.k = _CountingNative()  # every native launch goes through this proxy (bench.py reads the count)
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(shape, device=self.device, dtype=dtype)
+            self._ws[key] = t
+        return t
+
+    def _gemm(self, *a, **k):
+        return self.k.gemm(*a, **k)
+
+    def rope(self, f, h, w):
+        key = (f, h, w)
+        if key not in self._rope:
+            self._rope[key] = rope_table(self.model.freqs, f, h, w, self.device)
+        return self._rope[key]
+
+    # ------------------------------------------------------------------ conditioning
+    def time_state(self, timestep):
+        """t f32 [1,d] and t_mod f32 [6,d] for a scalar timestep (svi_video.py:90-91)."""
+        tv = float(timestep.reshape(-1)[0]) if isinstance(timestep, torch.Tensor) else float(timestep)
+        hit = self._time_cache.get(tv)
+        if hit is not None:
+            return hit
+        d = self.dim
+        te = sinusoidal_embedding_1d(self.model.freq_dim, torch.tensor([tv], dtype=torch.float64))
+        te = te.to(torch.bfloat16).to(self.device)
+        th = torch.empty(1, d, device=self.device, dtype=torch.bfloat16)
+        t = torch.empty(1, d, device=self.device, dtype=torch.float32)
+        ts = torch.empty(1, d, device=self.device, dtype=torch.bfloat16)
+        t_mod = torch.empty(1, 6 * d, device=self.device, dtype=torch.float32)
+        self.k.gemm(te, self.w_t0, th, bias=self.b_t0, act=nv.ACT_SILU)
+        self.k.gemm(th, self.w_t2, t, bias=self.b_t2)
+        self.k.cast_f32_to_bf16(t, ts, act=nv.ACT_SILU)
+        self.k.gemm(ts, self.w_tp, t_mod, bias=self.b_tp)
+        out = (t, t_mod.view(6, d))
+        self._time_cache[tv] = out
+        while len(self._time_cache) > 256:
+            self._time_cache.popitem(last=False)
+        return out
+
+    def context_state(self, context, clip_feature=None) -> ContextState:
+        """Embed the prompt (and CLIP) tokens and project every layer's cross-attention K/V once."""
+        key = (context.data_ptr(), context._version, tuple(context.shape),
+               None if clip_feature is None else (clip_feature.data_ptr(), clip_feature._version))
+        hit = self._ctx_cache.get(key)
+        if hit is not None:
+            self._ctx_cache.move_to_end(key)
+            return hit
+        d, dev = self.dim, self.device
+        ctx_in = context.reshape(-1, context.shape[-1])
+        n_txt = ctx_in.shape[0]
+        if ctx_in.dtype != torch.bfloat16:
+            src = ctx_in.to(device=dev, dtype=torch.float32).contiguous()
+            ctx_bf = torch.empty(src.shape, device=dev, dtype=torch.bfloat16)
+            self.k.cast_f32_to_bf16(src, ctx_bf)
+        else:
+            ctx_bf = ctx_in.to(dev).contiguous()
+        n_img = 257 if self.model.has_image_input else 0
+        emb = torch.empty(n_img + n_txt, d, device=dev, dtype=torch.bfloat16)
+        hid = torch.empty(n_txt, d, device=dev, dtype=torch.bfloat16)
+        self.k.gemm(ctx_bf, self.w_te0, hid, bias=self.b_te0, act=nv.ACT_GELU_TANH)
+        self.k.gemm(hid, self.w_te2, emb[n_img:], bias=self.b_te2)
+        if n_img:
+            if clip_feature is None:
+                raise RuntimeError("has_image_input model needs clip_feature")
+            cf = clip_feature.reshape(-1, clip_feature.shape[-1]).to(device=dev, dtype=torch.float32).contiguous()
+            if cf.shape[0] != 257:
+                raise RuntimeError(f"clip_feature must have 257 tokens, got {cf.shape[0]}")
+            c0 = torch.empty(257, 1280, device=dev, dtype=torch.bfloat16)
+            c1 = torch.empty(257, 1280, device=dev, dtype=torch.bfloat16)
+            c2 = torch.empty(257, d, device=dev, dtype=torch.float32)
+            self.k.layernorm_modulate(cf, c0, self.ie_ln0[2], gamma=self.ie_ln0[0], beta=self.ie_ln0[1])
+            self.k.gemm(c0, self.ie_w1, c1, bias=self.ie_b1, act=nv.ACT_GELU_ERF)
+            self.k.gemm(c1, self.ie_w3, c2, bias=self.ie_b3)
+            self.k.layernorm_modulate(c2, emb[:257], self.ie_ln4[2], gamma=self.ie_ln4[0], beta=self.ie_ln4[1])
+        st = ContextState(n_img, n_txt)
+        for bw in self.blocks:
+            kv = torch.empty(n_txt, 2 * d, device=dev, dtype=torch.bfloat16)
+            ss = torch.zeros(n_txt, 1, device=dev, dtype=torch.float32)
+            self.k.gemm(emb[n_img:], bw.w_ckv, kv, bias=bw.b_ckv, sumsq=ss, sumsq_group_cols=d)
+            self.k.rmsnorm_rope(kv[:, :d], ss, 0, bw.eps_qk, bw.cnk)
+            st.kv_txt.append(kv)
+            if n_img:
+                kvi = torch.empty(257, 2 * d, device=dev, dtype=torch.bfloat16)
+                ssi = torch.zeros(257, 1, device=dev, dtype=torch.float32)
+                self.k.gemm(emb[:257], bw.w_ckv_img, kvi, bias=bw.b_ckv_img, sumsq=ssi, sumsq_group_cols=d)
+                self.k.rmsnorm_rope(kvi[:, :d], ssi, 0, bw.eps_qk, bw.cnk_img)
+                st.kv_img.append(kvi)
+        self._ctx_cache[key] = st
+        while len(self._ctx_cache) > 8:
+            self._ctx_cache.popitem(last=False)
+        return st
+
+    # ------------------------------------------------------------------ block stack
+    def run_block(self, i, x, t_mod, ctx: ContextState, cos, sin, sp=None):
+        """x f32 [L,d] updated in place.  Reference DiTBlock.forward wan_video_dit.py:354-374."""
+        bw = self.blocks[i]
+        L, d, H = x.shape[0], self.dim, self.H
+        mod = self._buf("mod6", (6, d), torch.float32)
+        h = self._buf("h", (L, d), torch.bfloat16)
+        qkv = self._buf("qkv", (L, 3 * d), torch.bfloat16)
+        att = self._buf("att", (L, d), torch.bfloat16)
+        ss = self._buf("ss", (L, 2), torch.float32)
+        ffn = self._buf("ffn", (L, bw.w_f0.shape[0]), torch.bfloat16)
+        self.k.add_rows(bw.mod, t_mod, mod)
+        # --- self attention
+        self.k.layernorm_modulate(x, h, bw.eps, scale=mod[1], shift=mod[0])
+        ss.zero_()
+        self.k.gemm(h, bw.w_qkv, qkv, bias=bw.b_qkv, sumsq=ss, sumsq_group_cols=d)
+        row0 = 0 if sp is None else sp.row_offset
+        self.k.rmsnorm_rope(qkv[:, :d], ss, 0, bw.eps_qk, bw.nq, cos, sin, row0)
+        self.k.rmsnorm_rope(qkv[:, d:2 * d], ss, 1, bw.eps_qk, bw.nk, cos, sin, row0)
+        if sp is None:
+            self.k.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, H)
+        else:
+            kv_full = sp.all_gather_kv(qkv[:, d:])
+            self.k.attention(qkv[:, :d], kv_full[:, :d], kv_full[:, d:], att, H)
+        self.k.gemm(att, bw.w_o, x, bias=bw.b_o, gate=mod[2], residual=x)
+        # --- cross attention
+        self.k.layernorm_modulate(x, h, bw.eps, gamma=bw.n3w, beta=bw.n3b)
+        cq = qkv[:, :d]
+        ss1 = self._buf("ss1", (L, 1), torch.float32)
+        ss1.zero_()
+        self.k.gemm(h, bw.w_cq, cq, bias=bw.b_cq, sumsq=ss1, sumsq_group_cols=d)
+        self.k.rmsnorm_rope(cq, ss1, 0, bw.eps_qk, bw.cnq)
+        kv = ctx.kv_txt[i]
+        self.k.attention(cq, kv[:, :d], kv[:, d:], att, H)
+        if ctx.n_img:
+            kvi = ctx.kv_img[i]
+            self.k.attention(cq, kvi[:, :d], kvi[:, d:], att, H, accumulate=True)
+        self.k.gemm(att, bw.w_co, x, bias=bw.b_co, residual=x)
+        # --- FFN
+        self.k.layernorm_modulate(x, h, bw.eps, scale=mod[4], shift=mod[3])
+        self.k.gemm(h, bw.w_f0, ffn, bias=bw.b_f0, act=nv.ACT_GELU_TANH)
+        self.k.gemm(ffn, bw.w_f2, x, bias=bw.b_f2, gate=mod[5], residual=x)
+        return x
+
+    def forward(self, x, timestep, context, clip_feature=None, y=None, sp=None, out=None):
+        """One DiT forward (svi_video.py:74-137).  x [1,C,f,Hl,Wl] (any float dtype, CUDA) -> f32 [1,16,f,Hl,Wl].
+
+        `context` may be a tensor [1,Lc,text_dim] or a ContextState from context_state()."""
+        dev, d = self.device, self.dim
+        if x.dim() != 5 or x.shape[0] != 1:
+            raise RuntimeError(f"svi_b200: DiT forward expects x of shape [1,C,f,h,w], got {tuple(x.shape)}")
+        xs = x[0].to(device=dev, dtype=torch.float32).contiguous()
+        ys = None
+        if self.model.has_image_input:
+            if y is None:
+                raise RuntimeError("has_image_input model needs y")
+            ys = y[0].to(device=dev, dtype=torch.float32).contiguous()
+        C0, f, Hl, Wl = xs.shape
+        if (C0 + (0 if ys is None else ys.shape[0])) * 4 != self.kpatch:
+            raise RuntimeError("svi_b200: channel count does not match patch_embedding")
+        hh, ww = Hl // 2, Wl // 2
+        L = f * hh * ww
+        t, t_mod = self.time_state(timestep)
+        ctx = context if isinstance(context, ContextState) else self.context_state(context, clip_feature)
+        cos, sin = self.rope(f, hh, ww)
+        # patchify: im2col gather + GEMM (Conv3d k=s=(1,2,2), wan_video_dit.py:473-477)
+        tok = self._buf("tok", (L, self.kpatch), torch.bfloat16)
+        self.k.patchify_gather(xs, ys, tok)
+        if sp is None:
+            Ll, tok_l = L, tok
+        else:
+            Ll, tok_l = sp.local_rows(L), tok[sp.row_offset: sp.row_offset + sp.local_rows(L)]
+        xr = self._buf("x", (Ll, d), torch.float32)
+        self.k.gemm(tok_l, self.w_patch, xr, bias=self.b_patch)
+        for i in range(len(self.blocks)):
+            self.run_block(i, xr, t_mod, ctx, cos, sin, sp)
+        # head (wan_video_dit.py:401-404) + unpatchify (:479-484)
+        mod2 = self._buf("mod2", (2, d), torch.float32)
+        self.k.add_rows(self.head_mod, t, mod2)
+        h = self._buf("h", (Ll, d), torch.bfloat16)
+        self.k.layernorm_modulate(xr, h, self.eps, scale=mod2[1], shift=mod2[0])
+        nh = self.w_head.shape[0]
+        ho = self._buf("head_out", (L, nh), torch.float32)
+        ho_l = ho if sp is None else ho[sp.row_offset: sp.row_offset + Ll]
+        self.k.gemm(h, self.w_head, ho_l, bias=self.b_head)
+        if sp is not None:
+            sp.all_gather_rows(ho)
+        if out is None:
+            out = torch.empty(1, nh // 4, f, Hl, Wl, device=dev, dtype=torch.float32)
+        self.k.unpatchify(ho, out[0])
+        return out
+
+
+
+class WanModel(nn.Module):
+    """Reference wan_video_dit.py:407-567 — same constructor, parameter names and public attributes."""
+
+    def __init__(self, dim: int, in_dim: int, ffn_dim: int, out_dim: int, text_dim: int, freq_dim: int, eps: float,
+                 patch_size: Tuple[int, int, int], num_heads: int, num_layers: int, has_image_input: bool,
+                 enable_multitalk: bool = False):
+        super().__init__()
+        if dim // num_heads != HEAD_DIM or dim % num_heads:
+            raise ValueError(f"svi_b200 kernels are specialised for head_dim 128 (got dim={dim}, heads={num_heads})")
+        if tuple(patch_size) != (1, 2, 2):
+            raise ValueError("svi_b200 kernels are specialised for patch_size (1,2,2)")
+        self.dim, self.freq_dim, self.has_image_input = dim, freq_dim, has_image_input
+        self.patch_size, self.num_heads, self.out_dim, self.eps = tuple(patch_size), num_heads, out_dim, eps
+        self.patch_embedding = nn.Conv3d(in_dim, dim, kernel_size=self.patch_size, stride=self.patch_size)
+        self.text_embedding = nn.Sequential(nn.Linear(text_dim, dim), nn.GELU(approximate="tanh"), nn.Linear(dim, dim))
+        self.time_embedding = nn.Sequential(nn.Linear(freq_dim, dim), nn.SiLU(), nn.Linear(dim, dim))
+        self.time_projection = nn.Sequential(nn.SiLU(), nn.Linear(dim, dim * 6))
+        self.blocks = nn.ModuleList([DiTBlock(has_image_input, dim, num_heads, ffn_dim, eps, enable_multitalk)
+                                     for _ in range(num_layers)])
+        self.head = Head(dim, out_dim, self.patch_size, eps)
+        self.freqs = precompute_freqs_cis_3d(dim // num_heads)
+        if has_image_input:
+            self.img_emb = MLP(1280, dim)
+        self.enable_multitalk = enable_multitalk
+        self._engine: Optional[WanDiTEngine] = None
+
+    # -- engine management -------------------------------------------------------------------
+    def _param_signature(self):
+        """Cheap staleness stamp: parameter storage pointers + in-place version counters."""
+        s = 0
+        for p in self.parameters():
+            s = (s * 1000003 + p.data_ptr() + 7919 * p._version) % (1 << 61)
+        return s
+
+    def engine(self, device=None) -> WanDiTEngine:
+        if device is None:
+            device = next(self.parameters()).device
+            if device.type != "cuda":
+                device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else device
+        device = torch.device(device)
+        eng = self._engine
+        if eng is None or eng.device != device or eng.sig != self._param_signature():
+            launches = 0 if eng is None else eng.k.launches
+            eng = WanDiTEngine(self, device)
+            eng.k.launches = launches
+            self._engine = eng
+        return eng
+
+    def invalidate_engine(self):
+        self._engine = None
+
+    # -- reference surface ---------------------------------------------------------------------
+    def patchify(self, x: torch.Tensor):
+        """'b c f h w -> b (f h w) c' tokens after the patch embedding (f32)."""
+        eng = self.engine(x.device if x.is_cuda else None)
+        xs = x[0].to(device=eng.device, dtype=torch.float32).contiguous()
+        C, f, H, W = xs.shape
+        tok = torch.empty(f * (H // 2) * (W // 2), eng.kpatch, device=eng.device, dtype=torch.bfloat16)
+        nv.patchify_gather(xs, None, tok)
+        out = torch.empty(tok.shape[0], self.dim, device=eng.device, dtype=torch.float32)
+        nv.gemm(tok, eng.w_patch, out, bias=eng.b_patch)
+        return out.unsqueeze(0), (f, H // 2, W // 2)
+
+    def unpatchify(self, x: torch.Tensor, grid_size):
+        f, h, w = (int(v) for v in grid_size)
+        eng = self.engine(x.device if x.is_cuda else None)
+        ho = x[0].to(device=eng.device, dtype=torch.float32).contiguous()
+        out = torch.empty(1, ho.shape[1] // 4, f, 2 * h, 2 * w, device=eng.device, dtype=torch.float32)
+        nv.unpatchify(ho, out[0])
+        return out
+
+    def forward(self, x, timestep, context, clip_feature=None, y=None, **kwargs):
+        if kwargs.get("add_condition") is not None or kwargs.get("audio_embed_tuple") is not None:
+            raise NotImplementedError("pose / audio conditioning is outside the hot-path scope (SURVEY.md §8f)")
+        dev = x.device if x.is_cuda else None
+        out = self.engine(dev).forward(x, timestep, context, clip_feature, y)
+        return out.to(x.dtype) if x.is_floating_point() else out
+
+    @staticmethod
+    def state_dict_converter():
+        return WanModelStateDictConverter()
+
+
+# checkpoint key-set hash -> constructor config (reference wan_video_dit.py:656-714).  NOTE the reference's
+# 1.3B branch is shadowed by the following if/elif chain and ends up with `{}` (SURVEY.md headline 7); that
+# is a reference bug, not behaviour to preserve: here the 1.3B hash resolves to its config.
+_CIVITAI_CONFIGS = {
+    "9269f8db9040a9d860eaca435be61814": dict(has_image_input=False, patch_size=[1, 2, 2], in_dim=16, dim=1536,
+                                             ffn_dim=8960, freq_dim=256, text_dim=4096, out_dim=16, num_heads=12,
+                                             num_layers=30, eps=1e-6),
+    "aafcfd9672c3a2456dc46e1cb6e52c70": dict(has_image_input=False, patch_size=[1, 2, 2], in_dim=16, dim=5120,
+                                             ffn_dim=13824, freq_dim=256, text_dim=4096, out_dim=16, num_heads=40,
+                                             num_layers=40, eps=1e-6),
+    "6bfcfb3b342cb286ce886889d519a77e": dict(has_image_input=True, patch_size=[1, 2, 2], in_dim=36, dim=5120,
+                                             ffn_dim=13824, freq_dim=256, text_dim=4096, out_dim=16, num_heads=40,
+                                             num_layers=40, eps=1e-6),
+}
+
+
+class WanModelStateDictConverter:
+    def from_civitai(self, state_dict):
+        from .utils import hash_state_dict_keys
+        return state_dict, dict(_CIVITAI_CONFIGS.get(hash_state_dict_keys(state_dict), {}))
+
+    def from_diffusers(self, state_dict):
+        """diffusers-format Wan checkpoints (reference :578-655): key renaming only."""
+        ren = {"attn1.norm_k": "self_attn.norm_k", "attn1.norm_q": "self_attn.norm_q", "attn1.to_k": "self_attn.k",
+               "attn1.to_out.0": "self_attn.o", "attn1.to_q": "self_attn.q", "attn1.to_v": "self_attn.v",
+               "attn2.norm_k": "cross_attn.norm_k", "attn2.norm_q": "cross_attn.norm_q", "attn2.to_k": "cross_attn.k",
+               "attn2.to_out.0": "cross_attn.o", "attn2.to_q": "cross_attn.q", "attn2.to_v": "cross_attn.v",
+               "ffn.net.0.proj": "ffn.0", "ffn.net.2": "ffn.2", "norm2": "norm3", "scale_shift_table": "modulation"}
+        top = {"condition_embedder.text_embedder.linear_1": "text_embedding.0",
+               "condition_embedder.text_embedder.linear_2": "text_embedding.2",
+               "condition_embedder.time_embedder.linear_1": "time_embedding.0",
+               "condition_embedder.time_embedder.linear_2": "time_embedding.2",
+               "condition_embedder.time_proj": "time_projection.1", "patch_embedding": "patch_embedding",
+               "proj_out": "head.head"}
+        out = {}
+        for name, p in state_dict.items():
+            if name == "scale_shift_table":
+                out["head.modulation"] = p
+                continue
+            if name.startswith("blocks."):
+                _, idx, rest = name.split(".", 2)
+                for a, b in ren.items():
+                    if rest == a or rest.startswith(a + "."):
+                        out[f"blocks.{idx}.{b}{rest[len(a):]}"] = p
+                        break
+                continue
+            for a, b in top.items():
+                if name.startswith(a + "."):
+                    out[b + name[len(a):]] = p
+                    break
+        cfg = {}
+        if any(k.startswith("blocks.39.") for k in out) and out.get("patch_embedding.weight") is not None \
+                and out["patch_embedding.weight"].shape[1] == 16:
+            cfg = dict(_CIVITAI_CONFIGS["aafcfd9672c3a2456dc46e1cb6e52c70"])
+        return out, cfg
