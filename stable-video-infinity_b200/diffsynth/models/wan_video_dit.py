@@ -213,6 +213,7 @@ class WanDiTEngine:
         self._ws = {}
         self._ctx_cache = OrderedDict()
         self._time_cache = OrderedDict()
+        self.attn_events = None  # bench.py: list collecting (start, end) events around self-attention launches
         self.k = _CountingNative()  # every native launch goes through this proxy (bench.py reads the count)
 
     # ------------------------------------------------------------------ helpers
@@ -324,16 +325,37 @@ class WanDiTEngine:
         self.k.add_rows(bw.mod, t_mod, mod)
         # --- self attention
         self.k.layernorm_modulate(x, h, bw.eps, scale=mod[1], shift=mod[0])
-        ss.zero_()
-        self.k.gemm(h, bw.w_qkv, qkv, bias=bw.b_qkv, sumsq=ss, sumsq_group_cols=d)
-        row0 = 0 if sp is None else sp.row_offset
-        self.k.rmsnorm_rope(qkv[:, :d], ss, 0, bw.eps_qk, bw.nq, cos, sin, row0)
-        self.k.rmsnorm_rope(qkv[:, d:2 * d], ss, 1, bw.eps_qk, bw.nk, cos, sin, row0)
+        ev = self.attn_events
         if sp is None:
-            self.k.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, H)
+            ss.zero_()
+            self.k.gemm(h, bw.w_qkv, qkv, bias=bw.b_qkv, sumsq=ss, sumsq_group_cols=d)
+            self.k.rmsnorm_rope(qkv[:, :d], ss, 0, bw.eps_qk, bw.nq, cos, sin, 0)
+            self.k.rmsnorm_rope(qkv[:, d:2 * d], ss, 1, bw.eps_qk, bw.nk, cos, sin, 0)
+            q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
         else:
-            kv_full = sp.all_gather_kv(qkv[:, d:])
-            self.k.attention(qkv[:, :d], kv_full[:, :d], kv_full[:, d:], att, H)
+            # sequence parallel: q for the local rows; K|V written straight into this rank's rows of the full
+            # [L_total, 2d] buffer, normalised + rotated with the rank's row offset, then all-gathered in place
+            q = qkv[:, :d]
+            kvf = self._buf("kv_full", (L * sp.sp_size, 2 * d), torch.bfloat16)
+            kvl = kvf[sp.sp_rank * L:(sp.sp_rank + 1) * L]
+            ssq = self._buf("ssq", (L, 1), torch.float32)
+            ssk = self._buf("ssk", (L, 1), torch.float32)
+            ssq.zero_()
+            ssk.zero_()
+            self.k.gemm(h, bw.w_q, q, bias=bw.b_q, sumsq=ssq, sumsq_group_cols=d)
+            self.k.gemm(h, bw.w_kv, kvl, bias=bw.b_kv, sumsq=ssk, sumsq_group_cols=d)
+            self.k.rmsnorm_rope(q, ssq, 0, bw.eps_qk, bw.nq, cos, sin, sp.sp_rank * L)
+            self.k.rmsnorm_rope(kvl[:, :d], ssk, 0, bw.eps_qk, bw.nk, cos, sin, sp.sp_rank * L)
+            sp.all_gather_rows(kvf)
+            k, v = kvf[:, :d], kvf[:, d:]
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.k.attention(q, k, v, att, H)
+        if ev is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            ev.append((e0, e1))
         self.k.gemm(att, bw.w_o, x, bias=bw.b_o, gate=mod[2], residual=x)
         # --- cross attention
         self.k.layernorm_modulate(x, h, bw.eps, gamma=bw.n3w, beta=bw.n3b)
@@ -381,7 +403,9 @@ class WanDiTEngine:
         if sp is None:
             Ll, tok_l = L, tok
         else:
-            Ll, tok_l = sp.local_rows(L), tok[sp.row_offset: sp.row_offset + sp.local_rows(L)]
+            sp.set_tokens(L)
+            Ll = sp.local_rows(L)
+            tok_l = tok[sp.row_offset: sp.row_offset + Ll]
         xr = self._buf("x", (Ll, d), torch.float32)
         self.k.gemm(tok_l, self.w_patch, xr, bias=self.b_patch)
         for i in range(len(self.blocks)):

@@ -1,0 +1,248 @@
+"""SVIVideoPipeline — one clip of the SVI rolling loop on the B200-native kernels.
+
+Public surface follows the reference (``diffsynth/pipelines/svi_video.py``: ``SVIVideoPipeline`` :140-520,
+``model_fn_wan_video`` :74-137) so ``test_svi.py`` can drive it unchanged.  Differences are internal:
+
+* the 50-step CFG/Euler loop keeps fp32 latents on the device, reuses step-invariant conditioning
+  (embedded prompts and all cross-attention K/V, ``WanDiTEngine.context_state``) and finishes every step with
+  one fused CFG+Euler kernel (reference: 2 sequential forwards + 4 elementwise launches, :392-421);
+* nothing is offloaded or copied through the CPU (reference VAE round trip, wan_video_vae.py:761-786).
+"""
+import types
+from typing import Optional
+
+import numpy as np
+import torch
+from PIL import Image
+from tqdm import tqdm
+
+from .. import _native as nv
+from ..models.wan_video_dit import ContextState, WanModel
+from ..schedulers.flow_match import FlowMatchScheduler
+from .base import BasePipeline
+
+
+class TeaCache:
+    """Step-skipping approximation of the reference (svi_video.py:23-72); OFF by default there and not part of
+    the parity contract.  Kept as an explicit 'next' item."""
+
+    def __init__(self, num_inference_steps, rel_l1_thresh, model_id):
+        raise NotImplementedError("TeaCache is not implemented in the B200 hot path (SURVEY.md §8f.4)")
+
+
+def model_fn_wan_video(dit: WanModel, x: torch.Tensor, timestep: torch.Tensor, context, clip_feature: Optional[torch.Tensor] = None,
+                       y: Optional[torch.Tensor] = None, tea_cache=None, add_condition=None,
+                       use_unified_sequence_parallel: bool = False, **kwargs):
+    """Drop-in for reference svi_video.py:74-137: one DiT forward, result in x.dtype.  `context` may also be
+    a ContextState (pre-projected conditioning)."""
+    if tea_cache is not None:
+        raise NotImplementedError("TeaCache is not implemented in the B200 hot path (SURVEY.md §8f.4)")
+    if add_condition is not None:
+        raise NotImplementedError("pose add_condition (SVI-Dance) is outside the hot-path scope (SURVEY.md §8f.2)")
+    sp = None
+    if use_unified_sequence_parallel:
+        from ..distributed.sequence_parallel import get_sp_group
+        sp = get_sp_group()
+    eng = dit.engine(x.device if x.is_cuda else None)
+    out = eng.forward(x, timestep, context, clip_feature, y, sp=sp)
+    return out.to(x.dtype)
+
+
+class SVIVideoPipeline(BasePipeline):
+    def __init__(self, device="cuda", torch_dtype=torch.float16, tokenizer_path=None, is_test=False, num_train_timesteps=1000):
+        super().__init__(device=device, torch_dtype=torch_dtype)
+        self.scheduler = FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True, num_train_timesteps=num_train_timesteps)
+        self.prompter = None          # callable(prompt, positive=bool) -> [1,512,4096] (umT5 is out of scope, §8f.1)
+        self.text_encoder = None
+        self.image_encoder = None     # object with encode_image([f32 1x3xHxW]) -> [1,257,1280] (CLIP, out of scope)
+        self.dit: WanModel = None
+        self.vae = None
+        self.model_names = ["text_encoder", "dit", "vae"]
+        self.height_division_factor = 16
+        self.width_division_factor = 16
+        self.use_unified_sequence_parallel = False
+        self.is_test = is_test
+
+    # ------------------------------------------------------------------ construction
+    def enable_vram_management(self, num_persistent_param_in_dit=None):
+        """Reference svi_video.py:156-241 wraps every Linear for CPU offload under a 6e9-parameter budget.  On a
+        180 GB B200 the whole 14B model (32 GB bf16) is resident: this is the all-resident policy."""
+        for name in ("dit", "vae"):
+            m = getattr(self, name)
+            if m is not None:
+                m.to(self.device)
+                m.vram_management_enabled = False
+
+    def fetch_models(self, model_manager):
+        self.dit = model_manager.fetch_model("wan_video_dit")
+        self.vae = model_manager.fetch_model("wan_video_vae")
+        te = model_manager.fetch_model("wan_video_text_encoder", require_model_path=True)
+        if te is not None:
+            self.text_encoder = te[0]
+        self.image_encoder = model_manager.fetch_model("wan_video_image_encoder")
+        if self.dit is not None:
+            self.dit.to(self.device).eval()
+
+    @staticmethod
+    def from_model_manager(model_manager, torch_dtype=None, device=None, use_usp=False, is_test=False, num_train_timesteps=1000):
+        device = model_manager.device if device is None else device
+        torch_dtype = model_manager.torch_dtype if torch_dtype is None else torch_dtype
+        pipe = SVIVideoPipeline(device=device, torch_dtype=torch_dtype, is_test=is_test, num_train_timesteps=num_train_timesteps)
+        pipe.fetch_models(model_manager)
+        if use_usp:   # reference :265-273 patches in xfuser USP; here: native token-axis sequence parallelism
+            from ..distributed.sequence_parallel import get_sp_group
+            pipe.sp_size = get_sp_group().world
+            pipe.use_unified_sequence_parallel = True
+        return pipe
+
+    def denoising_model(self):
+        return self.dit
+
+    def prepare_unified_sequence_parallel(self):
+        return {"use_unified_sequence_parallel": self.use_unified_sequence_parallel}
+
+    def prepare_extra_input(self, latents=None):
+        return {}
+
+    # ------------------------------------------------------------------ conditioning
+    def encode_prompt(self, prompt, positive=True):
+        if self.prompter is None:
+            raise RuntimeError("svi_b200: no prompt encoder attached. umT5-XXL is outside the hot-path scope "
+                               "(SURVEY.md §8f.1); set pipe.prompter = callable(prompt, positive) -> [1,512,4096].")
+        emb = self.prompter(prompt, positive=positive)
+        return {"context": emb.to(self.device)}
+
+    def encode_images_adaptive(self, first_frames, random_ref_frame, num_frames, height, width, use_first_aug=False,
+                               ref_pad_cfg=False, ref_pad_num=None):
+        """reference svi_video.py:291-364: CLIP feature of the first frame, the 4-channel first-frame mask and
+        the VAE latents of [condition frames ++ padding]; everything in fp32 then cast to the pipeline dtype."""
+        dev = self.device
+        prep = lambda im: self.preprocess_image(im.resize((width, height))).to(device=dev, dtype=torch.float32)
+        ref = prep(random_ref_frame)
+        first = prep(first_frames[0])
+        clip_context = self.image_encoder.encode_image([first])
+        msk = torch.ones(1, num_frames, height // 8, width // 8, device=dev, dtype=torch.float32)
+        msk[:, (len(first_frames) if ref_pad_cfg else 1):] = 0
+        msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:]], dim=1)
+        msk = msk.view(1, msk.shape[1] // 4, 4, height // 8, width // 8).transpose(1, 2)[0]
+        if len(first_frames) > 1:
+            cond = torch.cat([prep(fr) for fr in first_frames], dim=0).permute(1, 0, 2, 3)
+        else:
+            cond = first.transpose(0, 1)
+        remaining = num_frames - len(first_frames)
+        if ref_pad_num == 0:
+            pad = torch.zeros(3, remaining, height, width, device=dev, dtype=torch.float32)
+        elif ref_pad_num == -1:
+            pad = ref.transpose(0, 1).repeat(1, remaining, 1, 1)
+        elif ref_pad_num is not None and ref_pad_num > 0:
+            pads = [ref.transpose(0, 1)] * ref_pad_num
+            if remaining > ref_pad_num:
+                pads += [torch.zeros(3, 1, height, width, device=dev, dtype=torch.float32)] * (remaining - ref_pad_num)
+            pad = torch.cat(pads, dim=1)
+        else:
+            raise ValueError(f"ref_pad_num must be -1, 0 or positive (got {ref_pad_num})")
+        vae_input = torch.concat([cond, pad], dim=1)
+        y = self.vae.encode([vae_input], device=dev)[0]
+        y = torch.concat([msk, y.to(torch.float32)]).unsqueeze(0)
+        return {"clip_feature": clip_context.to(dtype=self.torch_dtype, device=dev), "y": y.to(dtype=self.torch_dtype, device=dev)}
+
+    def tensor2video(self, frames):
+        """reference :366-370: [C,T,H,W] in [-1,1] -> list of uint8 PIL frames."""
+        fr = ((frames.float().permute(1, 2, 3, 0) + 1) * 127.5).clip(0, 255).cpu().numpy().astype(np.uint8)
+        return [Image.fromarray(f) for f in fr]
+
+    def encode_video(self, input_video, tiled=True, tile_size=(34, 34), tile_stride=(18, 16)):
+        lat = self.vae.encode(input_video.to(device=self.device, dtype=torch.float32), device=self.device, tiled=tiled,
+                              tile_size=tile_size, tile_stride=tile_stride)
+        return lat.to(device=self.device, dtype=self.torch_dtype)
+
+    def decode_video(self, latents, tiled=True, tile_size=(34, 34), tile_stride=(18, 16)):
+        return self.vae.decode(latents.to(device=self.device, dtype=torch.float32), device=self.device, tiled=tiled,
+                               tile_size=tile_size, tile_stride=tile_stride)
+
+    # ------------------------------------------------------------------ denoising
+    def denoise_latents(self, latents, context_posi, context_nega, clip_feature=None, y=None, cfg_scale=5.0,
+                        progress_bar_cmd=lambda x: x, sp=None):
+        """The hot loop (reference _sample_with_regular_video :392-421).  latents: f32 [1,16,f,h,w] on device,
+        updated in place and returned.  Timesteps/sigmas come from self.scheduler (already set)."""
+        eng = self.dit.engine(self.device)
+        lat = latents
+        if lat.dtype != torch.float32 or not lat.is_contiguous():
+            lat = lat.to(torch.float32).contiguous()
+        if y is not None:
+            y = y.to(device=self.device, dtype=torch.float32).contiguous()
+        cp = eng.context_state(context_posi, clip_feature)
+        use_cfg = cfg_scale != 1.0
+        cn = eng.context_state(context_nega, clip_feature) if use_cfg else None
+        v_c = torch.empty_like(lat)
+        v_u = torch.empty_like(lat) if use_cfg else None
+        sig = self.scheduler.sigmas
+        ts = self.scheduler.timesteps
+        n = len(ts)
+        for i in progress_bar_cmd(range(n)):
+            t = float(ts[i])
+            eng.forward(lat, t, cp, y=y, sp=sp, out=v_c)
+            if use_cfg:
+                eng.forward(lat, t, cn, y=y, sp=sp, out=v_u)
+            sigma = float(sig[i])
+            nxt = float(sig[i + 1]) if i + 1 < n else 0.0
+            eng.k.cfg_euler_step(lat, v_c, v_u, cfg_scale, sigma, nxt)
+        return lat
+
+    def _sample_with_regular_video(self, latents, prompt_emb_posi, prompt_emb_nega, image_emb, extra_input, tea_cache_posi,
+                                   tea_cache_nega, usp_kwargs, use_controlnet, cfg_scale, progress_bar_cmd):
+        if tea_cache_posi.get("tea_cache") is not None:
+            raise NotImplementedError("TeaCache is not implemented in the B200 hot path (SURVEY.md §8f.4)")
+        sp = None
+        if usp_kwargs.get("use_unified_sequence_parallel"):
+            from ..distributed.sequence_parallel import get_sp_group
+            sp = get_sp_group()
+        scale = cfg_scale["text"] if isinstance(cfg_scale, dict) else cfg_scale
+        bar = (lambda r: progress_bar_cmd(r)) if progress_bar_cmd is not None else (lambda r: r)
+        return self.denoise_latents(latents, prompt_emb_posi["context"], prompt_emb_nega["context"],
+                                    image_emb.get("clip_feature"), image_emb.get("y"), scale, bar, sp)
+
+    @torch.no_grad()
+    def __call__(self, prompt, negative_prompt="", input_image=None, input_video=None, denoising_strength=1.0, seed=None,
+                 rand_device="cpu", height=480, width=832, num_frames=81, cfg_scale=5.0, num_inference_steps=50,
+                 sigma_shift=5.0, tiled=True, tile_size=(30, 52), tile_stride=(15, 26), tea_cache_l1_thresh=None,
+                 tea_cache_model_id="", progress_bar_cmd=tqdm, random_ref_frame=None, use_controlnet=False, args=None,
+                 last_latent=None):
+        height, width = self.check_resize_height_width(height, width)
+        if num_frames % 4 != 1:
+            num_frames = (num_frames + 2) // 4 * 4 + 1
+            print(f"Only `num_frames % 4 != 1` is acceptable. We round it up to {num_frames}.")
+        if tea_cache_l1_thresh is not None:
+            raise NotImplementedError("TeaCache is not implemented in the B200 hot path (SURVEY.md §8f.4)")
+        tiler_kwargs = {"tiled": tiled, "tile_size": tile_size, "tile_stride": tile_stride}
+        self.scheduler.set_timesteps(num_inference_steps, denoising_strength=denoising_strength, shift=sigma_shift)
+        noise = self.generate_noise((1, 16, (num_frames - 1) // 4 + 1, height // 8, width // 8), seed=seed,
+                                    device=rand_device, dtype=torch.float32)
+        # the reference rounds the initial noise to the pipeline dtype (svi_video.py:465); keep that rounding so
+        # identical seeds start from identical latents, then carry fp32 through the loop
+        latents = noise.to(dtype=self.torch_dtype, device=self.device).to(torch.float32)
+        if input_video is not None:
+            vid = torch.stack(self.preprocess_images(input_video), dim=2).to(dtype=torch.float32, device=self.device)
+            lat0 = self.encode_video(vid, **tiler_kwargs).to(torch.float32)
+            latents = self.scheduler.add_noise(lat0, latents, timestep=self.scheduler.timesteps[0])
+        prompt_emb_posi = self.encode_prompt(prompt, positive=True)
+        prompt_emb_nega = self.encode_prompt(negative_prompt, positive=False)
+        if input_image is not None and self.image_encoder is not None:
+            ref_img = Image.fromarray(random_ref_frame.clone().cpu().numpy())
+            if not isinstance(input_image, list):
+                input_image = [input_image]
+            image_emb = self.encode_images_adaptive(input_image, ref_img, num_frames, height, width, use_first_aug=False,
+                                                    ref_pad_cfg=args.ref_pad_cfg, ref_pad_num=args.ref_pad_num)
+            if last_latent:
+                image_emb["y"][:, 0, ...] = last_latent
+        else:
+            image_emb = {}
+        scale = cfg_scale
+        usp_kwargs = self.prepare_unified_sequence_parallel()
+        latents = self._sample_with_regular_video(latents, prompt_emb_posi, prompt_emb_nega, image_emb, {}, {"tea_cache": None},
+                                                  {"tea_cache": None}, usp_kwargs, use_controlnet, scale, progress_bar_cmd)
+        frames = self.decode_video(latents, **tiler_kwargs)
+        frames = self.tensor2video(frames[0])
+        if hasattr(args, "sequential_cfg") and args.sequential_cfg == "latent":
+            return frames, latents[:, -1, ...]
+        return frames

@@ -1,0 +1,110 @@
+"""GPU parity: the native DiT (C-ABI kernels) against the CPU oracle on identical seeded weights / inputs.
+
+Tolerance (BASELINE.json north_star): rtol=1e-2 / atol=1e-3.  A 30-block bf16-operand model cannot satisfy a
+literal allclose (the reference's own bf16 path reaches 44 % of elements, SURVEY.md §7 hard part 1), so the
+stacked-model tests assert the fraction of elements inside the tolerance and the max / mean error against the
+survey's measured bars, while single ops/blocks are asserted strictly in test_kernels_gpu.py.
+"""
+import pytest
+import torch
+
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _stats(out, ref):
+    err = (out - ref).abs()
+    inside = (err <= 1e-3 + 1e-2 * ref.abs()).float().mean().item()
+    return inside, err.max().item(), err.mean().item() / ref.std().item()
+
+
+def _sd(cfg, seed):
+    """Seeded weights rounded to bf16 (what a real Wan checkpoint holds) and upcast: oracle and native model
+    consume IDENTICAL weights, so the comparison isolates the arithmetic."""
+    return {k: v.to(torch.bfloat16).float() for k, v in synth.make_dit_state_dict(cfg, seed=seed).items()}
+
+
+def _build(cfg, sd):
+    from diffsynth.models.wan_video_dit import WanModel
+    m = WanModel(**cfg).eval()
+    m.load_state_dict(sd)
+    return m.to("cuda")
+
+
+@pytest.mark.parametrize("cfg,f,h,w,ctx_len,seed", [(synth.CFG_TINY_T2V, 3, 8, 12, 40, 0), (synth.CFG_TINY_I2V, 2, 6, 10, 24, 1),
+                                                     (synth.CFG_TINY_T2V, 5, 18, 30, 512, 2)])
+def test_tiny_dit_matches_oracle(cfg, f, h, w, ctx_len, seed):
+    from oracle import wan_dit_oracle as O
+    sd = _sd(cfg, seed)
+    inp = synth.make_dit_inputs(cfg, f, h, w, seed=seed, ctx_len=ctx_len)
+    ts = torch.tensor([937.5])
+    ref = O.dit_forward(sd, cfg, inp["x"], ts, inp["context"], inp.get("clip_feature"), inp.get("y"))
+    m = _build(cfg, sd)
+    out = m(inp["x"].cuda(), ts, inp["context"].cuda(),
+            clip_feature=None if "clip_feature" not in inp else inp["clip_feature"].cuda(),
+            y=None if "y" not in inp else inp["y"].cuda()).float().cpu()
+    inside, mx, rel = _stats(out, ref)
+    print(f"tiny dit: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
+    # bf16 operands put ~2^-9 relative noise on every GEMM input: mean |err| ~ 0.2 % of the output std; with an
+    # output std ~1.1 the atol=1e-3 leg of the tolerance is tighter than that for small elements
+    assert inside > 0.80 and mx < 0.03 and rel < 4e-3
+
+
+def test_golden_fixture_tiny_t2v():
+    """Same check against the committed reference output itself (not via the oracle)."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dit_tiny_t2v.npz"))
+    cfg = synth.CFG_TINY_T2V
+    f, h, w = (int(v) for v in g["fhw"])
+    sd = synth.make_dit_state_dict(cfg, seed=int(g["seed"]))  # golden used fp32 weights
+    inp = synth.make_dit_inputs(cfg, f, h, w, seed=int(g["seed"]), ctx_len=int(g["ctx_len"]))
+    m = _build(cfg, sd)
+    out = m(inp["x"].cuda(), torch.from_numpy(g["timestep"]), inp["context"].cuda()).float().cpu()
+    inside, mx, rel = _stats(out, torch.from_numpy(g["out"]))
+    assert inside > 0.80 and mx < 0.03 and rel < 4e-3
+
+
+def test_model_fn_and_cfg_euler_step_match_oracle():
+    from diffsynth import _native as nv
+    from diffsynth.pipelines.svi_video import model_fn_wan_video
+    from oracle import wan_dit_oracle as O
+    cfg = synth.CFG_TINY_T2V
+    sd = _sd(cfg, 3)
+    a = synth.make_dit_inputs(cfg, 3, 8, 8, seed=3, ctx_len=32)
+    b = synth.make_dit_inputs(cfg, 3, 8, 8, seed=4, ctx_len=32)
+    m = _build(cfg, sd)
+    ref = O.denoise(sd, cfg, a["x"], a["context"], b["context"], steps=2, cfg_scale=5.0)
+    sig = O.flow_match_sigmas(2, 5.0)
+    lat = a["x"].cuda().float().clone()
+    for i in range(2):
+        ts = (sig[i] * 1000).reshape(1)
+        vc = model_fn_wan_video(m, lat, ts, a["context"].cuda())
+        vu = model_fn_wan_video(m, lat, ts, b["context"].cuda())
+        nv.cfg_euler_step(lat, vc, vu, 5.0, float(sig[i]), float(sig[i + 1]) if i + 1 < 2 else 0.0)
+    inside, mx, rel = _stats(lat.cpu(), ref)
+    print(f"2-step denoise: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
+    assert inside > 0.95 and mx < 0.1
+
+
+@pytest.mark.slow
+def test_cfg1_1p3b_one_step_matches_oracle():
+    """BASELINE config 1: Wan2.1-T2V-1.3B random-init, 1 denoise step, 17x320x512 (latent [1,16,5,40,64])."""
+    from oracle import wan_dit_oracle as O
+    cfg = synth.CFG_T2V_1_3B
+    sd = _sd(cfg, 0)
+    inp = synth.make_dit_inputs(cfg, 5, 40, 64, seed=0, ctx_len=512)
+    ts = torch.tensor([1000.0])
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    v_ref = O.dit_forward(sd, cfg, inp["x"], ts, inp["context"])
+    ref = inp["x"] - v_ref                                    # set_timesteps(1): sigma=[1.0] -> x + v*(0-1)
+    m = _build(cfg, {k: v.to(torch.bfloat16) for k, v in sd.items()})
+    del sd
+    v = m(inp["x"].cuda(), ts, inp["context"].cuda()).float()
+    out = (inp["x"].cuda() - v).cpu()
+    inside, mx, rel = _stats(out, ref)
+    print(f"cfg-1 1.3B: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
+    # bars from SURVEY.md §7: emulated bf16-operand/fp32-residual design = 97.5 % inside, max 0.005;
+    # the reference's own bf16 path = 44 % inside, max 0.042
+    assert inside > 0.90 and mx < 0.042 and rel < 6e-3
