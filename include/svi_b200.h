@@ -136,6 +136,60 @@ int svi_act_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, int32_t act
 int svi_add_rows(const float* table, const float* t, int32_t rows, int32_t rows_t, int32_t D,
                  float* out, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Wan 3-D causal VAE (reference diffsynth/models/wan_video_vae.py).  Activations are channels-last.
+ * ---------------------------------------------------------------------------------------------- */
+
+/*
+ * One causal conv launch (CausalConv3d :33-52, Conv2d of Resample :82-174, time_conv, shortcut 1x1x1) as an
+ * implicit GEMM on tcgen05.  Input: bf16 frame ring [ring_slots][in_H][in_W][C_in]; `slot[t*3 + a]` names the
+ * ring slot read by output frame t at temporal tap a (history frames stay in the ring — no pad/cat copies).
+ * Input pixel = output pixel + (k_h - pad_h, k_w - pad_w); out-of-range pixels read as zero.
+ * Weights: bf16 [w_rows, w_ld], row = output channel, column = ((a*kh + b)*kw + c)*ceil64(C_in) + channel.
+ * Output: f32 channels-last, frame t at out + t*out_frame_stride, pixel pitch out_ld; columns >= n_split
+ * (if n_split > 0) go to out + split_offset with column - n_split (upsample3d channel->frame split :153-156).
+ * out = conv + bias (+ residual).
+ */
+typedef struct svi_conv_desc {
+  const void* x_ring; int32_t ring_slots, in_H, in_W, C_in;
+  const void* w_packed; int32_t w_rows; int64_t w_ld;
+  int32_t kt, kh, kw, pad_h, pad_w;
+  int32_t H, W, T;            /* output height, width, frames (T <= 4) */
+  int32_t slot[12];
+  int32_t C_out;
+  int32_t tile_w;             /* output tile = (128/tile_w) x tile_w pixels; 8, 16, 32, 64 or 128 */
+  float* out; int64_t out_frame_stride; int32_t out_ld;
+  int32_t n_split; int64_t split_offset;
+  const float* bias;
+  const float* residual; int64_t res_frame_stride; int32_t res_ld;
+} svi_conv_desc;
+int svi_conv3d_causal(const svi_conv_desc* d, void* stream);
+
+/*
+ * y[p, 0:C] = bf16( act( x[p, 0:C] / max(||x[p,:]||_2, 1e-12) * sqrt(C) * gamma[0:C] ) ), y[p, C:Cpad] = 0.
+ * gamma == NULL: plain cast (no normalisation).  silu != 0: SiLU after the norm.  x f32 [n_pix, ldx].
+ * Replaces RMS_norm (:55-70) + nn.SiLU and the fp32->bf16 staging of conv inputs.
+ */
+int svi_vae_norm_act(const float* x, int64_t n_pix, int32_t C, int64_t ldx, const float* gamma, int32_t silu,
+                     void* y_bf16, int32_t Cpad, void* stream);
+/* nearest-exact x2 spatial upsample (Upsample :73-79) fused with the bf16 cast: x f32 [H,W,C] -> y bf16 [2H,2W,C] */
+int svi_vae_upsample2x(const float* x, int32_t H, int32_t W, int32_t C, void* y_bf16, void* stream);
+/* space-to-depth for the stride-2 Conv2d of downsample (:108-113): x f32 [H,W,C] -> y bf16 [H/2,W/2,4C],
+ * y[h,w,(dy*2+dx)*C + c] = x[2h+dy, 2w+dx, c] */
+int svi_vae_space_to_depth(const float* x, int32_t H, int32_t W, int32_t C, void* y_bf16, void* stream);
+/* planar f32 (channel c at x + c*ldc, n_pix contiguous) -> channels-last (x*scale[c] + shift[c]), f32 [n_pix, ldo]
+ * or bf16 (out_is_bf16), columns [C, ldo) zero */
+int svi_vae_from_planar(const float* x, int32_t C, int64_t n_pix, int64_t ldc, const float* scale, const float* shift,
+                        void* out, int32_t ldo, int32_t out_is_bf16, void* stream);
+/* channels-last f32 [n_pix, ldx] -> planar f32 (channel c at out + c*ldc): (x + pre_shift[c]) * scale[c],
+ * optional clamp to [-1,1] (WanVideoVAE.single_decode :753-756; latent normalisation :542-549) */
+int svi_vae_to_planar(const float* x, int64_t ldx, int32_t C, int64_t n_pix, const float* pre_shift,
+                      const float* scale, int32_t clamp, float* out, int64_t ldc, void* stream);
+/* p[r, 0:N] = bf16(softmax(s[r, 0:N] * scale)), p[r, N:ldp] = 0; s f32 [rows, lds] (VAE AttentionBlock :235-273) */
+int svi_softmax_rows(const float* s, int32_t rows, int32_t N, int64_t lds, float scale, void* p_bf16, int64_t ldp,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

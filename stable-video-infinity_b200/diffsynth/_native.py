@@ -26,6 +26,22 @@ class GemmEpilogue(_c.Structure):
     ]
 
 
+class ConvDesc(_c.Structure):
+    """Mirror of ``svi_conv_desc`` (include/svi_b200.h)."""
+    _fields_ = [
+        ("x_ring", _vp), ("ring_slots", _i32), ("in_H", _i32), ("in_W", _i32), ("C_in", _i32),
+        ("w_packed", _vp), ("w_rows", _i32), ("w_ld", _i64),
+        ("kt", _i32), ("kh", _i32), ("kw", _i32), ("pad_h", _i32), ("pad_w", _i32),
+        ("H", _i32), ("W", _i32), ("T", _i32),
+        ("slot", _i32 * 12),
+        ("C_out", _i32), ("tile_w", _i32),
+        ("out", _vp), ("out_frame_stride", _i64), ("out_ld", _i32),
+        ("n_split", _i32), ("split_offset", _i64),
+        ("bias", _vp),
+        ("residual", _vp), ("res_frame_stride", _i64), ("res_ld", _i32),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol the header declares (checked by tests)
 SIGNATURES = {
     "svi_abi_version": (_i32, []),
@@ -42,6 +58,13 @@ SIGNATURES = {
     "svi_cast_bf16_to_f32": (_i32, [_vp, _vp, _i64, _vp]),
     "svi_act_f32_to_bf16": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "svi_add_rows": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "svi_conv3d_causal": (_i32, [_c.POINTER(ConvDesc), _vp]),
+    "svi_vae_norm_act": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i32, _vp]),
+    "svi_vae_upsample2x": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "svi_vae_space_to_depth": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "svi_vae_from_planar": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "svi_vae_to_planar": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "svi_softmax_rows": (_i32, [_vp, _i32, _i32, _i64, _f32, _vp, _i64, _vp]),
 }
 
 _lib = None
@@ -221,3 +244,51 @@ def add_rows(table, t, out):
                              _ptr(out, torch.float32, "out"), _stream())
     _check(rc, "svi_add_rows")
     return out
+
+
+# --------------------------------------------------------------------------------------------- VAE
+def conv3d_causal(desc):
+    """Launch svi_conv3d_causal with a filled ConvDesc (pointers as ints)."""
+    _check(load().svi_conv3d_causal(ctypes.byref(desc), _stream()), "svi_conv3d_causal")
+
+
+def vae_norm_act(x, n_pix, C, ldx, gamma, silu, out, Cpad):
+    rc = load().svi_vae_norm_act(_ptr(x, torch.float32, "x"), n_pix, C, ldx, _ptr(gamma, torch.float32, "gamma"),
+                                 int(bool(silu)), _ptr(out, torch.bfloat16, "out"), Cpad, _stream())
+    _check(rc, "svi_vae_norm_act")
+    return out
+
+
+def vae_upsample2x(x, H, W, C, out):
+    _check(load().svi_vae_upsample2x(_ptr(x, torch.float32, "x"), H, W, C, _ptr(out, torch.bfloat16, "out"), _stream()),
+           "svi_vae_upsample2x")
+    return out
+
+
+def vae_space_to_depth(x, H, W, C, out):
+    _check(load().svi_vae_space_to_depth(_ptr(x, torch.float32, "x"), H, W, C, _ptr(out, torch.bfloat16, "out"), _stream()),
+           "svi_vae_space_to_depth")
+    return out
+
+
+def vae_from_planar(x, C, n_pix, scale, shift, out, ldo, out_is_bf16, ldc=None):
+    rc = load().svi_vae_from_planar(_ptr(x, torch.float32, "x"), C, n_pix, n_pix if ldc is None else ldc,
+                                    _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"),
+                                    _ptr(out, name="out"), ldo, int(bool(out_is_bf16)), _stream())
+    _check(rc, "svi_vae_from_planar")
+    return out
+
+
+def vae_to_planar(x, ldx, C, n_pix, pre_shift, scale, clamp, out, ldc=None):
+    rc = load().svi_vae_to_planar(_ptr(x, torch.float32, "x"), ldx, C, n_pix, _ptr(pre_shift, torch.float32, "pre_shift"),
+                                  _ptr(scale, torch.float32, "scale"), int(bool(clamp)), _ptr(out, torch.float32, "out"),
+                                  n_pix if ldc is None else ldc, _stream())
+    _check(rc, "svi_vae_to_planar")
+    return out
+
+
+def softmax_rows(s, N, scale, p):
+    rc = load().svi_softmax_rows(_ptr(s, torch.float32, "s"), s.shape[0], N, _rowmajor(s, "s"), float(scale),
+                                 _ptr(p, torch.bfloat16, "p"), _rowmajor(p, "p"), _stream())
+    _check(rc, "svi_softmax_rows")
+    return p

@@ -11,6 +11,7 @@ Numerics policy (SURVEY.md §7 hard part 1): bf16 GEMM/attention operands, fp32 
 stream / norms / softmax / modulation; RoPE in fp32 with an fp64-built (cos, sin) table.
 """
 import math
+import weakref
 from collections import OrderedDict
 from typing import Optional, Tuple
 
@@ -260,12 +261,12 @@ class WanDiTEngine:
 
     def context_state(self, context, clip_feature=None) -> ContextState:
         """Embed the prompt (and CLIP) tokens and project every layer's cross-attention K/V once."""
-        key = (context.data_ptr(), context._version, tuple(context.shape),
-               None if clip_feature is None else (clip_feature.data_ptr(), clip_feature._version))
+        # keyed by tensor IDENTITY (weak references): a freed tensor's address may be reused by different data
+        key = (id(context), context._version, None if clip_feature is None else (id(clip_feature), clip_feature._version))
         hit = self._ctx_cache.get(key)
-        if hit is not None:
+        if hit is not None and hit[0]() is context and (clip_feature is None or hit[1]() is clip_feature):
             self._ctx_cache.move_to_end(key)
-            return hit
+            return hit[2]
         d, dev = self.dim, self.device
         ctx_in = context.reshape(-1, context.shape[-1])
         n_txt = ctx_in.shape[0]
@@ -306,7 +307,7 @@ class WanDiTEngine:
                 self.k.gemm(emb[:257], bw.w_ckv_img, kvi, bias=bw.b_ckv_img, sumsq=ssi, sumsq_group_cols=d)
                 self.k.rmsnorm_rope(kvi[:, :d], ssi, 0, bw.eps_qk, bw.cnk_img)
                 st.kv_img.append(kvi)
-        self._ctx_cache[key] = st
+        self._ctx_cache[key] = (weakref.ref(context), None if clip_feature is None else weakref.ref(clip_feature), st)
         while len(self._ctx_cache) > 8:
             self._ctx_cache.popitem(last=False)
         return st

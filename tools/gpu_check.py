@@ -262,3 +262,69 @@ if __name__ == "__main__":
         globals()["sec_" + sec]()
         torch.cuda.synchronize()
         print(f"=== {sec} done in {time.time()-t0:.1f}s ===", flush=True)
+
+
+def sec_conv():
+    """svi_conv3d_causal against torch conv3d on hand-built frame rings."""
+    import ctypes
+    import torch.nn.functional as F
+    g = torch.Generator(device="cpu").manual_seed(7)
+
+    def run(Cin, Cout, kt, kh, kw, T, H, W, pad, n_split=0, residual=False):
+        S = T + 2
+        xs = (torch.randn(S, H, W, Cin, generator=g) * 0.5)
+        ring = torch.zeros(S + 1, H, W, Cin, dtype=torch.bfloat16, device=dev)
+        ring[:S] = xs.to(dev, torch.bfloat16)
+        w = torch.randn(Cout, Cin, kt, kh, kw, generator=g) / math.sqrt(Cin * kt * kh * kw)
+        b = torch.randn(Cout, generator=g) * 0.1
+        cpad = (Cin + 63) // 64 * 64
+        rows = (Cout + 15) // 16 * 16
+        wp = torch.zeros(rows, kt, kh, kw, cpad)
+        wp[:Cout, :, :, :, :Cin] = w.permute(0, 2, 3, 4, 1)
+        wp = wp.reshape(rows, -1).to(dev, torch.bfloat16).contiguous()
+        bias = torch.zeros(rows, device=dev)
+        bias[:Cout] = b.to(dev)
+        d = nv.ConvDesc()
+        d.x_ring, d.ring_slots, d.in_H, d.in_W, d.C_in = ring.data_ptr(), S + 1, H, W, Cin
+        d.w_packed, d.w_rows, d.w_ld = wp.data_ptr(), rows, wp.shape[1]
+        d.kt, d.kh, d.kw, d.pad_h, d.pad_w = kt, kh, kw, pad, pad
+        d.H, d.W, d.T = H, W, T
+        for t in range(T):
+            for a in range(kt):
+                d.slot[t * 3 + a] = t + a + (3 - kt)   # frames t..t+2 of the ring are (t-2, t-1, t) of the stream
+        d.C_out, d.tile_w = Cout, 8 if W <= 8 else 16
+        res = torch.randn(T, H, W, Cout, generator=g).to(dev) if residual else None
+        if n_split:
+            out = torch.full((2 * T, H, W, n_split), float("nan"), device=dev)
+            d.out, d.out_frame_stride, d.out_ld = out.data_ptr(), 2 * out.stride(0), n_split
+            d.n_split, d.split_offset = n_split, out.stride(0)
+        else:
+            out = torch.full((T, H, W, Cout), float("nan"), device=dev)
+            d.out, d.out_frame_stride, d.out_ld = out.data_ptr(), out.stride(0), Cout
+        d.bias = bias.data_ptr()
+        if residual:
+            d.residual, d.res_frame_stride, d.res_ld = res.data_ptr(), res.stride(0), Cout
+        nv.conv3d_causal(d)
+        torch.cuda.synchronize()
+        xin = ring[:S].float().permute(3, 0, 1, 2).unsqueeze(0)        # [1,C,S,H,W]
+        xin = xin[:, :, 3 - kt:] if kt < 3 else xin
+        ref = F.conv3d(F.pad(xin, (pad, pad, pad, pad, 0, 0)) if kh == 3 else xin, w.to(dev).bfloat16().float(), b.to(dev))
+        if kh == 2:   # 2x2 'valid' conv needs bottom/right zero pad to keep the output size (s2d down-sampling form)
+            ref = F.conv3d(F.pad(xin, (0, 1, 0, 1, 0, 0)), w.to(dev).bfloat16().float(), b.to(dev))
+        ref = ref[0].permute(1, 2, 3, 0)[:T]                           # [T,H,W,Cout]
+        if residual:
+            ref = ref + res
+        if n_split:
+            ref = torch.stack([ref[..., :n_split], ref[..., n_split:]], dim=1).reshape(2 * T, H, W, n_split)
+        report(f"conv Cin={Cin} Cout={Cout} k=({kt},{kh},{kw}) T={T} {H}x{W} split={n_split} res={residual}",
+               out.reshape(-1, out.shape[-1]), ref.reshape(-1, ref.shape[-1]), 2e-2)
+
+    run(64, 96, 3, 3, 3, 2, 16, 16, 1)
+    run(96, 96, 3, 3, 3, 1, 12, 20, 1, residual=True)
+    run(384, 384, 3, 3, 3, 1, 8, 8, 1)
+    run(192, 96, 1, 3, 3, 4, 20, 24, 1)
+    run(384, 768, 3, 1, 1, 2, 6, 10, 0, n_split=384)
+    run(192, 384, 1, 1, 1, 1, 9, 7, 0)
+    run(384, 96, 1, 2, 2, 2, 10, 14, 0)
+    run(64, 4, 3, 3, 3, 1, 4, 6, 1)
+    run(96, 384, 3, 3, 3, 4, 30, 52, 1)
