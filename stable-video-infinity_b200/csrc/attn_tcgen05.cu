@@ -44,7 +44,7 @@ struct Params {
   int accumulate;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(200)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -197,22 +197,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
       const int limit = p.Lk - j * BKV;  // number of valid key columns in this tile (>=128: all)
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld32(tS + cc * 32, r);
-        tmem_ld_wait();
-        if (limit >= BKV) {
+      // single pass: the whole 128-wide S row of this thread lives in registers (4 TMEM loads in flight, one wait)
+      uint32_t sr[4][32];
+      tmem_ld32(tS + 0, sr[0]);
+      tmem_ld32(tS + 32, sr[1]);
+      tmem_ld32(tS + 64, sr[2]);
+      tmem_ld32(tS + 96, sr[3]);
+      tmem_ld_wait();
+      if (limit < BKV) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
-        } else {
+        for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (cc * 32 + e < limit) mx = fmaxf(mx, __uint_as_float(r[e]));
-        }
+            if (cc * 32 + e >= limit) sr[cc][e] = 0xff800000u;  // -inf: masked key column
       }
+      // row max: 8 independent chains (the 128-long serial fmax chain was the critical path)
+      float m8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) m8[u] = fmaxf(__uint_as_float(sr[0][u]), __uint_as_float(sr[0][u + 8]));
+#pragma unroll
+      for (int e = 16; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[0][e]));
+#pragma unroll
+      for (int cc = 1; cc < 4; ++cc) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[cc][e]));
+      }
+      float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
       mx *= c;
       // lazy rescale (warp-uniform decision because tcgen05.ld/st are warp-collective)
       const bool need = (j > 0) && (mx > m_cur + RESCALE_THRESHOLD);
@@ -233,26 +243,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           tmem_st32(tO + cc * 32, r);
         }
       }
-      // pass 2: P = exp2(S*c - m), row sum, bf16 pack into TMEM (aliasing consumed S columns)
-#pragma unroll 1
+      // P = exp2(S*c - m) (masked columns: exp2(-inf) = 0), 4 independent row-sum chains, bf16 pack into TMEM
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld32(tS + cc * 32, r);
-        tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          float p0 = ex2(fmaf(__uint_as_float(r[e]), c, -m_cur));
-          float p1 = ex2(fmaf(__uint_as_float(r[e + 1]), c, -m_cur));
-          if (limit < BKV) {
-            if (cc * 32 + e >= limit) p0 = 0.f;
-            if (cc * 32 + e + 1 >= limit) p1 = 0.f;
-          }
-          l += p0 + p1;
+          const float p0 = ex2(fmaf(__uint_as_float(sr[cc][e]), c, -m_cur));
+          const float p1 = ex2(fmaf(__uint_as_float(sr[cc][e + 1]), c, -m_cur));
+          l4[(e >> 1) & 3] += p0 + p1;
           pk[e >> 1] = pack_bf16x2(p0, p1);
         }
         tmem_st16(tS + cc * 16, pk);
       }
+      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

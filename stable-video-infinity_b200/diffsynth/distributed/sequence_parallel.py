@@ -34,7 +34,7 @@ def all_gather_inplace(full, local, group=None):
         dist.all_gather_into_tensor(full, local, group=group)
     except (RuntimeError, NotImplementedError):   # gloo (CPU tests): list form
         n = dist.get_world_size(group)
-        dist.all_gather(list(full.chunk(n, dim=0)), local.clone(), group=group)
+        dist.all_gather([c.view_as(local) for c in full.chunk(n, dim=0)], local.clone(), group=group)
     return full
 
 
