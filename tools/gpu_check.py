@@ -15,6 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "stable-video-infinity_b200"))
 from diffsynth import _native as nv  # noqa: E402
 
 dev = "cuda"
+RESULTS = []   # (name, ok) of every report() call — tests/test_kernels_gpu.py asserts on it
 
 
 def report(name, got, ref, tol):
@@ -26,6 +27,7 @@ def report(name, got, ref, tol):
     bad = (err > tol * max(scale, 1e-6)).float().mean().item()
     ok = math.isfinite(mx) and mx <= tol * max(scale, 1e-6)
     print(f"[{'OK ' if ok else 'BAD'}] {name}: max_err={mx:.4e} ref_max={scale:.4e} frac_bad={bad:.4f}", flush=True)
+    RESULTS.append((name, ok))
     if not ok:
         # locate the error pattern to help debugging descriptor/layout mistakes
         idx = (err > tol * max(scale, 1e-6)).nonzero()
@@ -254,16 +256,6 @@ def sec_perf_attn():
     print(f"[PERF] cross attn L={L} Lk=512: {ms:.3f} ms = {4.0*L*512*H*128/ms/1e9:.1f} TFLOP/s", flush=True)
 
 
-if __name__ == "__main__":
-    print("device:", torch.cuda.get_device_name(0), "SMs:", nv.sm_count(), flush=True)
-    for sec in sys.argv[1:]:
-        print(f"=== {sec} ===", flush=True)
-        t0 = time.time()
-        globals()["sec_" + sec]()
-        torch.cuda.synchronize()
-        print(f"=== {sec} done in {time.time()-t0:.1f}s ===", flush=True)
-
-
 def sec_conv():
     """svi_conv3d_causal against torch conv3d on hand-built frame rings."""
     import ctypes
@@ -328,3 +320,13 @@ def sec_conv():
     run(384, 96, 1, 2, 2, 2, 10, 14, 0)
     run(64, 4, 3, 3, 3, 1, 4, 6, 1)
     run(96, 384, 3, 3, 3, 4, 30, 52, 1)
+
+
+if __name__ == "__main__":
+    print("device:", torch.cuda.get_device_name(0), "SMs:", nv.sm_count(), flush=True)
+    for sec in sys.argv[1:]:
+        print(f"=== {sec} ===", flush=True)
+        t0 = time.time()
+        globals()["sec_" + sec]()
+        torch.cuda.synchronize()
+        print(f"=== {sec} done in {time.time()-t0:.1f}s ===", flush=True)
