@@ -13,6 +13,8 @@
 // tensor pipe: while warpgroup 0 exponentiates S0(j+1), the tensor core runs PV1(j) and QK1(j+1).
 // Online softmax uses the lazy-rescale rule (O is only rescaled when a row max grows by > 2^8).
 // Replaces flash_attention(), reference wan_video_dit.py:116-147.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/svi_b200.h"
 
@@ -44,7 +46,8 @@ struct Params {
   int accumulate;
 };
 
-__global__ void __maxnreg__(200)
+// 10 warps over 4 SM sub-partitions put 3 warps on one 16K-register partition: 168 registers/thread is the ceiling
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -122,25 +125,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ------------------------------------ MMA issuer --------------------------------------
     constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major (d contiguous)
     constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);   // P K-major (TMEM), V MN-major
+    constexpr uint32_t hi_kmaj = smem_desc_hi(1024, 2);            // SBO 1024 B (8 rows x 128 B), 128B swizzle
+    const uint32_t lead = (lane == 0) ? 1u : 0u;
+    const uint32_t q_lo = smem_desc_lo(smem_u32(smem_q), 16);
+    const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
+    const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), HALF_BYTES);  // MN-major: LBO = distance of the 64-col atoms
+    // whole warp executes (uniform operands -> uniform registers); `lead` predicates the single issuing lane
     auto issue_qk = [&](int i, int ks) {
-      const uint32_t qb = smem_u32(smem_q + i * TILE_BYTES);
-      const uint32_t kb = smem_u32(smem_k + ks * TILE_BYTES);
 #pragma unroll
       for (int kk = 0; kk < HD / 16; ++kk) {
-        const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
-        tc_mma_ss(tmem_base + i * 128, make_smem_desc(qb + off, 16, 1024, 2),
-                  make_smem_desc(kb + off, 16, 1024, 2), idesc_qk, kk != 0);
+        const uint32_t off = ((kk >> 2) * HALF_BYTES + (kk & 3) * 32) >> 4;
+        tc_mma_ss_p(lead, tmem_base + i * 128, q_lo + ((i * TILE_BYTES) >> 4) + off, hi_kmaj,
+                    k_lo + ((ks * TILE_BYTES) >> 4) + off, hi_kmaj, idesc_qk, kk != 0);
       }
     };
     auto issue_pv = [&](int i, int vs, bool first_tile) {
-      const uint32_t vb = smem_u32(smem_v + vs * TILE_BYTES);
 #pragma unroll
-      for (int kk = 0; kk < BKV / 16; ++kk) {
-        // B = V tile, MN-major: 64-column atoms HALF_BYTES apart (LBO), 8-row groups 1024 B apart (SBO)
-        const uint64_t bdesc = make_smem_desc(vb + kk * 2048, HALF_BYTES, 1024, 2);
-        tc_mma_ts(tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8, bdesc, idesc_pv,
-                  !(first_tile && kk == 0));
-      }
+      for (int kk = 0; kk < BKV / 16; ++kk)
+        tc_mma_ts_p(lead, tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8,
+                    v_lo + ((vs * TILE_BYTES + kk * 2048) >> 4), hi_kmaj, idesc_pv, !(first_tile && kk == 0));
     };
 
     // prologue: S_i(0) = Q_i K_0^T
@@ -148,39 +151,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_wait(&q_full[i], 0);
       tc_fence_after();
-      if (lane == 0) {
-        issue_qk(i, 0);
-        tc_commit(&s_full[i]);
-      }
-      __syncwarp();
+      issue_qk(i, 0);
+      tc_commit_p(lead, &s_full[i]);
     }
-    if (lane == 0) tc_commit(&k_empty[0]);
-    __syncwarp();
+    tc_commit_p(lead, &k_empty[0]);
 
     for (int j = 0; j < n_kv; ++j) {
       const int vs = j % KV_STAGES;
       const int ks = (j + 1) % KV_STAGES;
       const bool has_next = (j + 1) < n_kv;
       mbar_wait(&v_full[vs], (j / KV_STAGES) & 1);
+#pragma unroll
       for (int i = 0; i < 2; ++i) {
         mbar_wait(&p_ready[i], j & 1);
         if (has_next && i == 0) mbar_wait(&k_full[ks], ((j + 1) / KV_STAGES) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          issue_pv(i, vs, j == 0);
-          if (!has_next) tc_commit(&o_full[i]);
-          if (has_next) {
-            issue_qk(i, ks);
-            tc_commit(&s_full[i]);
-          }
+        issue_pv(i, vs, j == 0);
+        if (has_next) {
+          issue_qk(i, ks);
+          tc_commit_p(lead, &s_full[i]);
+        } else {
+          tc_commit_p(lead, &o_full[i]);
         }
-        __syncwarp();
       }
-      if (lane == 0) {
-        tc_commit(&v_empty[vs]);
-        if (has_next) tc_commit(&k_empty[ks]);
-      }
-      __syncwarp();
+      tc_commit_p(lead, &v_empty[vs]);
+      if (has_next) tc_commit_p(lead, &k_empty[ks]);
     }
   } else {
     // ------------------------------------ softmax warpgroups ------------------------------
@@ -314,6 +309,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }  // namespace attn
 }  // namespace svi
 
+namespace svi {
+namespace attn2 {
+int launch(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+           long long ldo, int Lq, int Lk, int num_heads, float scale, int accumulate, cudaStream_t stream);
+}
+}  // namespace svi
+
 extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V,
                             int64_t ldv, void* O, int64_t ldo, int32_t Lq, int32_t Lk,
                             int32_t num_heads, float scale, int32_t accumulate, void* stream) {
@@ -329,6 +331,12 @@ extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t l
   SVI_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) |
                 reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(O)) & 15) == 0,
               "svi_attn_fwd: pointers must be 16-byte aligned");
+  // development switch: SVI_ATTN_IMPL=v1 selects the single-S-buffer kernel of this file (A/B timing); the
+  // software-pipelined kernel of attn2_tcgen05.cu is the product path
+  static const int use_v1 = []() { const char* e = getenv("SVI_ATTN_IMPL"); return (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; }();
+  if (!use_v1)
+    return svi::attn2::launch(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, num_heads, scale, accumulate,
+                              static_cast<cudaStream_t>(stream));
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_2d(&tq, Q, 2, (uint64_t)width, (uint64_t)Lq, (uint64_t)ldq * 2, 64, BQ);
   if (rc) return rc;

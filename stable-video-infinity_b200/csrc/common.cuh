@@ -200,6 +200,62 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       : "memory");
 }
 
+
+// ---- uniform-issue variants -------------------------------------------------------------------------------
+// The whole MMA warp executes these (no divergent `if (lane == 0)` around them): every operand is then
+// warp-uniform and ptxas keeps the descriptor arithmetic in uniform registers instead of building each
+// descriptor in vector registers and moving it over with R2UR (+ a compiler-inserted ELECT) per MMA, which cost
+// ~130 issue cycles per tcgen05.mma and made the single issuing thread the bottleneck (profiles/README.md).
+// The issuing lane is chosen by elect.sync inside each wrapper (deterministic for a full-warp mask, so every
+// mma / commit of the kernel comes from the same thread, as tcgen05.commit requires); `lead` is unused.
+__host__ __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ void tc_mma_ss_p(uint32_t lead, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                            uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+  (void)lead;
+}
+__device__ __forceinline__ void tc_mma_ts_p(uint32_t lead, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
+                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+  (void)lead;
+}
+__device__ __forceinline__ void tc_commit_p(uint32_t lead, uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+  (void)lead;
+}
+
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base+i), cols [c, c+32)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -140,6 +140,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(BM, p.BN, 0, 0);
+    constexpr uint32_t hi_kmaj = smem_desc_hi(1024, 2);  // SBO 1024 B, 128B swizzle, K-major
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -151,18 +152,17 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t b_base = a_base + A_STAGE_BYTES;
+        {
+          // whole warp executes with uniform operands; elect.sync inside the wrappers picks the issuing lane
+          const uint32_t a_lo = smem_desc_lo(smem_u32(smem + stage * STAGE_BYTES), 16);
+          const uint32_t b_lo = a_lo + (A_STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            tc_mma_ss(d_tmem, make_smem_desc(a_base + k * UMMA_K * 2, 16, 1024, 2),
-                      make_smem_desc(b_base + k * UMMA_K * 2, 16, 1024, 2), idesc, (kb | k) != 0);
-          }
-          tc_commit(&empty_bar[stage]);
-          if (kb == num_k - 1) tc_commit(&tmem_full_bar[acc]);
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tc_mma_ss_p(0, d_tmem, a_lo + ((k * UMMA_K * 2) >> 4), hi_kmaj, b_lo + ((k * UMMA_K * 2) >> 4), hi_kmaj,
+                        idesc, (kb | k) != 0);
+          tc_commit_p(0, &empty_bar[stage]);                       // smem slot free when MMAs retire
+          if (kb == num_k - 1) tc_commit_p(0, &tmem_full_bar[acc]);  // accumulator ready
         }
-        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -1,0 +1,88 @@
+"""GPU: one whole SVI clip through the public pipeline API (SVIVideoPipeline.__call__, same call shape as
+test_svi.py:457-470) on tiny random-init models, against the same clip computed by the CPU oracles
+(noise -> image conditioning (VAE encode) -> CFG denoise -> VAE decode -> uint8 frames)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from tools import synth, synth_vae
+
+pytestmark = pytest.mark.gpu
+
+H, W, FRAMES, STEPS, CTX = 64, 96, 9, 3, 24
+
+
+class _ClipStub:
+    """Stands in for CLIP ViT-H (out of scope): a fixed random projection of the pooled image."""
+
+    def __init__(self):
+        g = torch.Generator().manual_seed(99)
+        self.proj = torch.randn(3, 257 * 1280, generator=g) * 0.5
+
+    def encode_image(self, images):
+        pooled = images[0].float().cpu().mean(dim=(0, 2, 3))            # [3]
+        return (pooled @ self.proj).reshape(1, 257, 1280)
+
+
+def _prompter(prompt, positive=True):
+    g = torch.Generator().manual_seed(11 if positive else 12)
+    return torch.randn(1, CTX, synth.CFG_TINY_I2V["text_dim"], generator=g)
+
+
+def _image():
+    g = np.random.default_rng(5)
+    return Image.fromarray(g.integers(0, 255, size=(H, W, 3), dtype=np.uint8))
+
+
+def _oracle_clip(dit_sd, vae_sd, cfg, img, seed):
+    from oracle import wan_dit_oracle as O
+    from oracle import wan_vae_oracle as V
+    bf = lambda t: t.to(torch.bfloat16).float()
+    noise = bf(torch.randn((1, 16, (FRAMES - 1) // 4 + 1, H // 8, W // 8), generator=torch.Generator().manual_seed(seed)))
+    x = torch.from_numpy(np.array(img, dtype=np.float32) * (2 / 255) - 1).permute(2, 0, 1).unsqueeze(0)   # [1,3,H,W]
+    clip = bf(_ClipStub().encode_image([x]))
+    msk = torch.zeros(1, FRAMES, H // 8, W // 8)
+    msk[:, 0] = 1
+    msk = torch.cat([torch.repeat_interleave(msk[:, 0:1], 4, dim=1), msk[:, 1:]], dim=1)
+    msk = msk.view(1, msk.shape[1] // 4, 4, H // 8, W // 8).transpose(1, 2)[0]
+    vae_in = torch.cat([x.transpose(0, 1), x.transpose(0, 1).repeat(1, FRAMES - 1, 1, 1)], dim=1)        # ref_pad_num = -1
+    with torch.no_grad():
+        y = bf(torch.cat([msk, V.vae_encode(vae_sd, vae_in.unsqueeze(0))[0]]).unsqueeze(0))
+        lat = O.denoise(dit_sd, cfg, noise, bf(_prompter("p", True)), bf(_prompter("n", False)), steps=STEPS, cfg_scale=5.0,
+                        clip_feature=clip, y=y)
+        vid = V.vae_decode(vae_sd, lat)
+    return lat, ((vid[0].permute(1, 2, 3, 0) + 1) * 127.5).clip(0, 255).numpy().astype(np.uint8)
+
+
+def test_svi_clip_matches_oracle_clip():
+    from diffsynth import ModelManager, SVIVideoPipeline
+    from diffsynth.models.wan_video_dit import WanModel
+    from diffsynth.models.wan_video_vae import WanVideoVAE
+    cfg = synth.CFG_TINY_I2V
+    dit_sd = {k: v.to(torch.bfloat16).float() for k, v in synth.make_dit_state_dict(cfg, seed=2).items()}
+    vae_sd = {k: v.to(torch.bfloat16).float() for k, v in synth_vae.make_vae_state_dict(seed=0).items()}
+    dit = WanModel(**cfg).eval()
+    dit.load_state_dict(dit_sd)
+    vae = WanVideoVAE().eval()
+    vae.load_state_dict(vae_sd)
+    mm = ModelManager(torch_dtype=torch.bfloat16, device="cuda")
+    mm.add_model("wan_video_dit", dit.to("cuda"))
+    mm.add_model("wan_video_vae", vae.to("cuda"))
+    pipe = SVIVideoPipeline.from_model_manager(mm, torch_dtype=torch.bfloat16, device="cuda", is_test=True)
+    pipe.enable_vram_management(num_persistent_param_in_dit=6 * 10 ** 9)
+    pipe.prompter = _prompter
+    pipe.image_encoder = _ClipStub()
+    img = _image()
+    args = types.SimpleNamespace(ref_pad_cfg=False, ref_pad_num=-1, sequential_cfg="none")
+    frames = pipe(prompt="p", negative_prompt="n", input_image=img, num_inference_steps=STEPS, cfg_scale={"text": 5.0}, seed=42,
+                  tiled=False, random_ref_frame=torch.from_numpy(np.array(img)), height=H, width=W, num_frames=FRAMES,
+                  args=args, progress_bar_cmd=lambda x: x)
+    assert len(frames) == FRAMES and frames[0].size == (W, H)
+    got = np.stack([np.array(f) for f in frames]).astype(np.float32)
+    _, ref = _oracle_clip(dit_sd, vae_sd, cfg, img, seed=42)
+    diff = np.abs(got - ref.astype(np.float32))
+    print(f"clip parity: mean {diff.mean():.3f} levels, p99 {np.percentile(diff, 99):.1f}, max {diff.max():.0f}")
+    assert diff.mean() < 2.0 and np.percentile(diff, 99) < 12
