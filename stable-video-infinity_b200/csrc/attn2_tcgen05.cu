@@ -17,6 +17,8 @@
 //   warps 0-3 / 4-7 : softmax warpgroup of Q tile 0 / 1 (thread = row)
 //   warp 8          : TMA producer (Q once; K_j, V_j 64-row tiles into 4-stage rings)
 //   warp 9          : tcgen05.mma issuer + TMEM owner
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/svi_b200.h"
 
@@ -51,26 +53,26 @@ struct Params {
   int accumulate;
 };
 
+// DBG (development only, SVI_ATTN_DEBUG env): 0 = product kernel; 1 = exponentials replaced by FMAs (no MUFU);
+// 2 = softmax warps only move S -> P (no max / exp / sum) — timing probes that isolate the MMA / load side.
+template <int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_q = smem;
-  uint8_t* smem_k = smem + 2 * Q_TILE_BYTES;
-  uint8_t* smem_v = smem_k + KV_STAGES * KV_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + KV_STAGES * KV_TILE_BYTES);
-  uint64_t* q_full = bars;                    // [2]
-  uint64_t* k_full = bars + 2;                // [4]
-  uint64_t* k_empty = bars + 6;               // [4]
-  uint64_t* v_full = bars + 10;               // [4]
-  uint64_t* v_empty = bars + 14;              // [4]
-  uint64_t* s_full = bars + 18;               // [2][2]  index i*2+b
-  uint64_t* p_ready = bars + 22;              // [2][2]  index i*2+b (a softmax warpgroup may run ONE tile ahead of
-                                              //         the MMA warp, so consecutive tiles must not share a barrier)
-  uint64_t* pv_done = bars + 26;              // [2][2]  index i*2+b
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 30);
+  // everything below works on 32-bit shared-window addresses (uniform values -> uniform registers)
+  const uint32_t sraw = smem_u32(smem_raw);
+  const uint32_t sbase = (sraw + 1023u) & ~1023u;
+  constexpr uint32_t OFF_Q = 0;
+  constexpr uint32_t OFF_K = 2 * Q_TILE_BYTES;
+  constexpr uint32_t OFF_V = OFF_K + KV_STAGES * KV_TILE_BYTES;
+  constexpr uint32_t OFF_BAR = OFF_V + KV_STAGES * KV_TILE_BYTES;
+  enum : uint32_t { Q_FULL = 0, K_FULL = 2, K_EMPTY = 6, V_FULL = 10, V_EMPTY = 14, S_FULL = 18, P_READY = 22, PV_DONE = 26,
+                    NUM_BARS = 30 };
+  // S_FULL / P_READY / PV_DONE are indexed [i*2+b]: a softmax warpgroup may run ONE tile ahead of the MMA warp, so
+  // consecutive tiles must not share a barrier
+  auto bar = [&](uint32_t n) { return sbase + OFF_BAR + 8u * n; };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_raw + (sbase - sraw) + OFF_BAR + 8 * NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,16 +87,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
   if (warp == 9) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) mbar_init(&q_full[i], 1);
-      for (int i = 0; i < KV_STAGES; ++i) {
-        mbar_init(&p_ready[i], 4);  // one arrive per softmax warp
-        mbar_init(&k_full[i], 1);
-        mbar_init(&k_empty[i], 1);
-        mbar_init(&v_full[i], 1);
-        mbar_init(&v_empty[i], 1);
-        mbar_init(&s_full[i], 1);
-        mbar_init(&pv_done[i], 1);
-      }
+      for (uint32_t n = 0; n < NUM_BARS; ++n) mbar_init_a(bar(n), (n >= P_READY && n < PV_DONE) ? 4 : 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -104,91 +97,104 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  // The CTA owns all 512 TMEM columns (1 CTA / SM), so the allocation starts at column 0 / lane 0: TMEM addresses
+  // below are compile-time constants.  Verified here; anything else is a hard error.
+  if (*tmem_ptr_smem != 0u) {
+    if (threadIdx.x == 0) printf("svi: unexpected TMEM base 0x%x\n", *tmem_ptr_smem);
+    __trap();
+  }
+  constexpr uint32_t tmem_base = 0;
 
   if (warp == 8) {
     // ------------------------------------ TMA producer ------------------------------------
     if (lane == 0) {
       const int col0 = head * HD;
-      mbar_expect_tx(&q_full[0], Q_TILE_BYTES);
-      tma_load_2d(smem_q, &tmap_q, &q_full[0], col0, q_row0);
-      tma_load_2d(smem_q + Q_HALF_BYTES, &tmap_q, &q_full[0], col0 + 64, q_row0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_expect_tx(&k_full[s], KV_TILE_BYTES);
-        tma_load_2d(smem_k + s * KV_TILE_BYTES, &tmap_k, &k_full[s], col0, j * BKV);
-        tma_load_2d(smem_k + s * KV_TILE_BYTES + KV_HALF_BYTES, &tmap_k, &k_full[s], col0 + 64, j * BKV);
-        if (j == 0) {
-          mbar_expect_tx(&q_full[1], Q_TILE_BYTES);
-          tma_load_2d(smem_q + Q_TILE_BYTES, &tmap_q, &q_full[1], col0, q_row0 + BQ);
-          tma_load_2d(smem_q + Q_TILE_BYTES + Q_HALF_BYTES, &tmap_q, &q_full[1], col0 + 64, q_row0 + BQ);
+      mbar_expect_tx_a(bar(Q_FULL + 0), Q_TILE_BYTES);
+      tma_load_2d_a(sbase + OFF_Q, &tmap_q, bar(Q_FULL + 0), col0, q_row0);
+      tma_load_2d_a(sbase + OFF_Q + Q_HALF_BYTES, &tmap_q, bar(Q_FULL + 0), col0 + 64, q_row0);
+      for (int j0 = 0; j0 < n_kv; j0 += KV_STAGES) {
+        const uint32_t ph = (j0 / KV_STAGES) & 1;
+#pragma unroll
+        for (int s = 0; s < KV_STAGES; ++s) {
+          const int j = j0 + s;
+          if (j >= n_kv) break;
+          mbar_wait_a(bar(K_EMPTY + s), ph ^ 1);
+          mbar_expect_tx_a(bar(K_FULL + s), KV_TILE_BYTES);
+          tma_load_2d_a(sbase + OFF_K + s * KV_TILE_BYTES, &tmap_k, bar(K_FULL + s), col0, j * BKV);
+          tma_load_2d_a(sbase + OFF_K + s * KV_TILE_BYTES + KV_HALF_BYTES, &tmap_k, bar(K_FULL + s), col0 + 64, j * BKV);
+          if (j == 0) {
+            mbar_expect_tx_a(bar(Q_FULL + 1), Q_TILE_BYTES);
+            tma_load_2d_a(sbase + OFF_Q + Q_TILE_BYTES, &tmap_q, bar(Q_FULL + 1), col0, q_row0 + BQ);
+            tma_load_2d_a(sbase + OFF_Q + Q_TILE_BYTES + Q_HALF_BYTES, &tmap_q, bar(Q_FULL + 1), col0 + 64, q_row0 + BQ);
+          }
+          mbar_wait_a(bar(V_EMPTY + s), ph ^ 1);
+          mbar_expect_tx_a(bar(V_FULL + s), KV_TILE_BYTES);
+          tma_load_2d_a(sbase + OFF_V + s * KV_TILE_BYTES, &tmap_v, bar(V_FULL + s), col0, j * BKV);
+          tma_load_2d_a(sbase + OFF_V + s * KV_TILE_BYTES + KV_HALF_BYTES, &tmap_v, bar(V_FULL + s), col0 + 64, j * BKV);
         }
-        mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_expect_tx(&v_full[s], KV_TILE_BYTES);
-        tma_load_2d(smem_v + s * KV_TILE_BYTES, &tmap_v, &v_full[s], col0, j * BKV);
-        tma_load_2d(smem_v + s * KV_TILE_BYTES + KV_HALF_BYTES, &tmap_v, &v_full[s], col0 + 64, j * BKV);
       }
     }
   } else if (warp == 9) {
     // ------------------------------------ MMA issuer --------------------------------------
+    // The WHOLE warp runs this code with warp-uniform operands; the issuing lane is picked by elect.sync inside the
+    // batched wrappers (4 K-steps per asm block).  Stage / buffer indices are compile-time constants (x4 unroll).
     constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
     constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);   // P K-major (TMEM), V MN-major
-    constexpr uint32_t hi_kmaj = smem_desc_hi(1024, 2);
-    const uint32_t lead = (lane == 0) ? 1u : 0u;
-    const uint32_t q_lo = smem_desc_lo(smem_u32(smem_q), 16);
-    const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
-    const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), KV_HALF_BYTES);  // MN-major: LBO = distance of the 64-col atoms
-    // whole warp executes (uniform operands -> uniform registers); `lead` predicates the single issuing lane
-    auto issue_qk = [&](int i, int ks, int b) {
-#pragma unroll
-      for (int kk = 0; kk < HD / 16; ++kk) {
-        const uint32_t offq = ((kk >> 2) * Q_HALF_BYTES + (kk & 3) * 32) >> 4;
-        const uint32_t offk = ((kk >> 2) * KV_HALF_BYTES + (kk & 3) * 32) >> 4;
-        tc_mma_ss_p(lead, tmem_base + i * 128 + b * 64, q_lo + ((i * Q_TILE_BYTES) >> 4) + offq, hi_kmaj,
-                    k_lo + ((ks * KV_TILE_BYTES) >> 4) + offk, hi_kmaj, idesc_qk, kk != 0);
-      }
+    constexpr uint32_t hi_kmaj = smem_desc_hi(1024, 2);            // SBO 1024 B (8 rows x 128 B), 128B swizzle
+    const uint32_t q_lo = smem_desc_lo(sbase + OFF_Q, 16);
+    const uint32_t k_lo = smem_desc_lo(sbase + OFF_K, 16);
+    const uint32_t v_lo = smem_desc_lo(sbase + OFF_V, KV_HALF_BYTES);  // MN-major: LBO = distance of the 64-col atoms
+    auto issue_qk = [&](int i, int ks, int b) {   // S_i[b] = Q_i K^T : 8 K-steps = 2 swizzle boxes x 4
+      const uint32_t d = tmem_base + i * 128 + b * 64;
+      const uint32_t a0 = q_lo + ((i * Q_TILE_BYTES) >> 4), b0 = k_lo + ((ks * KV_TILE_BYTES) >> 4);
+      tc_mma_ss_k4(d, a0, hi_kmaj, b0, hi_kmaj, idesc_qk, 0);
+      tc_mma_ss_k4(d, a0 + (Q_HALF_BYTES >> 4), hi_kmaj, b0 + (KV_HALF_BYTES >> 4), hi_kmaj, idesc_qk, 1);
     };
-    auto issue_pv = [&](int i, int vs, int b, bool first_tile) {
-#pragma unroll
-      for (int kk = 0; kk < BKV / 16; ++kk)
-        tc_mma_ts_p(lead, tmem_base + 256 + i * 128, tmem_base + i * 128 + b * 64 + kk * 8,
-                    v_lo + ((vs * KV_TILE_BYTES + kk * 2048) >> 4), hi_kmaj, idesc_pv, !(first_tile && kk == 0));
+    auto issue_pv = [&](int i, int vs, int b, uint32_t accumulate) {   // O_i (+)= P_i[b] V : 4 K-steps of 16 rows
+      tc_mma_ts_k4(tmem_base + 256 + i * 128, tmem_base + i * 128 + b * 64, v_lo + ((vs * KV_TILE_BYTES) >> 4), hi_kmaj,
+                   idesc_pv, accumulate);
     };
 
-    mbar_wait(&k_full[0], 0);
+    mbar_wait_a(bar(K_FULL + 0), 0);
+#pragma unroll
     for (int i = 0; i < 2; ++i) {
-      mbar_wait(&q_full[i], 0);
+      mbar_wait_a(bar(Q_FULL + i), 0);
       tc_fence_after();
       issue_qk(i, 0, 0);
-      tc_commit_p(lead, &s_full[i * 2 + 0]);
+      tc_commit_a(bar(S_FULL + i * 2 + 0));
     }
-    tc_commit_p(lead, &k_empty[0]);
+    tc_commit_a(bar(K_EMPTY + 0));
 
-    for (int j = 0; j < n_kv; ++j) {
-      if (j + 1 < n_kv) {  // next tile's S for both Q tiles goes first: it does not depend on this tile's softmax
-        const int ks = (j + 1) % KV_STAGES;
-        const int b = (j + 1) & 1;
-        mbar_wait(&k_full[ks], ((j + 1) / KV_STAGES) & 1);
-        tc_fence_after();
-        issue_qk(0, ks, b);
-        tc_commit_p(lead, &s_full[0 * 2 + b]);
-        issue_qk(1, ks, b);
-        tc_commit_p(lead, &s_full[1 * 2 + b]);
-        tc_commit_p(lead, &k_empty[ks]);
-      }
-      const int vs = j % KV_STAGES;
-      const int b = j & 1;
-      mbar_wait(&v_full[vs], (j / KV_STAGES) & 1);
+    for (int j0 = 0; j0 < n_kv; j0 += KV_STAGES) {
+      const uint32_t ph = (j0 / KV_STAGES) & 1;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        mbar_wait(&p_ready[i * 2 + b], (j >> 1) & 1);
-        tc_fence_after();
-        issue_pv(i, vs, b, j == 0);
-        tc_commit_p(lead, &pv_done[i * 2 + b]);
+      for (int u = 0; u < KV_STAGES; ++u) {
+        const int j = j0 + u;
+        if (j >= n_kv) break;
+        if (j + 1 < n_kv) {  // next tile's S for both Q tiles goes first: it does not depend on this tile's softmax
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int ks = (u + 1) & 3;
+          const int b1 = (u + 1) & 1;
+          mbar_wait_a(bar(K_FULL + ks), (u == 3) ? (ph ^ 1) : ph);
+          tc_fence_after();
+          issue_qk(0, ks, b1);
+          tc_commit_a(bar(S_FULL + 0 * 2 + b1));
+          issue_qk(1, ks, b1);
+          tc_commit_a(bar(S_FULL + 1 * 2 + b1));
+          tc_commit_a(bar(K_EMPTY + ks));
+        }
+        const int b = u & 1;
+        mbar_wait_a(bar(V_FULL + u), ph);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait_a(bar(P_READY + i * 2 + b), (u >> 1) & 1);   // tile j uses phase (j >> 1) & 1 = (u >> 1) & 1
+          tc_fence_after();
+          issue_pv(i, u, b, j != 0);
+          tc_commit_a(bar(PV_DONE + i * 2 + b));
+        }
+        tc_commit_a(bar(V_EMPTY + u));
       }
-      tc_commit_p(lead, &v_empty[vs]);
     }
   } else {
     // ------------------------------------ softmax warpgroups ------------------------------
@@ -203,7 +209,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int j = 0; j < n_kv; ++j) {
       const int b = j & 1;
       const uint32_t tS = tmem_base + i * 128 + b * 64 + lane_sel;
-      mbar_wait(&s_full[i * 2 + b], (j >> 1) & 1);
+      mbar_wait_a(bar(S_FULL + i * 2 + b), (j >> 1) & 1);
       tc_fence_after();
       uint32_t sr[2][32];
       tmem_ld32(tS + 0, sr[0]);
@@ -217,6 +223,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int e = 0; e < 32; ++e)
             if (cc * 32 + e >= limit) sr[cc][e] = 0xff800000u;  // -inf
       }
+      if (DBG == 2) m_cur = 0.f;
       float m8[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) m8[u] = fmaxf(__uint_as_float(sr[0][u]), __uint_as_float(sr[0][u + 8]));
@@ -226,12 +233,12 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int e = 0; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[1][e]));
       float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
       mx *= c;
-      const bool need = (j > 0) && (mx > m_cur + RESCALE_THRESHOLD);
+      const bool need = (DBG != 2) && (j > 0) && (mx > m_cur + RESCALE_THRESHOLD);
       if (j == 0) {
-        m_cur = mx;
+        if (DBG != 2) m_cur = mx;
       } else if (__any_sync(0xffffffffu, need)) {
         // O_i must be quiescent: PV_i(j-1) has to retire first (S(j) can arrive before it in this pipeline)
-        mbar_wait(&pv_done[i * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+        mbar_wait_a(bar(PV_DONE + i * 2 + ((j - 1) & 1)), ((j - 1) >> 1) & 1);
         tc_fence_after();
         const float m_new = fmaxf(m_cur, mx);
         const float alpha = ex2(m_cur - m_new);
@@ -253,8 +260,12 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(sr[cc][e]), c, -m_cur));
-          const float p1 = ex2(fmaf(__uint_as_float(sr[cc][e + 1]), c, -m_cur));
+          float p0 = fmaf(__uint_as_float(sr[cc][e]), c, -m_cur);
+          float p1 = fmaf(__uint_as_float(sr[cc][e + 1]), c, -m_cur);
+          if (DBG == 0) {
+            p0 = ex2(p0);
+            p1 = ex2(p1);
+          }
           l4[(e >> 1) & 3] += p0 + p1;
           pk[e >> 1] = pack_bf16x2(p0, p1);
         }
@@ -264,11 +275,11 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[i * 2 + b]);
+      if (lane == 0) mbar_arrive_a(bar(P_READY + i * 2 + b));
     }
 
     // epilogue: wait for the last PV, O / l -> bf16 -> global
-    mbar_wait(&pv_done[i * 2 + ((n_kv - 1) & 1)], ((n_kv - 1) >> 1) & 1);
+    mbar_wait_a(bar(PV_DONE + i * 2 + ((n_kv - 1) & 1)), ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
     const int row = q_row0 + i * BQ + quad * 32 + lane;
     const float inv_l = 1.0f / l;
@@ -326,7 +337,9 @@ int launch(const void* Q, long long ldq, const void* K, long long ldk, const voi
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(attn2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t ce = cudaFuncSetAttribute(attn2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(attn2_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(attn2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (ce != cudaSuccess) {
       set_last_error("svi_attn_fwd(v2): cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce));
       return SVI_ERR_LAUNCH;
@@ -341,7 +354,10 @@ int launch(const void* Q, long long ldq, const void* K, long long ldk, const voi
   p.scale_log2 = scale * 1.4426950408889634f;
   p.accumulate = accumulate;
   dim3 grid((Lq + 2 * BQ - 1) / (2 * BQ), num_heads);
-  attn2_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  static const int dbg = []() { const char* e = getenv("SVI_ATTN_DEBUG"); return e ? atoi(e) : 0; }();
+  if (dbg == 1) attn2_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  else if (dbg == 2) attn2_fwd_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  else attn2_fwd_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
   SVI_CUDA_LAUNCH_CHECK("svi_attn_fwd(v2)");
   return SVI_OK;
 }

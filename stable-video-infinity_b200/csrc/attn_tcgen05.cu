@@ -131,19 +131,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
     const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), HALF_BYTES);  // MN-major: LBO = distance of the 64-col atoms
     // whole warp executes (uniform operands -> uniform registers); `lead` predicates the single issuing lane
-    auto issue_qk = [&](int i, int ks) {
-#pragma unroll
-      for (int kk = 0; kk < HD / 16; ++kk) {
-        const uint32_t off = ((kk >> 2) * HALF_BYTES + (kk & 3) * 32) >> 4;
-        tc_mma_ss_p(lead, tmem_base + i * 128, q_lo + ((i * TILE_BYTES) >> 4) + off, hi_kmaj,
-                    k_lo + ((ks * TILE_BYTES) >> 4) + off, hi_kmaj, idesc_qk, kk != 0);
-      }
+    auto issue_qk = [&](int i, int ks) {   // 8 K-steps = 2 swizzle boxes x 4 (batched issue)
+      const uint32_t a0 = q_lo + ((i * TILE_BYTES) >> 4), b0 = k_lo + ((ks * TILE_BYTES) >> 4);
+      tc_mma_ss_k4(tmem_base + i * 128, a0, hi_kmaj, b0, hi_kmaj, idesc_qk, 0);
+      tc_mma_ss_k4(tmem_base + i * 128, a0 + (HALF_BYTES >> 4), hi_kmaj, b0 + (HALF_BYTES >> 4), hi_kmaj, idesc_qk, 1);
     };
-    auto issue_pv = [&](int i, int vs, bool first_tile) {
-#pragma unroll
-      for (int kk = 0; kk < BKV / 16; ++kk)
-        tc_mma_ts_p(lead, tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8,
-                    v_lo + ((vs * TILE_BYTES + kk * 2048) >> 4), hi_kmaj, idesc_pv, !(first_tile && kk == 0));
+    auto issue_pv = [&](int i, int vs, bool first_tile) {   // 8 K-steps of 16 K/V rows
+      const uint32_t b0 = v_lo + ((vs * TILE_BYTES) >> 4);
+      tc_mma_ts_k4(tmem_base + 256 + i * 128, tmem_base + i * 128, b0, hi_kmaj, idesc_pv, first_tile ? 0u : 1u);
+      tc_mma_ts_k4(tmem_base + 256 + i * 128, tmem_base + i * 128 + 32, b0 + ((4 * 2048) >> 4), hi_kmaj, idesc_pv, 1);
     };
 
     // prologue: S_i(0) = Q_i K_0^T

@@ -256,6 +256,121 @@ __device__ __forceinline__ void tc_commit_p(uint32_t lead, uint64_t* bar) {
   (void)lead;
 }
 
+// ---- batched issue: four consecutive K-steps (K = 64 bf16 = one 128-byte swizzle row) in ONE asm block ------
+// One elect.sync and one descriptor pair per batch; the per-step descriptor advance (+32 B = +2 in the 16-byte
+// start-address field) is plain 32-bit adds, so a 128x{64..256}x64 tile costs ~20 SASS instructions instead of
+// ~60.  The first MMA uses `acc_first` as the accumulate flag, the other three always accumulate.
+__device__ __forceinline__ void tc_mma_ss_k4(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                             uint32_t b_hi, uint32_t idesc, uint32_t acc_first) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q, t;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 a1, b1;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "add.u32 a1, %1, 2;\n"
+      "add.u32 b1, %3, 2;\n"
+      "mov.b64 da, {a1, %2};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n"
+      "add.u32 a1, %1, 4;\n"
+      "add.u32 b1, %3, 4;\n"
+      "mov.b64 da, {a1, %2};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n"
+      "add.u32 a1, %1, 6;\n"
+      "add.u32 b1, %3, 6;\n"
+      "mov.b64 da, {a1, %2};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
+// A operand (P, bf16) in TMEM: +8 columns per K-step; B = MN-major V tile: +2048 B (16 rows x 128 B) per K-step
+__device__ __forceinline__ void tc_mma_ts_k4(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t acc_first) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q, t;\n"
+      ".reg .b64 db;\n"
+      ".reg .b32 a1, b1;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+      "add.u32 a1, %1, 8;\n"
+      "add.u32 b1, %2, 128;\n"
+      "mov.b64 db, {b1, %3};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], db, %4, t;\n"
+      "add.u32 a1, %1, 16;\n"
+      "add.u32 b1, %2, 256;\n"
+      "mov.b64 db, {b1, %3};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], db, %4, t;\n"
+      "add.u32 a1, %1, 24;\n"
+      "add.u32 b1, %2, 384;\n"
+      "mov.b64 db, {b1, %3};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], db, %4, t;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
+
+// ---- 32-bit shared-address forms (no generic 64-bit pointer arithmetic in the hot warps) -----------------
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) {
+      printf("svi: mbarrier timeout block(%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c_inner,
+                                              int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(m), "r"(bar), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_a(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar)
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base+i), cols [c, c+32)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -127,10 +127,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // whole warp executes with uniform operands; elect.sync inside the wrappers picks the issuing lane
           const uint32_t a_lo = smem_desc_lo(smem_u32(smem + stage * STAGE_BYTES), 16);
           const uint32_t b_lo = a_lo + (A_STAGE_BYTES >> 4);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            tc_mma_ss_p(0, d_tmem, a_lo + ((k * UMMA_K * 2) >> 4), hi_kmaj, b_lo + ((k * UMMA_K * 2) >> 4), hi_kmaj,
-                        idesc, (kb | k) != 0);
+          tc_mma_ss_k4(d_tmem, a_lo, hi_kmaj, b_lo, hi_kmaj, idesc, kb != 0);   // BK = 64 = 4 K-steps, one asm block
           tc_commit_p(0, &empty_bar[stage]);                       // smem slot free when MMAs retire
           if (kb == num_k - 1) tc_commit_p(0, &tmem_full_bar[acc]);  // accumulator ready
         }
