@@ -54,7 +54,8 @@ struct Params {
 };
 
 // DBG (development only, SVI_ATTN_DEBUG env): 0 = product kernel; 1 = exponentials replaced by FMAs (no MUFU);
-// 2 = softmax warps only move S -> P (no max / exp / sum) — timing probes that isolate the MMA / load side.
+// 2 = softmax warps only move S -> P (no max / exp / sum); 3 = 2 + the MMA warp ignores P_READY; 4 = 3 + the MMA warp
+// ignores K_FULL / V_FULL (results are garbage for DBG >= 1) — timing probes that isolate the MMA / load side.
 template <int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -176,7 +177,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           (void)dummy;
           const int ks = (u + 1) & 3;
           const int b1 = (u + 1) & 1;
-          mbar_wait_a(bar(K_FULL + ks), (u == 3) ? (ph ^ 1) : ph);
+          if (DBG < 4) mbar_wait_a(bar(K_FULL + ks), (u == 3) ? (ph ^ 1) : ph);
           tc_fence_after();
           issue_qk(0, ks, b1);
           tc_commit_a(bar(S_FULL + 0 * 2 + b1));
@@ -185,10 +186,10 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           tc_commit_a(bar(K_EMPTY + ks));
         }
         const int b = u & 1;
-        mbar_wait_a(bar(V_FULL + u), ph);
+        if (DBG < 4) mbar_wait_a(bar(V_FULL + u), ph);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          mbar_wait_a(bar(P_READY + i * 2 + b), (u >> 1) & 1);   // tile j uses phase (j >> 1) & 1 = (u >> 1) & 1
+          if (DBG < 3) mbar_wait_a(bar(P_READY + i * 2 + b), (u >> 1) & 1);   // tile j uses phase (j >> 1) & 1 = (u >> 1) & 1
           tc_fence_after();
           issue_pv(i, u, b, j != 0);
           tc_commit_a(bar(PV_DONE + i * 2 + b));
@@ -223,7 +224,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int e = 0; e < 32; ++e)
             if (cc * 32 + e >= limit) sr[cc][e] = 0xff800000u;  // -inf
       }
-      if (DBG == 2) m_cur = 0.f;
+      if (DBG >= 2) m_cur = 0.f;
       float m8[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) m8[u] = fmaxf(__uint_as_float(sr[0][u]), __uint_as_float(sr[0][u + 8]));
@@ -233,9 +234,9 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int e = 0; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[1][e]));
       float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
       mx *= c;
-      const bool need = (DBG != 2) && (j > 0) && (mx > m_cur + RESCALE_THRESHOLD);
+      const bool need = (DBG < 2) && (j > 0) && (mx > m_cur + RESCALE_THRESHOLD);
       if (j == 0) {
-        if (DBG != 2) m_cur = mx;
+        if (DBG < 2) m_cur = mx;
       } else if (__any_sync(0xffffffffu, need)) {
         // O_i must be quiescent: PV_i(j-1) has to retire first (S(j) can arrive before it in this pipeline)
         mbar_wait_a(bar(PV_DONE + i * 2 + ((j - 1) & 1)), ((j - 1) >> 1) & 1);
@@ -340,6 +341,8 @@ int launch(const void* Q, long long ldq, const void* K, long long ldk, const voi
     cudaError_t ce = cudaFuncSetAttribute(attn2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(attn2_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(attn2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(attn2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(attn2_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (ce != cudaSuccess) {
       set_last_error("svi_attn_fwd(v2): cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce));
       return SVI_ERR_LAUNCH;
@@ -357,6 +360,8 @@ int launch(const void* Q, long long ldq, const void* K, long long ldk, const voi
   static const int dbg = []() { const char* e = getenv("SVI_ATTN_DEBUG"); return e ? atoi(e) : 0; }();
   if (dbg == 1) attn2_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
   else if (dbg == 2) attn2_fwd_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  else if (dbg == 3) attn2_fwd_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  else if (dbg == 4) attn2_fwd_kernel<4><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
   else attn2_fwd_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
   SVI_CUDA_LAUNCH_CHECK("svi_attn_fwd(v2)");
   return SVI_OK;

@@ -327,10 +327,11 @@ extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t l
   SVI_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) |
                 reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(O)) & 15) == 0,
               "svi_attn_fwd: pointers must be 16-byte aligned");
-  // development switch: SVI_ATTN_IMPL=v1 selects the single-S-buffer kernel of this file (A/B timing); the
-  // software-pipelined kernel of attn2_tcgen05.cu is the product path
-  static const int use_v1 = []() { const char* e = getenv("SVI_ATTN_IMPL"); return (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; }();
-  if (!use_v1)
+  // Two kernels exist (profiles/README.md): this file's 128-row K/V tile kernel (product path: fewest MMAs and
+  // least shared-memory traffic) and the software-pipelined 64-row variant of attn2_tcgen05.cu, kept for the
+  // next round's 2-CTA work and selectable for A/B timing with SVI_ATTN_IMPL=v2.  Both measure ~1.16-1.18 PFLOP/s.
+  static const int use_v2 = []() { const char* e = getenv("SVI_ATTN_IMPL"); return (e && e[0] == 'v' && e[1] == '2') ? 1 : 0; }();
+  if (use_v2)
     return svi::attn2::launch(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, num_heads, scale, accumulate,
                               static_cast<cudaStream_t>(stream));
   CUtensorMap tq, tk, tv;
