@@ -273,9 +273,16 @@ def main():
         b.record()
         torch.cuda.synchronize()
         e2e_ms = a.elapsed_time(b) / args.steps
+        # how much of the e2e step is the per-call re-projection of the prompt (embedding MLP + 30 layers of K/V)
+        a.record()
+        for i in range(4):
+            eng.context_state(ctx_pos_host.to(dev, non_blocking=True))
+        b.record()
+        torch.cuda.synchronize()
+        ctx_ms = a.elapsed_time(b) / 4
         h2d = lat_host.numel() * 4 + 2 * ctx_pos_host.numel() * 4
         e2e = {"value": f / (CLIP_STEPS * e2e_ms / 1e3), "unit": "latent_frames/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4, "context_prep_ms_per_prompt": ctx_ms,
                "api": "diffsynth.pipelines.svi_video.model_fn_wan_video x2 + svi_cfg_euler_step, pinned host buffers"}
 
     if rank != 0:

@@ -44,7 +44,7 @@ def main():
                 print(f"[rank {rank}] {sp.describe()} has_image={cfg['has_image_input']} forward max|sp - single| = {err:.3e} {'OK' if good else 'BAD'}", flush=True)
             # full step under the plan vs two local forwards + fused update
             cp = eng.context_state(inp["context"].to(dev), kw.get("clip_feature"))
-            ctx2 = torch.randn_like(inp["context"]).to(dev)
+            ctx2 = torch.randn(inp["context"].shape, generator=torch.Generator().manual_seed(77)).to(dev)   # same on every rank
             cn = eng.context_state(ctx2, kw.get("clip_feature"))
             lat_a, lat_b = x.clone().float(), x.clone().float()
             vc, vu = torch.empty_like(lat_a), torch.empty_like(lat_a)
