@@ -86,3 +86,67 @@ def test_svi_clip_matches_oracle_clip():
     diff = np.abs(got - ref.astype(np.float32))
     print(f"clip parity: mean {diff.mean():.3f} levels, p99 {np.percentile(diff, 99):.1f}, max {diff.max():.0f}")
     assert diff.mean() < 2.0 and np.percentile(diff, 99) < 12
+
+
+def test_wan_t2v_pipeline_matches_oracle():
+    """WanVideoPipeline (scalar cfg_scale, no image conditioning) — reference pipelines/wan_video.py:25-286."""
+    from diffsynth import ModelManager, WanVideoPipeline
+    from diffsynth.models.wan_video_dit import WanModel
+    from diffsynth.models.wan_video_vae import WanVideoVAE
+    from oracle import wan_dit_oracle as O
+    from oracle import wan_vae_oracle as V
+    cfg = synth.CFG_TINY_T2V
+    dit_sd = {k: v.to(torch.bfloat16).float() for k, v in synth.make_dit_state_dict(cfg, seed=5).items()}
+    vae_sd = {k: v.to(torch.bfloat16).float() for k, v in synth_vae.make_vae_state_dict(seed=0).items()}
+    dit = WanModel(**cfg).eval()
+    dit.load_state_dict(dit_sd)
+    vae = WanVideoVAE().eval()
+    vae.load_state_dict(vae_sd)
+    mm = ModelManager(torch_dtype=torch.bfloat16, device="cuda")
+    mm.add_model("wan_video_dit", dit.to("cuda"))
+    mm.add_model("wan_video_vae", vae.to("cuda"))
+    pipe = WanVideoPipeline.from_model_manager(mm, torch_dtype=torch.bfloat16, device="cuda")
+    pipe.prompter = lambda prompt, positive=True: torch.randn(1, CTX, cfg["text_dim"], generator=torch.Generator().manual_seed(21 if positive else 22))
+    frames = pipe(prompt="p", negative_prompt="n", num_inference_steps=STEPS, cfg_scale=5.0, seed=7, tiled=False,
+                  height=H, width=W, num_frames=FRAMES, progress_bar_cmd=lambda x: x)
+    got = np.stack([np.array(f) for f in frames]).astype(np.float32)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    noise = bf(torch.randn((1, 16, (FRAMES - 1) // 4 + 1, H // 8, W // 8), generator=torch.Generator().manual_seed(7)))
+    with torch.no_grad():
+        lat = O.denoise(dit_sd, cfg, noise, bf(pipe.prompter("p", True)), bf(pipe.prompter("n", False)), steps=STEPS, cfg_scale=5.0)
+        vid = V.vae_decode(vae_sd, lat)
+    ref = ((vid[0].permute(1, 2, 3, 0) + 1) * 127.5).clip(0, 255).numpy().astype(np.uint8).astype(np.float32)
+    diff = np.abs(got - ref)
+    print(f"t2v clip parity: mean {diff.mean():.3f} levels, p99 {np.percentile(diff, 99):.1f}, max {diff.max():.0f}")
+    assert diff.mean() < 2.0 and np.percentile(diff, 99) < 12
+
+
+def test_lora_merge_on_native_gemm_and_engine_invalidation():
+    """load_lora_v2: W += alpha * B @ A (reference lora.py:246-267) computed through the GEMM epilogue."""
+    from diffsynth import ModelManager
+    from diffsynth.models.wan_video_dit import WanModel
+    cfg = synth.CFG_TINY_T2V
+    sd = synth.make_dit_state_dict(cfg, seed=9)
+    dit = WanModel(**cfg).eval()
+    dit.load_state_dict(sd)
+    dit.to(device="cuda", dtype=torch.bfloat16)
+    mm = ModelManager(torch_dtype=torch.bfloat16, device="cuda")
+    mm.add_model("wan_video_dit", dit)
+    inp = synth.make_dit_inputs(cfg, 2, 8, 8, seed=9, ctx_len=16)
+    before = dit(inp["x"].cuda(), torch.tensor([500.0]), inp["context"].cuda()).float().clone()
+    g = torch.Generator().manual_seed(1)
+    r, alpha = 12, 0.5
+    lora = {}
+    targets = ["blocks.0.self_attn.q", "blocks.1.ffn.0", "blocks.1.ffn.2"]
+    for t in targets:
+        w = dict(dit.named_parameters())[t + ".weight"]
+        lora[f"pipe.dit.{t}.lora_A.default.weight"] = torch.randn(r, w.shape[1], generator=g) * 0.1
+        lora[f"pipe.dit.{t}.lora_B.default.weight"] = torch.randn(w.shape[0], r, generator=g) * 0.1
+    w0 = {t: dict(dit.named_parameters())[t + ".weight"].detach().float().clone() for t in targets}
+    mm.load_lora_v2("synthetic.safetensors", state_dict=lora, lora_alpha=alpha)
+    for t in targets:
+        want = w0[t] + alpha * (lora[f"pipe.dit.{t}.lora_B.default.weight"].cuda() @ lora[f"pipe.dit.{t}.lora_A.default.weight"].cuda())
+        got = dict(dit.named_parameters())[t + ".weight"].detach().float()
+        assert (got - want).abs().max().item() < 2e-2 * want.abs().max().item()       # one bf16 rounding of the merged weight
+    after = dit(inp["x"].cuda(), torch.tensor([500.0]), inp["context"].cuda()).float()
+    assert (after - before).abs().max().item() > 1e-3      # the engine picked up the merged weights
