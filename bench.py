@@ -128,11 +128,16 @@ def run_reference_arm(args, wl_name, cfg, f, h, w, ctx_len, desc):
         return
     L = f * (h // 2) * (w // 2)
     times = []
+    budget_s = 170.0        # keep the whole arm within a few minutes on any host
+    t_start = time.perf_counter()
+    warm = args.warmup
     for i in range(args.warmup + args.steps):
         dt, cores = cpu_block_baseline(cfg, L, ctx_len)
-        if i >= args.warmup:
+        if i == 0 and dt > 8.0:
+            warm = min(warm, 1)          # a >8 s sample: one untimed warm-up is all the budget allows
+        if i >= warm:
             times.append(dt)
-        if sum(times) > 150:   # keep the whole arm within a few minutes
+        if len(times) >= args.steps or (times and time.perf_counter() - t_start > budget_s):
             break
     t_blk = sum(times) / len(times)
     step_s = t_blk * cfg["num_layers"] * 2            # one denoise step = 2 forwards x num_layers blocks (+ negligible rest)
@@ -273,16 +278,9 @@ def main():
         b.record()
         torch.cuda.synchronize()
         e2e_ms = a.elapsed_time(b) / args.steps
-        # how much of the e2e step is the per-call re-projection of the prompt (embedding MLP + 30 layers of K/V)
-        a.record()
-        for i in range(4):
-            eng.context_state(ctx_pos_host.to(dev, non_blocking=True))
-        b.record()
-        torch.cuda.synchronize()
-        ctx_ms = a.elapsed_time(b) / 4
         h2d = lat_host.numel() * 4 + 2 * ctx_pos_host.numel() * 4
         e2e = {"value": f / (CLIP_STEPS * e2e_ms / 1e3), "unit": "latent_frames/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4, "context_prep_ms_per_prompt": ctx_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4,
                "api": "diffsynth.pipelines.svi_video.model_fn_wan_video x2 + svi_cfg_euler_step, pinned host buffers"}
 
     if rank != 0:
@@ -296,8 +294,12 @@ def main():
     if attn_ms:
         a_ms = sum(attn_ms) / len(attn_ms)
         ach = attn_flops / (a_ms * 1e-3) / 1e12
+        traffic = None   # DRAM bytes per launch from the committed ncu --set full capture (single-GPU shape only)
+        tpath = os.path.join(ROOT, "profiles", "attn_traffic.json")
+        if sp is None and args.workload == "cfg2" and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("bytes_per_launch")
         roof = {"kernel": "attn_fwd_kernel (self-attention)", "bound": "tensor", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "launches_timed": len(attn_ms), "avg_ms": a_ms,
                 "share_of_step": sum(attn_ms) / ms}
     line = {"metric": "denoised latent frames/sec (81fx480p, 50 steps)", "value": value, "unit": "latent_frames/s",
