@@ -13,8 +13,6 @@
 // tensor pipe: while warpgroup 0 exponentiates S0(j+1), the tensor core runs PV1(j) and QK1(j+1).
 // Online softmax uses the lazy-rescale rule (O is only rescaled when a row max grows by > 2^8).
 // Replaces flash_attention(), reference wan_video_dit.py:116-147.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "../../include/svi_b200.h"
 
@@ -341,13 +339,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }  // namespace attn
 }  // namespace svi
 
-namespace svi {
-namespace attn2 {
-int launch(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
-           long long ldo, int Lq, int Lk, int num_heads, float scale, int accumulate, cudaStream_t stream);
-}
-}  // namespace svi
-
 extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V,
                             int64_t ldv, void* O, int64_t ldo, int32_t Lq, int32_t Lk,
                             int32_t num_heads, float scale, int32_t accumulate, void* stream) {
@@ -363,13 +354,6 @@ extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t l
   SVI_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) |
                 reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(O)) & 15) == 0,
               "svi_attn_fwd: pointers must be 16-byte aligned");
-  // Two kernels exist (profiles/README.md): this file's 128-row K/V tile kernel (product path: fewest MMAs and
-  // least shared-memory traffic) and the software-pipelined 64-row variant of attn2_tcgen05.cu, kept for the
-  // next round's 2-CTA work and selectable for A/B timing with SVI_ATTN_IMPL=v2.  Both measure ~1.16-1.18 PFLOP/s.
-  static const int use_v2 = []() { const char* e = getenv("SVI_ATTN_IMPL"); return (e && e[0] == 'v' && e[1] == '2') ? 1 : 0; }();
-  if (use_v2)
-    return svi::attn2::launch(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, num_heads, scale, accumulate,
-                              static_cast<cudaStream_t>(stream));
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_2d(&tq, Q, 2, (uint64_t)width, (uint64_t)Lq, (uint64_t)ldq * 2, 64, BQ);
   if (rc) return rc;

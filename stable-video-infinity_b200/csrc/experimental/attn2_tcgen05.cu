@@ -19,8 +19,8 @@
 //   warp 9          : tcgen05.mma issuer + TMEM owner
 #include <stdlib.h>
 
-#include "common.cuh"
-#include "../../include/svi_b200.h"
+#include "../common.cuh"
+#include "../../../include/svi_b200.h"
 
 namespace svi {
 namespace attn2 {

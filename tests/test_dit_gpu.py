@@ -109,3 +109,21 @@ def test_cfg1_1p3b_one_step_matches_oracle():
     # bars from SURVEY.md §7: emulated bf16-operand/fp32-residual design = 97.5 % inside, max 0.005;
     # the reference's own bf16 path = 44 % inside, max 0.042
     assert inside > 0.85 and mx < 0.042 and rel < 6e-3
+
+
+@pytest.mark.slow
+def test_14b_width_single_layer_matches_oracle():
+    """Wan2.1-I2V-14B geometry (d=5120, 40 heads, ffn 13824, image branch) with ONE layer at a small token count:
+    exercises the wide shapes of every kernel (N=15360 QKV, K=13824 FFN, LayerNorm over 5120, 40-head attention,
+    257-token image cross-attention with accumulate)."""
+    from oracle import wan_dit_oracle as O
+    cfg = dict(synth.CFG_I2V_14B, num_layers=1, text_dim=256)
+    sd = _sd(cfg, 11)
+    inp = synth.make_dit_inputs(cfg, 2, 12, 20, seed=11, ctx_len=77)
+    ts = torch.tensor([640.0])
+    ref = O.dit_forward(sd, cfg, inp["x"], ts, inp["context"], inp["clip_feature"], inp["y"])
+    m = _build(cfg, sd)
+    out = m(inp["x"].cuda(), ts, inp["context"].cuda(), clip_feature=inp["clip_feature"].cuda(), y=inp["y"].cuda()).float().cpu()
+    inside, mx, rel = _stats(out, ref)
+    print(f"14B-width 1 layer: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
+    assert inside > 0.80 and mx < 0.03 and rel < 4e-3
