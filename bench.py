@@ -153,6 +153,35 @@ def run_reference_arm(args, wl_name, cfg, f, h, w, ctx_len, desc):
     print(json.dumps(line), flush=True)
 
 
+def vae_clip_leg(dev, f, h, w, ms_per_step):
+    """Times WanVideoVAE.decode / .encode (public API, random-init weights) at the bench clip shape and folds them into a
+    whole-clip figure: one SVI clip = encode(81 frames) + 50 CFG steps + decode(21 latent frames)."""
+    from diffsynth.models.wan_video_vae import WanVideoVAE
+    from tools import synth_vae
+    vae = WanVideoVAE().eval()
+    vae.load_state_dict(synth_vae.make_vae_state_dict(seed=0))
+    vae.to(dev)
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(1, 16, f, h, w, generator=g).to(dev)
+    frames = 4 * (f - 1) + 1
+    video = (torch.rand(3, frames, 8 * h, 8 * w, generator=g) * 2 - 1).to(dev)
+    out = {}
+    for name, fn in (("decode", lambda: vae.decode(z, device=dev)), ("encode", lambda: vae.encode([video], device=dev))):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        out[name] = a.elapsed_time(b)
+    clip_s = (out["encode"] + out["decode"] + CLIP_STEPS * ms_per_step) / 1e3
+    return {"vae_decode_ms": out["decode"], "vae_encode_ms": out["encode"], "denoise_s": CLIP_STEPS * ms_per_step / 1e3,
+            "clip_s": clip_s, "clips_per_hour": 3600.0 / clip_s, "pixel_frames_per_s": frames / clip_s,
+            "note": "81f x 480x832 clip = VAE encode + 50 CFG steps (extrapolated from the timed steps) + VAE decode; "
+                    "text/CLIP encoders excluded (out of scope, SURVEY.md §8f.1)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,6 +191,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the clip-boundary VAE leg (decode 21->81 frames, encode 81 frames)")
     args = ap.parse_args()
     from tools import synth
     cfg_name, f, h, w, ctx_len, desc = WORKLOADS[args.workload]
@@ -283,6 +313,12 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4,
                "api": "diffsynth.pipelines.svi_video.model_fn_wan_video x2 + svi_cfg_euler_step, pinned host buffers"}
 
+    # ---- clip leg ("for cfg-4, end-to-end clips/hour with VAE included"): the VAE work one SVI clip adds
+    # around the 50 denoising steps — encode of the 81-frame conditioning video and decode of the 21 denoised latent frames.
+    clip = None
+    if not args.no_vae and world == 1 and args.workload == "cfg2":
+        clip = vae_clip_leg(dev, f, h, w, ms_per_step)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -311,7 +347,7 @@ def main():
                        "numerics": "bf16 operands, fp32 accumulate/residual/norm/softmax"},
             "dit_tflops": flops_step / (ms_per_step * 1e-3) / 1e12,
             "dit_tflops_frac_of_peak": flops_step / (ms_per_step * 1e-3) / 1e12 / (peak * world),
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e, "clip": clip}
     if not args.no_cpu_baseline and world == 1:
         t_blk, cores = cpu_block_baseline(cfg, L, ctx_len)
         step_s = t_blk * cfg["num_layers"] * 2

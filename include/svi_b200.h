@@ -79,6 +79,37 @@ int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const v
                  int32_t accumulate, void* stream);
 
 /*
+ * ---- sequence-parallel self-attention: K|V exchange over NVLink peer memory -----------------------------------
+ * Replaces the xfuser wiring of the reference's multi-GPU path: usp_attn_forward,
+ * diffsynth/distributed/xdit_context_parallel.py:108-129 (xFuserLongContextAttention = Ulysses all-to-all / ring
+ * attention over NCCL) and the process-group setup in pipelines/svi_video.py:266-275.
+ *
+ * svi_sp_alloc   cudaMalloc (zero-filled) of a symmetric buffer + its 64-byte CUDA IPC handle; the caller ships the
+ *                handle to the peer processes (torch.distributed all_gather_object) which map it with svi_sp_open.
+ * svi_sp_push    on `stream`: for every peer i, copy `bytes` from src (this rank's rows of its own buffer) to
+ *                peer_dst[i] (the same rows inside peer i's buffer) with the copy engine, then copy the 4-byte word
+ *                at `epoch_word` (device memory holding this layer's epoch number) into peer_flag[i] (this rank's
+ *                slot in peer i's flag array).  Stream order makes the flag land after the rows.
+ * svi_attn_fwd_sp  svi_attn_fwd over the full [Lk, *] K / V buffers of this GPU where rows
+ *                [c*kv_chunk_rows, (c+1)*kv_chunk_rows) are produced by rank c: the K/V stream starts on the local
+ *                chunk kv_self_chunk and the TMA producer waits for kv_flags[c] == kv_epoch (ld.acquire.sys) before
+ *                the first tile that touches chunk c, so the push of the remote rows overlaps the attention math.
+ *                kv_flags: device uint32[n_chunks] inside this rank's symmetric allocation.
+ * Flags are compared for equality: the caller alternates two buffers/flag arrays by layer parity and numbers the
+ * launches 1,2,3,... so a flag cannot advance past the epoch a consumer still waits for.
+ */
+int svi_sp_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int svi_sp_free(void* ptr);
+int svi_sp_open(const unsigned char* handle64, void** peer_ptr);
+int svi_sp_close(void* peer_ptr);
+int svi_sp_push(const void* src, void* const* peer_dst, void* const* peer_flag, int32_t n_peers, size_t bytes,
+                const void* epoch_word, void* stream);
+int svi_attn_fwd_sp(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                    void* O, int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale,
+                    const void* kv_flags, uint32_t kv_epoch, int32_t kv_chunk_rows, int32_t kv_self_chunk,
+                    void* stream);
+
+/*
  * y[m,:] = LayerNorm(x[m,:]; eps, no affine unless gamma/beta) * (1 + scale[:]) + shift[:]  -> bf16.
  * x f32 [M, D]; gamma/beta/scale/shift f32 [D] or NULL.  D % 8 == 0, D <= 8192.
  * Replaces nn.LayerNorm + modulate(): wan_video_dit.py:150-151,331-333,358,368-372,401-403.

@@ -61,7 +61,36 @@ struct Params {
   int Lq, Lk;
   float scale_log2;  // softmax scale * log2(e)
   int accumulate;
+  // sequence-parallel K/V stream (sp_exchange.cu); kv_flags == nullptr: plain attention
+  const uint32_t* kv_flags;  // [n_chunks] arrival flag of each source rank's rows, written by that rank's push
+  uint32_t kv_epoch;         // value a flag holds once the rows of this launch have landed
+  int kv_chunk_rows;         // rows owned by each rank
+  int kv_self_chunk;         // this rank's chunk: produced locally, never waited for
+  int kv_first_tile;         // KV tile the stream starts on (first tile fully inside the local chunk)
 };
+
+// KV tile visited at iteration j: the stream starts on the rank's own rows and wraps around
+__device__ __forceinline__ int kv_tile_at(int j, int first_tile, int n_kv) {
+  const int t = j + first_tile;
+  return t >= n_kv ? t - n_kv : t;
+}
+
+// Producer side of the K/V exchange: block until the rows of `chunk` have been pushed into this GPU's buffer.
+__device__ __forceinline__ void wait_kv_chunk(const uint32_t* flags, int chunk, uint32_t epoch) {
+  const uint32_t* f = flags + chunk;
+  uint32_t v;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v == epoch) break;
+    __nanosleep(64);
+    if (++spins > (1u << 25)) {   // > 2 s: a peer died or the protocol is broken -> visible error, not a hang
+      printf("svi: K/V exchange timeout block(%d,%d) chunk %d flag %u want %u\n", blockIdx.x, blockIdx.y, chunk, v, epoch);
+      __trap();
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");   // later TMA (async proxy) reads see the pushed rows
+}
 
 // 10 warps over 4 SM sub-partitions put 3 warps on one 16K-register partition: 168 registers/thread is the ceiling
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -130,14 +159,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tma_load_2d(dst + HALF_BYTES, m, bar, col0 + 64, row);
       };
       load_tile(smem_q, &tmap_q, &q_full[0], q_row0);
+      int landed = p.kv_self_chunk;   // most recent remote chunk known to be present (chunks are visited in runs)
       for (int j = 0; j < n_kv; ++j) {
         const int s = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
+        const int row = kv_tile_at(j, p.kv_first_tile, n_kv) * BKV;
+        if (p.kv_flags) {
+          const int c0 = row / p.kv_chunk_rows;
+          const int c1 = (min(row + BKV, p.Lk) - 1) / p.kv_chunk_rows;
+          for (int c = c0; c <= c1; ++c) {
+            if (c == p.kv_self_chunk || c == landed) continue;
+            wait_kv_chunk(p.kv_flags, c, p.kv_epoch);
+            landed = c;
+          }
+        }
         mbar_wait(&k_empty[s], ph ^ 1);
-        load_tile(smem_k + s * TILE_BYTES, &tmap_k, &k_full[s], j * BKV);
+        load_tile(smem_k + s * TILE_BYTES, &tmap_k, &k_full[s], row);
         if (j == 0) load_tile(smem_q + TILE_BYTES, &tmap_q, &q_full[1], q_row0 + BQ);
         mbar_wait(&v_empty[s], ph ^ 1);
-        load_tile(smem_v + s * TILE_BYTES, &tmap_v, &v_full[s], j * BKV);
+        load_tile(smem_v + s * TILE_BYTES, &tmap_v, &v_full[s], row);
       }
     }
   } else if (warp == 9) {
@@ -208,7 +248,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
-      const int limit = p.Lk - j * BKV;  // number of valid key columns in this tile (>=128: all)
+      const int limit = p.Lk - kv_tile_at(j, p.kv_first_tile, n_kv) * BKV;  // valid key columns in this tile (>=128: all)
       // single pass: the whole 128-wide S row of this thread lives in registers (4 TMEM loads in flight, one wait)
       uint32_t sr[4][32];
       tmem_ld32(tS + 0, sr[0]);
@@ -339,21 +379,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }  // namespace attn
 }  // namespace svi
 
-extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V,
-                            int64_t ldv, void* O, int64_t ldo, int32_t Lq, int32_t Lk,
-                            int32_t num_heads, float scale, int32_t accumulate, void* stream) {
-  using namespace svi;
-  using namespace svi::attn;
-  SVI_REQUIRE(Q && K && V && O, "svi_attn_fwd: null pointer");
-  SVI_REQUIRE(Lq > 0 && Lk > 0 && num_heads > 0, "svi_attn_fwd: Lq, Lk, num_heads must be positive");
+namespace svi {
+namespace attn {
+
+static int launch_attn(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                       int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale, int32_t accumulate,
+                       const uint32_t* kv_flags, uint32_t kv_epoch, int kv_chunk_rows, int kv_self_chunk, void* stream,
+                       const char* who) {
+  SVI_REQUIRE(Q && K && V && O, "%s: null pointer", who);
+  SVI_REQUIRE(Lq > 0 && Lk > 0 && num_heads > 0, "%s: Lq, Lk, num_heads must be positive", who);
   const int64_t width = (int64_t)num_heads * HD;
   SVI_REQUIRE(ldq >= width && ldk >= width && ldv >= width && ldo >= width,
-              "svi_attn_fwd: leading dimensions must be >= num_heads*128");
+              "%s: leading dimensions must be >= num_heads*128", who);
   SVI_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
-              "svi_attn_fwd: leading dimensions must be multiples of 8 elements");
+              "%s: leading dimensions must be multiples of 8 elements", who);
   SVI_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) |
                 reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(O)) & 15) == 0,
-              "svi_attn_fwd: pointers must be 16-byte aligned");
+              "%s: pointers must be 16-byte aligned", who);
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_2d(&tq, Q, 2, (uint64_t)width, (uint64_t)Lq, (uint64_t)ldq * 2, 64, BQ);
   if (rc) return rc;
@@ -367,7 +409,7 @@ extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t l
     cudaError_t ce = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           SMEM_BYTES);
     if (ce != cudaSuccess) {
-      set_last_error("svi_attn_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce));
+      set_last_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(ce));
       return SVI_ERR_LAUNCH;
     }
     attr_set = true;
@@ -379,8 +421,41 @@ extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t l
   p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.accumulate = accumulate;
+  p.kv_flags = kv_flags;
+  p.kv_epoch = kv_epoch;
+  p.kv_chunk_rows = kv_chunk_rows;
+  p.kv_self_chunk = kv_self_chunk;
+  p.kv_first_tile = 0;
+  if (kv_flags) {
+    const int n_kv = (Lk + BKV - 1) / BKV;
+    const int first = (int)(((int64_t)kv_self_chunk * kv_chunk_rows + BKV - 1) / BKV);
+    p.kv_first_tile = first >= n_kv ? 0 : first;
+  }
   dim3 grid((Lq + 2 * BQ - 1) / (2 * BQ), num_heads);
   attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
-  SVI_CUDA_LAUNCH_CHECK("svi_attn_fwd");
+  SVI_CUDA_LAUNCH_CHECK(who);
   return SVI_OK;
+}
+
+}  // namespace attn
+}  // namespace svi
+
+extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V,
+                            int64_t ldv, void* O, int64_t ldo, int32_t Lq, int32_t Lk,
+                            int32_t num_heads, float scale, int32_t accumulate, void* stream) {
+  return svi::attn::launch_attn(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, num_heads, scale, accumulate, nullptr, 0, 1, 0,
+                                stream, "svi_attn_fwd");
+}
+
+extern "C" int svi_attn_fwd_sp(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V,
+                               int64_t ldv, void* O, int64_t ldo, int32_t Lq, int32_t Lk,
+                               int32_t num_heads, float scale, const void* kv_flags, uint32_t kv_epoch,
+                               int32_t kv_chunk_rows, int32_t kv_self_chunk, void* stream) {
+  using namespace svi;
+  SVI_REQUIRE(kv_flags, "svi_attn_fwd_sp: kv_flags is null");
+  SVI_REQUIRE(kv_chunk_rows >= 128 && kv_self_chunk >= 0 && (int64_t)kv_self_chunk * kv_chunk_rows < Lk,
+              "svi_attn_fwd_sp: need kv_chunk_rows >= 128 and the local chunk inside [0, Lk)");
+  return svi::attn::launch_attn(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, num_heads, scale, 0,
+                                static_cast<const uint32_t*>(kv_flags), kv_epoch, kv_chunk_rows, kv_self_chunk, stream,
+                                "svi_attn_fwd_sp");
 }

@@ -88,6 +88,71 @@ layernorm_modulate_kernel(const float* __restrict__ x, int D, float eps, const f
   }
 }
 
+
+// Warp-per-row variant for D <= 2048 (the 1.3B model, D = 1536): no block barriers, the whole row is fetched with up
+// to 16 independent 16-byte loads per lane before anything is reduced (memory-level parallelism is what an HBM-bound
+// 6 KB-per-row kernel needs; the block-per-row version above reached only ~2.7 TB/s, profiles/README.md).
+constexpr int LNW_WARPS = 8;
+constexpr int LNW_MAX_VEC = 16;  // float4 per lane -> D <= 2048
+
+__global__ void __launch_bounds__(LNW_WARPS * 32)
+layernorm_modulate_warp_kernel(const float* __restrict__ x, int M, int D, float eps, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ scale,
+                               const float* __restrict__ shift, __nv_bfloat16* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * LNW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  const int nvec = D >> 2;
+  float4 v[LNW_MAX_VEC];
+#pragma unroll
+  for (int i = 0; i < LNW_MAX_VEC; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) v[i] = __ldcs(xr + idx);   // streaming: the fp32 residual row is not re-read soon
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LNW_MAX_VEC; ++i)
+    if (lane + i * 32 < nvec) s += v[i].x + v[i].y + v[i].z + v[i].w;
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LNW_MAX_VEC; ++i)
+    if (lane + i * 32 < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + row * D);
+#pragma unroll
+  for (int i = 0; i < LNW_MAX_VEC; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      float o[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+      if (gamma) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+        o[0] *= g.x; o[1] *= g.y; o[2] *= g.z; o[3] *= g.w;
+      }
+      if (beta) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+        o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+      }
+      if (scale) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + idx);
+        o[0] *= 1.f + sc.x; o[1] *= 1.f + sc.y; o[2] *= 1.f + sc.z; o[3] *= 1.f + sc.w;
+      }
+      if (shift) {
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + idx);
+        o[0] += sh.x; o[1] += sh.y; o[2] += sh.z; o[3] += sh.w;
+      }
+      uint2 pk;
+      pk.x = pack_bf16x2(o[0], o[1]);
+      pk.y = pack_bf16x2(o[2], o[3]);
+      yr[idx] = pk;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // full-width RMSNorm (row sum of squares supplied by the GEMM epilogue) + interleaved-pair RoPE,
 // in place on bf16.  One thread = 8 consecutive columns (4 rotation pairs).
@@ -252,8 +317,12 @@ extern "C" int svi_layernorm_modulate(const float* x, int32_t M, int32_t D, floa
               "svi_layernorm_modulate: need M>0, D %% 8 == 0, D <= 8192 (M=%d D=%d)", M, D);
   SVI_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0,
               "svi_layernorm_modulate: alignment");
-  layernorm_modulate_kernel<<<M, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, D, eps, gamma, beta, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16));
+  if (D <= 128 * LNW_MAX_VEC)
+    layernorm_modulate_warp_kernel<<<(M + LNW_WARPS - 1) / LNW_WARPS, LNW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, M, D, eps, gamma, beta, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16));
+  else
+    layernorm_modulate_kernel<<<M, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, D, eps, gamma, beta, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16));
   SVI_CUDA_LAUNCH_CHECK("svi_layernorm_modulate");
   return SVI_OK;
 }

@@ -7,6 +7,7 @@
 // Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, double buffered so
 // the epilogue of tile i overlaps the MMAs of tile i+1), and the static persistent tile loop.
 // Replaces every F.linear of the reference's DiT (see include/svi_b200.h for the line map).
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/svi_b200.h"
 
@@ -239,6 +240,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }  // namespace gemm
 }  // namespace svi
 
+namespace svi { namespace gemm2 {
+int launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const svi_gemm_epilogue* e,
+           cudaStream_t stream);
+} }
+
 extern "C" int svi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M,
                              int32_t N, int32_t K, const svi_gemm_epilogue* e, void* stream) {
   using namespace svi;
@@ -262,6 +268,11 @@ extern "C" int svi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   if (e->sumsq)
     SVI_REQUIRE(e->sumsq_groups > 0 && e->sumsq_group_cols > 0 && e->sumsq_group_cols % 32 == 0,
                 "svi_gemm_bf16: sumsq_group_cols must be a positive multiple of 32");
+
+  // More than one 128-row tile of A: CTA pairs (256x256 tiles, gemm2_tcgen05.cu; 12-13 % faster on the DiT shapes
+  // because each SM pulls a third less operand data through L2).  M <= 128 (time/text embeddings, LoRA merges of
+  // narrow matrices) would leave the odd CTA of every pair idle, so those stay on the single-CTA kernel below.
+  if (M > BM) return svi::gemm2::launch(A, lda, W, ldw, M, N, K, e, static_cast<cudaStream_t>(stream));
 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);

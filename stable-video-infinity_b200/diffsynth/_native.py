@@ -49,6 +49,12 @@ SIGNATURES = {
     "svi_sm_count": (_i32, []),
     "svi_gemm_bf16": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _c.POINTER(GemmEpilogue), _vp]),
     "svi_attn_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp]),
+    "svi_attn_fwd_sp": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _c.c_uint32, _i32, _i32, _vp]),
+    "svi_sp_alloc": (_i32, [_c.c_size_t, _c.POINTER(_vp), _c.c_char_p]),
+    "svi_sp_free": (_i32, [_vp]),
+    "svi_sp_open": (_i32, [_c.c_char_p, _c.POINTER(_vp)]),
+    "svi_sp_close": (_i32, [_vp]),
+    "svi_sp_push": (_i32, [_vp, _c.POINTER(_vp), _c.POINTER(_vp), _i32, _c.c_size_t, _vp, _vp]),
     "svi_layernorm_modulate": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "svi_rmsnorm_rope": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _i32, _vp]),
     "svi_patchify_gather": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
@@ -164,6 +170,59 @@ def attention(q, k, v, out, num_heads, scale=None, accumulate=False):
                              q.shape[0], k.shape[0], num_heads, float(scale), int(bool(accumulate)), _stream())
     _check(rc, "svi_attn_fwd")
     return out
+
+
+def attention_sp(q, k, v, out, num_heads, kv_flags, kv_epoch, kv_chunk_rows, kv_self_chunk, scale=None):
+    """Self-attention over the rank's full K|V buffer whose remote rows are still being pushed by the peers
+    (svi_attn_fwd_sp): kv_flags int32 [n_chunks] device tensor inside the symmetric allocation."""
+    ldq, ldk, ldv, ldo = (_rowmajor(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")))
+    if scale is None:
+        scale = 128 ** -0.5
+    rc = load().svi_attn_fwd_sp(_ptr(q, torch.bfloat16, "q"), ldq, _ptr(k, torch.bfloat16, "k"), ldk,
+                                _ptr(v, torch.bfloat16, "v"), ldv, _ptr(out, torch.bfloat16, "out"), ldo,
+                                q.shape[0], k.shape[0], num_heads, float(scale), _ptr(kv_flags, torch.int32, "kv_flags"),
+                                int(kv_epoch) & 0xFFFFFFFF, int(kv_chunk_rows), int(kv_self_chunk), _stream())
+    _check(rc, "svi_attn_fwd_sp")
+    return out
+
+
+class _RawCuda:
+    """Exposes a raw device allocation to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def sp_alloc(nbytes, device):
+    """Symmetric (peer-mappable) allocation: returns (ptr:int, handle:bytes[64], uint8 tensor view of it)."""
+    ptr = _vp()
+    handle = ctypes.create_string_buffer(64)
+    _check(load().svi_sp_alloc(nbytes, ctypes.byref(ptr), handle), "svi_sp_alloc")
+    view = torch.as_tensor(_RawCuda(ptr.value, nbytes), device=device)
+    return ptr.value, handle.raw, view
+
+
+def sp_free(ptr):
+    _check(load().svi_sp_free(_vp(ptr)), "svi_sp_free")
+
+
+def sp_open(handle):
+    ptr = _vp()
+    _check(load().svi_sp_open(handle, ctypes.byref(ptr)), "svi_sp_open")
+    return ptr.value
+
+
+def sp_close(ptr):
+    _check(load().svi_sp_close(_vp(ptr)), "svi_sp_close")
+
+
+def sp_push(src_ptr, peer_dst, peer_flag, nbytes, epoch_word_ptr, stream):
+    """Copy-engine push of this rank's rows + flag word to every peer on `stream` (a torch.cuda.Stream)."""
+    n = len(peer_dst)
+    arr = _vp * n
+    rc = load().svi_sp_push(_vp(src_ptr), arr(*peer_dst), arr(*peer_flag), n, nbytes, _vp(epoch_word_ptr),
+                            _vp(stream.cuda_stream))
+    _check(rc, "svi_sp_push")
 
 
 def layernorm_modulate(x, out, eps, gamma=None, beta=None, scale=None, shift=None):
