@@ -191,6 +191,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cfg-parallel", action="store_true", help="N>1: split only the token axis (sp = N); for A/B runs")
+    ap.add_argument("--breakdown", action="store_true", help="after the timed run, one extra step with every kernel call "
+                    "bracketed by CUDA events; per-call-type sums go to stderr (not part of the JSON line)")
     ap.add_argument("--no-vae", action="store_true", help="skip the clip-boundary VAE leg (decode 21->81 frames, encode 81 frames)")
     args = ap.parse_args()
     from tools import synth
@@ -213,7 +216,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         from diffsynth.distributed.sequence_parallel import init_sp_groups
-        sp = init_sp_groups(world, rank, cfg_parallel=True)
+        sp = init_sp_groups(world, rank, cfg_parallel=not args.no_cfg_parallel)
         plan = sp.describe()
     from diffsynth import _native as nv
     from diffsynth.pipelines.svi_video import model_fn_wan_video
@@ -313,6 +316,18 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4,
                "api": "diffsynth.pipelines.svi_video.model_fn_wan_video x2 + svi_cfg_euler_step, pinned host buffers"}
 
+    if args.breakdown and world == 1:
+        eng.k.events = []
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        step(0)
+        b1.record()
+        bd = eng.k.breakdown()
+        tot = b0.elapsed_time(b1)
+        print(f"breakdown of one step ({tot:.1f} ms wall, {sum(v[0] for v in bd.values()):.1f} ms inside kernels)", file=sys.stderr)
+        for tag, (ms_, n) in sorted(bd.items(), key=lambda kv: -kv[1][0]):
+            print(f"  {ms_:9.2f} ms {100 * ms_ / tot:6.2f}%  n={n:4d}  avg={1e3 * ms_ / n:9.1f} us  {tag}", file=sys.stderr)
+
     # ---- clip leg ("for cfg-4, end-to-end clips/hour with VAE included"): the VAE work one SVI clip adds
     # around the 50 denoising steps — encode of the 81-frame conditioning video and decode of the 21 denoised latent frames.
     clip = None
@@ -343,6 +358,8 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "tokens": L, "text_tokens": ctx_len,
                        "cfg_scale": CFG_SCALE, "clip_steps": CLIP_STEPS, "parallelism": plan,
+                       "kv_exchange": None if sp is None or sp.sp_size == 1 else
+                       ("NVLink peer push (copy engine) consumed by flag-gated attention" if sp._peer is not None else "NCCL all-gather"),
                        "l2_policy": "inputs larger than L2 (weights 2.8 GB + activations per step)",
                        "numerics": "bf16 operands, fp32 accumulate/residual/norm/softmax"},
             "dit_tflops": flops_step / (ms_per_step * 1e-3) / 1e12,

@@ -72,11 +72,20 @@ int svi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_
  * Q: [Lq, ldq] bf16 with head h at columns [h*128, h*128+128); K, V likewise with ldk / ldv;
  * O: [Lq, ldo].  Any Lq, Lk >= 1 (ragged tails masked).  accumulate != 0: O += result
  * (used for the image branch of cross-attention, wan_video_dit.py:300-301).
+ * workspace (optional, 16-byte aligned device memory of workspace_bytes, may be NULL / 0): lets the launch cut the
+ * (head, Q-tile-pair) units of its last, partly filled wave of CTAs into K/V slices that are merged by a second
+ * kernel (log-sum-exp merge), so all SMs stay busy; svi_attn_workspace_bytes() returns the size that allows every
+ * plan.  The library never allocates.  Results are the same function of the inputs either way (fp32 merge).
  * Replaces flash_attention(), wan_video_dit.py:116-147 (the single attention entry point).
  */
 int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
                  void* O, int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale,
-                 int32_t accumulate, void* stream);
+                 int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+size_t svi_attn_workspace_bytes(int32_t Lq, int32_t Lk, int32_t num_heads);
+/* The launch plan svi_attn_fwd uses (pure host function, no device needed): `units` = num_heads * ceil(Lq/256) equal
+ * CTAs, kv_tiles = ceil(Lk/128), on `sms` SMs with a workspace of workspace_bytes -> units [0, n_full) run whole, the
+ * rest are cut into `split` K/V slices each (split == 1: nothing is sliced). */
+void svi_attn_plan(int32_t units, int32_t kv_tiles, int32_t sms, size_t workspace_bytes, int32_t* n_full, int32_t* split);
 
 /*
  * ---- sequence-parallel self-attention: K|V exchange over NVLink peer memory -----------------------------------
@@ -107,7 +116,7 @@ int svi_sp_push(const void* src, void* const* peer_dst, void* const* peer_flag, 
 int svi_attn_fwd_sp(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
                     void* O, int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale,
                     const void* kv_flags, uint32_t kv_epoch, int32_t kv_chunk_rows, int32_t kv_self_chunk,
-                    void* stream);
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * y[m,:] = LayerNorm(x[m,:]; eps, no affine unless gamma/beta) * (1 + scale[:]) + shift[:]  -> bf16.

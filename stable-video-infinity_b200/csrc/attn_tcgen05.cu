@@ -12,6 +12,11 @@
 // The issue order  PV_i(j) ; QK_i(j+1)  per tile ping-pongs the two softmax warpgroups against the
 // tensor pipe: while warpgroup 0 exponentiates S0(j+1), the tensor core runs PV1(j) and QK1(j+1).
 // Online softmax uses the lazy-rescale rule (O is only rescaled when a row max grows by > 2^8).
+//
+// Work units are (head, pair of Q tiles).  The launch plan (plan_split, host side) runs `n_full` units whole and cuts
+// each of the remaining ones into `split` slices of the K/V stream, so the last, partly filled wave of CTAs is spread
+// over all SMs; sliced units leave (unnormalised O, row max, row sum) in a workspace and attn_merge_kernel combines
+// them.  Without a workspace every unit runs whole.
 // Replaces flash_attention(), reference wan_video_dit.py:116-147.
 #include "common.cuh"
 #include "../../include/svi_b200.h"
@@ -67,6 +72,12 @@ struct Params {
   int kv_chunk_rows;         // rows owned by each rank
   int kv_self_chunk;         // this rank's chunk: produced locally, never waited for
   int kv_first_tile;         // KV tile the stream starts on (first tile fully inside the local chunk)
+  // launch plan: units [0, n_full) whole; unit n_full + t/split gets slice t%split of the K/V stream
+  int n_qpairs;              // Q-tile pairs per head
+  int n_full;
+  int split;
+  float* ws_o;               // [slices][256 rows][128] unnormalised partial O
+  float2* ws_ml;             // [slices][256 rows] (row max in scaled log2 units, row sum)
 };
 
 // KV tile visited at iteration j: the stream starts on the rank's own rows and wraps around
@@ -116,9 +127,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q_row0 = blockIdx.x * (2 * BQ);
-  const int n_kv = (p.Lk + BKV - 1) / BKV;
+  const int n_kv_total = (p.Lk + BKV - 1) / BKV;
+  int unit = blockIdx.x, j_begin = 0, n_kv = n_kv_total;   // n_kv: K/V tiles THIS CTA streams, starting at j_begin
+  const int slice_slot = (int)blockIdx.x - p.n_full;        // >= 0: this CTA computes one slice of a unit
+  if (slice_slot >= 0) {
+    unit = p.n_full + slice_slot / p.split;
+    const int sl = slice_slot % p.split;
+    j_begin = (int)((long long)n_kv_total * sl / p.split);
+    n_kv = (int)((long long)n_kv_total * (sl + 1) / p.split) - j_begin;
+  }
+  const int head = unit / p.n_qpairs;
+  const int q_row0 = (unit % p.n_qpairs) * (2 * BQ);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -163,7 +182,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int j = 0; j < n_kv; ++j) {
         const int s = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
-        const int row = kv_tile_at(j, p.kv_first_tile, n_kv) * BKV;
+        const int row = kv_tile_at(j_begin + j, p.kv_first_tile, n_kv_total) * BKV;
         if (p.kv_flags) {
           const int c0 = row / p.kv_chunk_rows;
           const int c1 = (min(row + BKV, p.Lk) - 1) / p.kv_chunk_rows;
@@ -248,7 +267,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
-      const int limit = p.Lk - kv_tile_at(j, p.kv_first_tile, n_kv) * BKV;  // valid key columns in this tile (>=128: all)
+      const int limit = p.Lk - kv_tile_at(j_begin + j, p.kv_first_tile, n_kv_total) * BKV;  // valid key columns (>=128: all)
       // single pass: the whole 128-wide S row of this thread lives in registers (4 TMEM loads in flight, one wait)
       uint32_t sr[4][32];
       tmem_ld32(tS + 0, sr[0]);
@@ -333,6 +352,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_wait(&o_full[i], 0);
     tc_fence_after();
     const int row = q_row0 + i * BQ + quad * 32 + lane;
+    if (slice_slot >= 0 && p.split > 1) {
+      // one slice of the K/V stream: leave (O, m, l) for attn_merge_kernel
+      const long long prow = (long long)slice_slot * (2 * BQ) + i * BQ + quad * 32 + lane;
+      float4* dst = reinterpret_cast<float4*>(p.ws_o + prow * HD);
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tO + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          dst[cc * 8 + g] = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                        __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+      }
+      p.ws_ml[prow] = make_float2(m_cur, l);
+    } else {
     const float inv_l = 1.0f / l;
     __nv_bfloat16* orow = p.O + (long long)row * p.ldo + head * HD;
 #pragma unroll 1
@@ -366,6 +401,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
     }
+    }
   }
 
   tc_fence_before();
@@ -382,10 +418,71 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 namespace svi {
 namespace attn {
 
+constexpr size_t SLICE_BYTES = (size_t)2 * BQ * HD * 4 + (size_t)2 * BQ * 8;   // partial O + (m, l) of one slice
+constexpr int MAX_SPLIT = 8;
+constexpr int MIN_SLICE_TILES = 8;   // a slice shorter than this is dominated by its prologue / epilogue
+
+// Combines the slices of the sliced units: one warp per Q row (lane = 4 output columns), 8 rows per block.
+__global__ void __launch_bounds__(256)
+attn_merge_kernel(const float* __restrict__ ws_o, const float2* __restrict__ ws_ml, int split, int n_full, int n_qpairs,
+                  int Lq, __nv_bfloat16* __restrict__ O, long long ldo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x / (2 * BQ / 8);                       // sliced unit
+  const int r = (blockIdx.x % (2 * BQ / 8)) * 8 + warp;          // row inside the unit's 256
+  const int unit = n_full + t;
+  const int head = unit / n_qpairs;
+  const int row = (unit % n_qpairs) * (2 * BQ) + r;
+  if (row >= Lq) return;
+  float m = -INFINITY;
+  for (int s = 0; s < split; ++s) m = fmaxf(m, ws_ml[((long long)t * split + s) * (2 * BQ) + r].x);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float l = 0.f;
+  for (int s = 0; s < split; ++s) {
+    const long long prow = ((long long)t * split + s) * (2 * BQ) + r;
+    const float2 ml = ws_ml[prow];
+    const float w = ex2(ml.x - m);
+    const float4 o = __ldcs(reinterpret_cast<const float4*>(ws_o + prow * HD) + lane);
+    acc.x += o.x * w; acc.y += o.y * w; acc.z += o.z * w; acc.w += o.w * w;
+    l += ml.y * w;
+  }
+  const float inv = 1.0f / l;
+  uint2 pk;
+  pk.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+  pk.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+  *reinterpret_cast<uint2*>(O + (long long)row * ldo + head * HD + lane * 4) = pk;
+}
+
+// Launch plan: `units` equal CTAs on `sms` SMs cost ceil(units/sms) rounds.  Running r rounds of whole units and cutting
+// the remaining t units into S slices costs r + ceil(t*S/sms)/S rounds (+ a little for the merge).  Returns the cheapest
+// (n_full, split) that fits the workspace; (units, 1) when slicing does not pay.
+static void plan_split(int units, int n_kv, int sms, size_t ws_bytes, int* n_full, int* split) {
+  *n_full = units;
+  *split = 1;
+  if (ws_bytes < SLICE_BYTES || units <= 0) return;
+  const int rounds = units / sms;
+  double best = (double)((units + sms - 1) / sms);
+  const double need = best * 0.985;   // must save at least 1.5 %
+  for (int r = rounds; r >= 0 && r >= rounds - 1; --r) {
+    const int t = units - r * sms;
+    if (t <= 0) continue;
+    for (int S = 2; S <= MAX_SPLIT; ++S) {
+      if (n_kv / S < MIN_SLICE_TILES) break;
+      const long long slices = (long long)t * S;
+      if ((size_t)slices * SLICE_BYTES > ws_bytes) break;
+      const double cost = r + (double)((slices + sms - 1) / sms) / S + 0.04 * (double)t / sms + 0.01 * S;
+      if (cost < best && cost < need) {
+        best = cost;
+        *n_full = units - t;
+        *split = S;
+      }
+    }
+  }
+}
+
 static int launch_attn(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                        int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale, int32_t accumulate,
-                       const uint32_t* kv_flags, uint32_t kv_epoch, int kv_chunk_rows, int kv_self_chunk, void* stream,
-                       const char* who) {
+                       const uint32_t* kv_flags, uint32_t kv_epoch, int kv_chunk_rows, int kv_self_chunk, void* workspace,
+                       size_t workspace_bytes, void* stream, const char* who) {
   SVI_REQUIRE(Q && K && V && O, "%s: null pointer", who);
   SVI_REQUIRE(Lq > 0 && Lk > 0 && num_heads > 0, "%s: Lq, Lk, num_heads must be positive", who);
   const int64_t width = (int64_t)num_heads * HD;
@@ -431,9 +528,23 @@ static int launch_attn(const void* Q, int64_t ldq, const void* K, int64_t ldk, c
     const int first = (int)(((int64_t)kv_self_chunk * kv_chunk_rows + BKV - 1) / BKV);
     p.kv_first_tile = first >= n_kv ? 0 : first;
   }
-  dim3 grid((Lq + 2 * BQ - 1) / (2 * BQ), num_heads);
-  attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  p.n_qpairs = (Lq + 2 * BQ - 1) / (2 * BQ);
+  const int units = p.n_qpairs * num_heads;
+  const int sms = sm_count();
+  if (sms <= 0) return SVI_ERR_DRIVER;
+  SVI_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "%s: workspace must be 16-byte aligned", who);
+  plan_split(units, (Lk + BKV - 1) / BKV, sms, (workspace && !accumulate) ? workspace_bytes : 0, &p.n_full, &p.split);
+  const int n_sliced = units - p.n_full;
+  const long long slices = (long long)n_sliced * p.split;
+  p.ws_o = static_cast<float*>(workspace);
+  p.ws_ml = reinterpret_cast<float2*>(static_cast<char*>(workspace) + (size_t)slices * 2 * BQ * HD * 4);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  attn_fwd_kernel<<<(unsigned)(p.n_full + slices), NUM_THREADS, SMEM_BYTES, st>>>(tq, tk, tv, p);
   SVI_CUDA_LAUNCH_CHECK(who);
+  if (p.split > 1) {
+    attn_merge_kernel<<<n_sliced * (2 * BQ / 8), 256, 0, st>>>(p.ws_o, p.ws_ml, p.split, p.n_full, p.n_qpairs, Lq, p.O, ldo);
+    SVI_CUDA_LAUNCH_CHECK(who);
+  }
   return SVI_OK;
 }
 
@@ -442,20 +553,40 @@ static int launch_attn(const void* Q, int64_t ldq, const void* K, int64_t ldk, c
 
 extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V,
                             int64_t ldv, void* O, int64_t ldo, int32_t Lq, int32_t Lk,
-                            int32_t num_heads, float scale, int32_t accumulate, void* stream) {
+                            int32_t num_heads, float scale, int32_t accumulate, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   return svi::attn::launch_attn(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, num_heads, scale, accumulate, nullptr, 0, 1, 0,
-                                stream, "svi_attn_fwd");
+                                workspace, workspace_bytes, stream, "svi_attn_fwd");
+}
+
+extern "C" void svi_attn_plan(int32_t units, int32_t kv_tiles, int32_t sms, size_t workspace_bytes, int32_t* n_full,
+                              int32_t* split) {
+  int a = units, b = 1;
+  if (sms > 0) svi::attn::plan_split(units, kv_tiles, sms, workspace_bytes, &a, &b);
+  if (n_full) *n_full = a;
+  if (split) *split = b;
+}
+
+extern "C" size_t svi_attn_workspace_bytes(int32_t Lq, int32_t Lk, int32_t num_heads) {
+  // enough for the largest plan plan_split can choose: up to two rounds of units, each cut into MAX_SPLIT slices
+  using namespace svi::attn;
+  (void)Lk;
+  const long long units = (long long)((Lq + 2 * BQ - 1) / (2 * BQ)) * num_heads;
+  const int sms = svi::sm_count();
+  const long long tail = units < 2LL * sms ? units : 2LL * sms;
+  return (size_t)tail * MAX_SPLIT * SLICE_BYTES;
 }
 
 extern "C" int svi_attn_fwd_sp(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V,
                                int64_t ldv, void* O, int64_t ldo, int32_t Lq, int32_t Lk,
                                int32_t num_heads, float scale, const void* kv_flags, uint32_t kv_epoch,
-                               int32_t kv_chunk_rows, int32_t kv_self_chunk, void* stream) {
+                               int32_t kv_chunk_rows, int32_t kv_self_chunk, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   using namespace svi;
   SVI_REQUIRE(kv_flags, "svi_attn_fwd_sp: kv_flags is null");
   SVI_REQUIRE(kv_chunk_rows >= 128 && kv_self_chunk >= 0 && (int64_t)kv_self_chunk * kv_chunk_rows < Lk,
               "svi_attn_fwd_sp: need kv_chunk_rows >= 128 and the local chunk inside [0, Lk)");
   return svi::attn::launch_attn(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, num_heads, scale, 0,
-                                static_cast<const uint32_t*>(kv_flags), kv_epoch, kv_chunk_rows, kv_self_chunk, stream,
-                                "svi_attn_fwd_sp");
+                                static_cast<const uint32_t*>(kv_flags), kv_epoch, kv_chunk_rows, kv_self_chunk, workspace,
+                                workspace_bytes, stream, "svi_attn_fwd_sp");
 }

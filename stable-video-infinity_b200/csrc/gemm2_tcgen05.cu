@@ -8,7 +8,9 @@
 //
 //   cluster = 2 CTAs (same TPC).  Per CTA: warp 0 TMA producer (its A rows + its half of W; completion bytes of
 //   BOTH CTAs land on the even CTA's `full` barrier), warp 1 MMA issuer (even CTA only) + TMEM owner
-//   (cta_group::2 allocation), warps 2-5 epilogue of the CTA's own 128 accumulator rows.
+//   (cta_group::2 allocation), warps 2-9 epilogue of the CTA's own 128 accumulator rows (two warps per TMEM lane
+//   quadrant, 128 columns each: with activation / residual epilogues four warps took longer than the K loop of a
+//   K = 1536 tile and the tensor pipe waited for a free accumulator).
 //   `empty` / `tmem_full` are signalled in both CTAs by multicast commits; the odd CTA's epilogue releases the
 //   accumulator with a remote arrive on the even CTA's `tmem_empty`.
 // Epilogue and C-ABI contract are those of gemm_tcgen05.cu (shared entry point svi_gemm_bf16).
@@ -25,7 +27,8 @@ constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
 constexpr int B_STAGE_BYTES = BN_HALF * BK * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quadrant, each draining one 128-column half of the tile
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int STAGES = 6;       // 7 fit but measured 1-2 % slower
 constexpr int GROUP_M = 4;      // measured: 1..4 equal on M >> N shapes, 4..8 best on square ones
@@ -171,7 +174,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       for (uint32_t i = 0; i < 2; ++i) {
         mbar_init_a(bar(TMEM_FULL + i), 1);
-        mbar_init_a(bar(TMEM_EMPTY + i), 8);  // 4 epilogue warps x 2 CTAs (only the even CTA's copy is used)
+        mbar_init_a(bar(TMEM_EMPTY + i), 2 * EPI_WARPS);  // epilogue warps of both CTAs (only the even CTA's copy is used)
       }
       fence_mbar_init();
     }
@@ -235,7 +238,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else {
     // ------------------------------- epilogue (both CTAs, own 128 rows) ---------------------
-    const int quad = warp & 3;
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may read (hardware rule: warp id % 4)
+    const int col_half = (warp - 2) >> 2;       // which 128 accumulator columns this warp drains
     const int row_in_tile = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -244,15 +248,30 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tile_coords(tile, num_m, num_n, group_m, m_blk, n_blk);
       const int row = m_blk * 2 * BM + (int)rank * BM + row_in_tile;
       const bool row_ok = row < M;
+      if (ep.residual && row_ok) {
+        // the residual rows of this tile are needed only after the whole K loop: pull them into L2 now
+        const char* rp = reinterpret_cast<const char*>(ep.residual + (long long)row * ep.ldr + n_blk * BN + col_half * 128);
+        const int cols = min(128, N - (n_blk * BN + col_half * 128));
+        for (int b = 0; b < cols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
+      }
       mbar_wait_a(bar(TMEM_FULL + acc), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
       float ss = 0.f;
       int ss_group = -1;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = col_half * 4; c < col_half * 4 + 4; ++c) {
         const int n0 = n_blk * BN + c * 32;
         if (n0 >= N) break;
+        const bool whole = n0 + 32 <= N;     // all 32 columns of the chunk exist (always, except in the last N tile)
+        // residual of the whole chunk first: eight independent 16-byte loads in flight under the TMEM load (with an
+        // in-place residual the compiler may not move them above the stores of the previous group itself)
+        float4 res[8];
+        if (ep.residual && row_ok && whole) {
+          const float4* rp = reinterpret_cast<const float4*>(ep.residual + (long long)row * ep.ldr + n0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) res[q] = rp[q];
+        }
         uint32_t r[32];
         tmem_ld32(t_base + c * 32, r);
         tmem_ld_wait();
@@ -294,9 +313,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
             }
             if (ep.residual) {
-              const float* rp = ep.residual + (long long)row * ep.ldr + n;
-              const float4 r0 = *reinterpret_cast<const float4*>(rp);
-              const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+              float4 r0, r1;
+              if (whole) {
+                r0 = res[2 * j8];
+                r1 = res[2 * j8 + 1];
+              } else {
+                const float* rp = ep.residual + (long long)row * ep.ldr + n;
+                r0 = *reinterpret_cast<const float4*>(rp);
+                r1 = *reinterpret_cast<const float4*>(rp + 4);
+              }
               v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
               v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
             }

@@ -48,8 +48,10 @@ SIGNATURES = {
     "svi_last_error": (_c.c_char_p, []),
     "svi_sm_count": (_i32, []),
     "svi_gemm_bf16": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _c.POINTER(GemmEpilogue), _vp]),
-    "svi_attn_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp]),
-    "svi_attn_fwd_sp": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _c.c_uint32, _i32, _i32, _vp]),
+    "svi_attn_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp, _c.c_size_t, _vp]),
+    "svi_attn_workspace_bytes": (_c.c_size_t, [_i32, _i32, _i32]),
+    "svi_attn_plan": (None, [_i32, _i32, _i32, _c.c_size_t, _c.POINTER(_i32), _c.POINTER(_i32)]),
+    "svi_attn_fwd_sp": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _c.c_uint32, _i32, _i32, _vp, _c.c_size_t, _vp]),
     "svi_sp_alloc": (_i32, [_c.c_size_t, _c.POINTER(_vp), _c.c_char_p]),
     "svi_sp_free": (_i32, [_vp]),
     "svi_sp_open": (_i32, [_c.c_char_p, _c.POINTER(_vp)]),
@@ -160,19 +162,40 @@ def gemm(a, w, out, bias=None, act=ACT_NONE, gate=None, residual=None, sumsq=Non
     return out
 
 
-def attention(q, k, v, out, num_heads, scale=None, accumulate=False):
-    """out[Lq, H*128] (+)= softmax(q k^T * scale) v per head; q,k,v,out bf16 2-D (column-slice views allowed)."""
+def attention(q, k, v, out, num_heads, scale=None, accumulate=False, workspace=None):
+    """out[Lq, H*128] (+)= softmax(q k^T * scale) v per head; q,k,v,out bf16 2-D (column-slice views allowed).
+    workspace: optional device scratch (attention_workspace_bytes) that lets the launch slice its last wave of units."""
     ldq, ldk, ldv, ldo = (_rowmajor(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")))
     if scale is None:
         scale = 128 ** -0.5
     rc = load().svi_attn_fwd(_ptr(q, torch.bfloat16, "q"), ldq, _ptr(k, torch.bfloat16, "k"), ldk,
                              _ptr(v, torch.bfloat16, "v"), ldv, _ptr(out, torch.bfloat16, "out"), ldo,
-                             q.shape[0], k.shape[0], num_heads, float(scale), int(bool(accumulate)), _stream())
+                             q.shape[0], k.shape[0], num_heads, float(scale), int(bool(accumulate)),
+                             *_workspace(workspace), _stream())
     _check(rc, "svi_attn_fwd")
     return out
 
 
-def attention_sp(q, k, v, out, num_heads, kv_flags, kv_epoch, kv_chunk_rows, kv_self_chunk, scale=None):
+def _workspace(ws):
+    if ws is None:
+        return None, 0
+    if not ws.is_cuda or not ws.is_contiguous():
+        raise RuntimeError("svi_b200: attention workspace must be a contiguous CUDA tensor")
+    return _vp(ws.data_ptr()), ws.numel() * ws.element_size()
+
+
+def attention_plan(units, kv_tiles, sms, workspace_bytes):
+    """(n_full, split) the attention launch would use — pure host logic (svi_attn_plan)."""
+    a, b = _i32(), _i32()
+    load().svi_attn_plan(units, kv_tiles, sms, workspace_bytes, ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
+def attention_workspace_bytes(Lq, Lk, num_heads):
+    return int(load().svi_attn_workspace_bytes(Lq, Lk, num_heads))
+
+
+def attention_sp(q, k, v, out, num_heads, kv_flags, kv_epoch, kv_chunk_rows, kv_self_chunk, scale=None, workspace=None):
     """Self-attention over the rank's full K|V buffer whose remote rows are still being pushed by the peers
     (svi_attn_fwd_sp): kv_flags int32 [n_chunks] device tensor inside the symmetric allocation."""
     ldq, ldk, ldv, ldo = (_rowmajor(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")))
@@ -181,7 +204,8 @@ def attention_sp(q, k, v, out, num_heads, kv_flags, kv_epoch, kv_chunk_rows, kv_
     rc = load().svi_attn_fwd_sp(_ptr(q, torch.bfloat16, "q"), ldq, _ptr(k, torch.bfloat16, "k"), ldk,
                                 _ptr(v, torch.bfloat16, "v"), ldv, _ptr(out, torch.bfloat16, "out"), ldo,
                                 q.shape[0], k.shape[0], num_heads, float(scale), _ptr(kv_flags, torch.int32, "kv_flags"),
-                                int(kv_epoch) & 0xFFFFFFFF, int(kv_chunk_rows), int(kv_self_chunk), _stream())
+                                int(kv_epoch) & 0xFFFFFFFF, int(kv_chunk_rows), int(kv_self_chunk), *_workspace(workspace),
+                                _stream())
     _check(rc, "svi_attn_fwd_sp")
     return out
 

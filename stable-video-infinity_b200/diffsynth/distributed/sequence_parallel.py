@@ -11,7 +11,11 @@ Plan for N ranks (one process per GPU):
     velocity fields (8 MB) per step joins them;
   * inside a branch the token axis is split over sp_size = N/2 ranks: every row-local op (LayerNorm, GEMMs,
     RMSNorm, RoPE with a row offset, cross-attention, FFN) runs on L/sp rows; self-attention needs all K/V:
-    one in-place NCCL all-gather of the [L, 2d] K|V buffer per layer (NVLink 5 / NVSwitch);
+    on GPUs every rank pushes its rows of the [L, 2d] K|V buffer into its peers' buffers over NVLink peer memory
+    (copy engines, side stream) and the attention kernel consumes remote rows as their arrival flags flip
+    (`PeerExchange`, csrc/sp_exchange.cu, svi_attn_fwd_sp) — no collective call, transfer overlapped with the
+    attention on the local rows.  SVI_SP_EXCHANGE=nccl (and the CPU/gloo tests) use one in-place all-gather
+    per layer instead;
   * the head output rows are all-gathered once per forward (reference: get_sp_group().all_gather).
 Requires L % sp_size == 0 like the reference (torch.chunk + equal-size gather).
 """
@@ -38,6 +42,95 @@ def all_gather_inplace(full, local, group=None):
     return full
 
 
+def push_order(sp_rank, sp_size):
+    """Peers in the order a rank pushes its rows: nearest lower rank first.  Every consumer walks the chunks upwards
+    from its own (c, c+1, ...), so the chunk it needs next is always at the head of its owner's queue."""
+    return [(sp_rank - i) % sp_size for i in range(1, sp_size)]
+
+
+def epoch_of(launch, modulus=1 << 16):
+    """Flag value of the launch-th exchange (launch = 1, 2, ...): cycles through 1..modulus-1, never the 0 the flag
+    words are initialised with."""
+    return 1 + (launch - 1) % (modulus - 1)
+
+
+class PeerExchange:
+    """Symmetric K|V buffers of one sequence-parallel group, mapped into every member process (CUDA IPC).
+
+    Two buffers alternate by launch parity.  That is enough: a rank pushes launch c+2 only after its own attention
+    c+1 has run, which needed every peer's push c+1, which each peer issued after finishing its attention c — so
+    nobody still reads the buffer of parity c when it is overwritten.  Flag words hold the launch
+    number (epoch) of the rows currently in the buffer.
+    """
+
+    EPOCHS = 1 << 16
+
+    def __init__(self, sp, L_total, width, device):
+        from .. import _native as nv
+        self.nv, self.sp, self.device = nv, sp, device
+        self.L, self.width = L_total, width
+        self.rows = L_total // sp.sp_size
+        self.kv_bytes = L_total * width * 2
+        flag_off = (self.kv_bytes + 255) // 256 * 256
+        self.slab_bytes = self.rows * width * 2
+        nbytes = flag_off + 256
+        self.ptrs, self.kv, self.flags, handles = [], [], [], []
+        for _ in range(2):
+            ptr, handle, view = nv.sp_alloc(nbytes, device)
+            self.ptrs.append(ptr)
+            handles.append(handle)
+            self.kv.append(view[:self.kv_bytes].view(torch.bfloat16).view(L_total, width))
+            self.flags.append(view[flag_off:flag_off + 4 * sp.sp_size].view(torch.int32))
+        gathered = [None] * sp.sp_size
+        dist.all_gather_object(gathered, handles, group=sp.sp_group)
+        self.peers = push_order(sp.sp_rank, sp.sp_size)
+        self.peer_base = {r: [nv.sp_open(h) for h in gathered[r]] for r in self.peers}
+        off = sp.sp_rank * self.slab_bytes
+        self.peer_dst = [[self.peer_base[r][b] + off for r in self.peers] for b in range(2)]
+        self.peer_flag = [[self.peer_base[r][b] + flag_off + 4 * sp.sp_rank for r in self.peers] for b in range(2)]
+        self.src = [self.ptrs[b] + off for b in range(2)]
+        self.epoch_table = torch.arange(self.EPOCHS, dtype=torch.int32, device=device)
+        self.stream = torch.cuda.Stream(device=device)
+        self.pushed = [None, None]       # event: my last push out of buffer b has left (the slab may be rewritten)
+        self.launch = 0
+        dist.barrier(group=sp.sp_group)  # everybody has mapped everybody before the first push
+
+    def begin(self):
+        """Next launch: returns (buffer index, local K|V slab to fill).  Waits for the previous push out of the slab."""
+        self.launch += 1
+        b = self.launch & 1
+        if self.pushed[b] is not None:
+            torch.cuda.current_stream().wait_event(self.pushed[b])
+        r = self.sp.sp_rank
+        return b, self.kv[b][r * self.rows:(r + 1) * self.rows]
+
+    @property
+    def epoch(self):
+        return epoch_of(self.launch, self.EPOCHS)
+
+    def push(self, b):
+        """The local slab of buffer b is complete on the current stream: send it to every peer."""
+        ready = torch.cuda.Event()
+        ready.record()
+        self.stream.wait_event(ready)
+        self.nv.sp_push(self.src[b], self.peer_dst[b], self.peer_flag[b], self.slab_bytes,
+                        self.epoch_table.data_ptr() + 4 * self.epoch, self.stream)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        self.pushed[b] = ev
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.sp.sp_group)
+        for r in self.peers:
+            for p in self.peer_base[r]:
+                self.nv.sp_close(p)
+        self.kv, self.flags = [], []
+        for p in self.ptrs:
+            self.nv.sp_free(p)
+        self.ptrs = []
+
+
 class SequenceParallelGroup:
     def __init__(self, world, rank, cfg_parallel=True):
         self.world, self.rank = world, rank
@@ -57,6 +150,7 @@ class SequenceParallelGroup:
                 self.cfg_group = g
         self._rows = None
         self._bufs = {}
+        self._peer = None
 
     def describe(self):
         return f"cfg{self.cfg_groups}xsp{self.sp_size}"
@@ -78,6 +172,22 @@ class SequenceParallelGroup:
     def local_slice(self, full):
         n = full.shape[0] // self.sp_size
         return full[self.sp_rank * n:(self.sp_rank + 1) * n]
+
+    # ---- K|V exchange over peer memory (GPU only)
+    def peer_exchange(self, L_total, width, device):
+        """The group's PeerExchange for [L_total, width] K|V buffers, or None when the NCCL/gloo all-gather is to be used
+        (CPU tensors, SVI_SP_EXCHANGE=nccl, or slabs narrower than one attention tile)."""
+        import os
+        if self.sp_size == 1 or device.type != "cuda" or os.environ.get("SVI_SP_EXCHANGE", "peer") == "nccl":
+            return None
+        if L_total // self.sp_size < 128:
+            return None
+        pe = self._peer
+        if pe is None or pe.L != L_total or pe.width != width:
+            if pe is not None:
+                pe.close()
+            pe = self._peer = PeerExchange(self, L_total, width, device)
+        return pe
 
     # ---- collectives
     def all_gather_rows(self, full):

@@ -169,14 +169,38 @@ class _CountingNative:
 
     def __init__(self):
         self.launches = 0
+        self.events = None      # list -> every call is bracketed by CUDA events (bench.py --breakdown)
 
     def __getattr__(self, name):
         fn = getattr(nv, name)
 
         def call(*a, **k):
             self.launches += 1
-            return fn(*a, **k)
+            if self.events is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            tag = name
+            if name == "gemm":
+                tag = f"gemm M={a[0].shape[0]} N={a[1].shape[0]} K={a[1].shape[1]}"
+            elif name == "attention":
+                tag = f"attention Lq={a[0].shape[0]} Lk={a[1].shape[0]}"
+            self.events.append((tag, e0, e1))
+            return r
         return call
+
+    def breakdown(self):
+        """Sum of the bracketed durations per call tag (ms), and clears the list."""
+        torch.cuda.synchronize()
+        out = {}
+        for tag, e0, e1 in self.events:
+            t = out.setdefault(tag, [0.0, 0])
+            t[0] += e0.elapsed_time(e1)
+            t[1] += 1
+        self.events = None
+        return out
 
 
 class WanDiTEngine:
@@ -312,6 +336,11 @@ class WanDiTEngine:
             self._ctx_cache.popitem(last=False)
         return st
 
+    def _attn_workspace(self, Lq, Lk):
+        """Scratch for the sliced last wave of the self-attention launch (svi_attn_fwd workspace)."""
+        n = nv.attention_workspace_bytes(Lq, Lk, self.H)
+        return self._buf("attn_ws", ((n + 3) // 4,), torch.float32)
+
     # ------------------------------------------------------------------ block stack
     def run_block(self, i, x, t_mod, ctx: ContextState, cos, sin, sp=None):
         """x f32 [L,d] updated in place.  Reference DiTBlock.forward wan_video_dit.py:354-374."""
@@ -335,24 +364,38 @@ class WanDiTEngine:
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
         else:
             # sequence parallel: q for the local rows; K|V written straight into this rank's rows of the full
-            # [L_total, 2d] buffer, normalised + rotated with the rank's row offset, then all-gathered in place
+            # [L_total, 2d] buffer, normalised + rotated with the rank's row offset.  GPUs: the rows are pushed into the
+            # peers' buffers over NVLink while the attention kernel already works on the local rows (PeerExchange);
+            # otherwise one in-place all-gather.
             q = qkv[:, :d]
-            kvf = self._buf("kv_full", (L * sp.sp_size, 2 * d), torch.bfloat16)
-            kvl = kvf[sp.sp_rank * L:(sp.sp_rank + 1) * L]
+            pe = sp.peer_exchange(L * sp.sp_size, 2 * d, x.device)
+            if pe is not None:
+                pbuf, kvl = pe.begin()
+                kvf = pe.kv[pbuf]
+            else:
+                kvf = self._buf("kv_full", (L * sp.sp_size, 2 * d), torch.bfloat16)
+                kvl = kvf[sp.sp_rank * L:(sp.sp_rank + 1) * L]
             ssq = self._buf("ssq", (L, 1), torch.float32)
             ssk = self._buf("ssk", (L, 1), torch.float32)
             ssq.zero_()
             ssk.zero_()
-            self.k.gemm(h, bw.w_q, q, bias=bw.b_q, sumsq=ssq, sumsq_group_cols=d)
             self.k.gemm(h, bw.w_kv, kvl, bias=bw.b_kv, sumsq=ssk, sumsq_group_cols=d)
-            self.k.rmsnorm_rope(q, ssq, 0, bw.eps_qk, bw.nq, cos, sin, sp.sp_rank * L)
             self.k.rmsnorm_rope(kvl[:, :d], ssk, 0, bw.eps_qk, bw.nk, cos, sin, sp.sp_rank * L)
-            sp.all_gather_rows(kvf)
+            if pe is not None:
+                pe.push(pbuf)
+            self.k.gemm(h, bw.w_q, q, bias=bw.b_q, sumsq=ssq, sumsq_group_cols=d)
+            self.k.rmsnorm_rope(q, ssq, 0, bw.eps_qk, bw.nq, cos, sin, sp.sp_rank * L)
+            if pe is None:
+                sp.all_gather_rows(kvf)
             k, v = kvf[:, :d], kvf[:, d:]
         if ev is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        self.k.attention(q, k, v, att, H)
+        ws = self._attn_workspace(L, k.shape[0])
+        if sp is not None and pe is not None:
+            self.k.attention_sp(q, k, v, att, H, pe.flags[pbuf], pe.epoch, L, sp.sp_rank, workspace=ws)
+        else:
+            self.k.attention(q, k, v, att, H, workspace=ws)
         if ev is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()

@@ -42,6 +42,28 @@ def test_library_contains_blackwell_tensor_and_tma_instructions():
     assert "HMMA.16816" not in sass       # no legacy mma.sync tensor path
 
 
+def test_attention_launch_plan_slices_only_the_partial_wave():
+    """svi_attn_plan (host logic of svi_attn_fwd): whole units for the full waves, K/V slices for the last partial one."""
+    from diffsynth import _native as nv
+    big = 1 << 40
+    slice_bytes = 256 * 128 * 4 + 256 * 8
+    # bench shape on one B200: 12 heads x 128 Q-tile pairs = 1536 units = 10.38 waves of 148
+    n_full, split = nv.attention_plan(1536, 256, 148, big)
+    tail = 1536 - n_full
+    assert split > 1 and n_full % 148 == 0 and 0 < tail <= 2 * 148
+    waves = n_full / 148 + -(-tail * split // 148) / split
+    assert waves < 10.75                                            # 11 waves unsliced
+    # sequence-parallel shapes (sp = 2, 4): 5.19 and 2.59 waves
+    for units in (768, 384):
+        nf, sp = nv.attention_plan(units, 256, 148, big)
+        assert sp > 1 and nf / 148 + -(-(units - nf) * sp // 148) / sp < -(-units // 148) - 0.3
+    assert nv.attention_plan(1536, 256, 148, 0) == (1536, 1)        # no workspace: nothing sliced
+    assert nv.attention_plan(1480, 256, 148, big) == (1480, 1)      # exact multiple of the SM count
+    assert nv.attention_plan(1536, 4, 148, big) == (1536, 1)        # cross-attention: K/V stream too short to slice
+    nf, sp = nv.attention_plan(1536, 256, 148, 60 * slice_bytes)    # workspace for 60 slices only
+    assert (1536 - nf) * sp <= 60
+
+
 def test_native_calls_refuse_cpu_tensors():
     from diffsynth import _native as nv
     a = torch.zeros(8, 8, dtype=torch.bfloat16)

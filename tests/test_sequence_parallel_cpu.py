@@ -17,6 +17,19 @@ def test_partition_plans():
     assert partition(3, 2) == (1, 3, 0, 2)            # odd world: no CFG split
 
 
+def test_peer_exchange_host_logic():
+    from diffsynth.distributed.sequence_parallel import epoch_of, push_order
+    assert push_order(1, 4) == [0, 3, 2] and push_order(0, 2) == [1] and push_order(0, 1) == []
+    # consumer c walks chunks c+1, c+2, ...: chunk c+k is owned by rank c+k, whose k-th push goes to rank c
+    for P in (2, 4, 8):
+        for c in range(P):
+            for k in range(1, P):
+                assert push_order((c + k) % P, P)[k - 1] == c
+    eps = [epoch_of(i, 8) for i in range(1, 30)]
+    assert 0 not in eps and eps[:8] == [1, 2, 3, 4, 5, 6, 7, 1]
+    assert all(a != b for a, b in zip(eps, eps[2:]))     # same-parity neighbours always differ
+
+
 def _worker(rank, world, port, cfg_parallel, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import sys
@@ -40,6 +53,7 @@ def _worker(rank, world, port, cfg_parallel, q):
             vp[sp.cfg_idx] = float(sp.cfg_idx + 1)
             all_gather_inplace(vp, vp[sp.cfg_idx], sp.cfg_group)
             ok &= torch.equal(vp, torch.tensor([[1.0] * 4, [2.0] * 4]))
+        ok &= sp.peer_exchange(1024, 64, torch.device("cpu")) is None      # CPU tensors: gather path, no CUDA IPC
         with_err = sp.sp_size == 1
         if sp.sp_size > 1:
             try:

@@ -114,14 +114,18 @@ def sec_attn():
     g = torch.Generator(device="cpu").manual_seed(2)
     scale = 128 ** -0.5
     for (Lq, Lk, H, amp) in [(256, 128, 1, 1.0), (256, 256, 1, 1.0), (256, 512, 2, 1.0), (128, 128, 1, 1.0),
-                             (300, 333, 2, 1.0), (1000, 1000, 3, 3.0), (257, 77, 1, 1.0), (3200, 3200, 2, 2.0)]:
+                             (300, 333, 2, 1.0), (1000, 1000, 3, 3.0), (257, 77, 1, 1.0), (3200, 3200, 2, 2.0),
+                             # 156 units on 148 SMs: the 8 units of the second wave are cut into K/V slices and merged
+                             (3200, 3200, 12, 1.0), (3000, 4100, 13, 2.0)]:
         q = (torch.randn(Lq, H * 128, generator=g) * amp).to(dev, torch.bfloat16)
         k = (torch.randn(Lk, H * 128, generator=g) * amp).to(dev, torch.bfloat16)
         v = torch.randn(Lk, H * 128, generator=g).to(dev, torch.bfloat16)
-        out = torch.full((Lq, H * 128), float("nan"), device=dev, dtype=torch.bfloat16)
-        nv.attention(q, k, v, out, H, scale)
-        torch.cuda.synchronize()
-        report(f"attn Lq={Lq} Lk={Lk} H={H} amp={amp}", out, attn_ref(q, k, v, H, scale), 2e-2)
+        ref = attn_ref(q, k, v, H, scale)
+        for ws in (None, torch.empty(nv.attention_workspace_bytes(Lq, Lk, H) // 4 + 1, device=dev)):
+            out = torch.full((Lq, H * 128), float("nan"), device=dev, dtype=torch.bfloat16)
+            nv.attention(q, k, v, out, H, scale, workspace=ws)
+            torch.cuda.synchronize()
+            report(f"attn Lq={Lq} Lk={Lk} H={H} amp={amp} workspace={'yes' if ws is not None else 'no'}", out, ref, 2e-2)
 
 
 def sec_attn_cross():
@@ -228,6 +232,31 @@ def sec_perf_gemm():
         print(f"[PERF] gemm {name} M={M} N={N} K={K}: {ms:.3f} ms = {tf:.1f} TFLOP/s | cuBLAS {ms_t:.3f} ms = {2.0*M*N*K/ms_t/1e9:.1f}", flush=True)
 
 
+def sec_perf_gemm_epi():
+    """The DiT's GEMMs with the epilogues they carry in the block (the bare GEMM is perf_gemm)."""
+    g = torch.Generator(device="cpu").manual_seed(7)
+    L, d, f = 32760, 1536, 8960
+    h = torch.randn(L, d, generator=g).to(dev, torch.bfloat16)
+    hf = torch.randn(L, f, generator=g).to(dev, torch.bfloat16)
+    x = torch.randn(L, d, generator=g).to(dev)
+    gate = torch.randn(d, generator=g).to(dev)
+    mk = lambda n, k: (torch.randn(n, k, generator=g) * 0.02).to(dev, torch.bfloat16)
+    w_qkv, w_o, w_f0, w_f2 = mk(3 * d, d), mk(d, d), mk(f, d), mk(d, f)
+    b3, b1, bf_ = torch.randn(3 * d, generator=g).to(dev), torch.randn(d, generator=g).to(dev), torch.randn(f, generator=g).to(dev)
+    qkv = torch.empty(L, 3 * d, device=dev, dtype=torch.bfloat16)
+    ffn = torch.empty(L, f, device=dev, dtype=torch.bfloat16)
+    ss = torch.zeros(L, 2, device=dev)
+    cases = [
+        ("qkv  bias+sumsq -> bf16", lambda: nv.gemm(h, w_qkv, qkv, bias=b3, sumsq=ss, sumsq_group_cols=d), 2.0 * L * 3 * d * d),
+        ("o    bias+gate+residual (in place f32)", lambda: nv.gemm(h, w_o, x, bias=b1, gate=gate, residual=x), 2.0 * L * d * d),
+        ("ffn0 bias+gelu_tanh -> bf16", lambda: nv.gemm(h, w_f0, ffn, bias=bf_, act=nv.ACT_GELU_TANH), 2.0 * L * f * d),
+        ("ffn2 bias+gate+residual (in place f32)", lambda: nv.gemm(hf, w_f2, x, bias=b1, gate=gate, residual=x), 2.0 * L * f * d),
+    ]
+    for name, fn, fl in cases:
+        ms = time_ms(fn)
+        print(f"[PERF] gemm {name}: {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def sec_perf_attn():
     g = torch.Generator(device="cpu").manual_seed(6)
     scale = 128 ** -0.5
@@ -239,6 +268,9 @@ def sec_perf_attn():
         ms = time_ms(lambda: nv.attention(q, k, v, out, H, scale), iters=5, warm=2)
         fl = 4.0 * L * L * H * 128
         print(f"[PERF] attn L={L} H={H}: {ms:.3f} ms = {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+        ws = torch.empty(nv.attention_workspace_bytes(L, L, H) // 4 + 1, device=dev)
+        ms = time_ms(lambda: nv.attention(q, k, v, out, H, scale, workspace=ws), iters=5, warm=2)
+        print(f"[PERF] attn L={L} H={H} + workspace (sliced last wave): {ms:.3f} ms = {fl/ms/1e9:.1f} TFLOP/s", flush=True)
         try:
             from flash_attn import flash_attn_func
             q4, k4, v4 = (t.view(1, L, H, 128) for t in (q, k, v))

@@ -24,7 +24,8 @@ def main():
     from diffsynth.distributed.sequence_parallel import SequenceParallelGroup
     from diffsynth.models.wan_video_dit import WanModel
     ok = True
-    for cfg, (f, h, w) in ((synth.CFG_TINY_T2V, (4, 8, 16)), (synth.CFG_TINY_I2V, (2, 16, 16))):
+    # token counts: 128 (slabs < one attention tile -> NCCL all-gather path), 1024 and the ragged 540 (peer exchange)
+    for cfg, (f, h, w) in ((synth.CFG_TINY_T2V, (4, 8, 16)), (synth.CFG_TINY_T2V, (4, 32, 32)), (synth.CFG_TINY_I2V, (3, 20, 36))):
         sd = synth.make_dit_state_dict(cfg, seed=0)
         m = WanModel(**cfg).eval()
         m.load_state_dict(sd)
@@ -41,7 +42,7 @@ def main():
                 err = (out - ref).abs().max().item()
                 good = err < 2e-2
                 ok &= good
-                print(f"[rank {rank}] {sp.describe()} has_image={cfg['has_image_input']} forward max|sp - single| = {err:.3e} {'OK' if good else 'BAD'}", flush=True)
+                print(f"[rank {rank}] {sp.describe()} L={f * (h // 2) * (w // 2)} peer={sp._peer is not None} has_image={cfg['has_image_input']} forward max|sp - single| = {err:.3e} {'OK' if good else 'BAD'}", flush=True)
             # full step under the plan vs two local forwards + fused update
             cp = eng.context_state(inp["context"].to(dev), kw.get("clip_feature"))
             ctx2 = torch.randn(inp["context"].shape, generator=torch.Generator().manual_seed(77)).to(dev)   # same on every rank
