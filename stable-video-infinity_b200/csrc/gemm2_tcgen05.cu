@@ -32,7 +32,8 @@ constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int STAGES = 6;       // 7 fit but measured 1-2 % slower
 constexpr int GROUP_M = 4;      // measured: 1..4 equal on M >> N shapes, 4..8 best on square ones
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int VEC_BYTES = 2 * 2 * BN * 4;   // bias and gate of the tile's 256 columns, double buffered by accumulator
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + VEC_BYTES;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> even CTA
 
 struct Epi {
@@ -117,13 +118,15 @@ __device__ __forceinline__ void commit2_multicast(uint32_t bar) {
       "}\n" ::"r"(bar)
       : "memory");
 }
-// arrive on the barrier at this shared::cta offset in CTA `target_rank` of the cluster
+// arrive on the barrier at this shared::cta offset in CTA `target_rank` of the cluster.  Relaxed: the only thing the
+// MMA issuer must observe is that this warp's tcgen05.ld have completed, which tcgen05.wait::ld + the tcgen05 fence
+// before the arrive already order; a release here costs a MEMBAR over all the epilogue's global stores per tile.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t target_rank) {
   asm volatile(
       "{\n"
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
       "}\n" ::"r"(bar),
       "r"(target_rank)
       : "memory");
@@ -151,6 +154,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   enum : uint32_t { FULL = 0, EMPTY = STAGES, TMEM_FULL = 2 * STAGES, TMEM_EMPTY = 2 * STAGES + 2, NUM_BARS = 2 * STAGES + 4 };
   auto bar = [&](uint32_t n) { return sbase + OFF_BAR + 8u * n; };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_raw + (sbase - sraw) + OFF_BAR + 8 * NUM_BARS);
+  float* vec_smem = reinterpret_cast<float*>(smem_raw + (sbase - sraw) + OFF_BAR + 256);   // [2 acc][bias | gate][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -254,6 +258,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int cols = min(128, N - (n_blk * BN + col_half * 128));
         for (int b = 0; b < cols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
       }
+      // per-column vectors of this tile -> shared memory while the K loop still runs (every lane needs the same 8
+      // values at a time: an L1/L2 round trip per group of 8 columns was half of all epilogue stall samples)
+      float* sbias = vec_smem + acc * 2 * BN;
+      float* sgate = sbias + BN;
+      {
+        const int t = threadIdx.x - 64;          // 0..255 = column inside the tile
+        const int n = n_blk * BN + t;
+        if (ep.bias) sbias[t] = n < N ? __ldg(ep.bias + n) : 0.f;
+        if (ep.gate) sgate[t] = n < N ? __ldg(ep.gate + n) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // epilogue warps only
+      }
       mbar_wait_a(bar(TMEM_FULL + acc), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
@@ -293,8 +308,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j8 * 8 + j]);
             if (ep.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+              const float4 b0 = *reinterpret_cast<const float4*>(sbias + c * 32 + j8 * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sbias + c * 32 + j8 * 8 + 4);
               v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
@@ -307,8 +322,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
             }
             if (ep.gate) {
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gate + n));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.gate + n + 4));
+              const float4 g0 = *reinterpret_cast<const float4*>(sgate + c * 32 + j8 * 8);
+              const float4 g1 = *reinterpret_cast<const float4*>(sgate + c * 32 + j8 * 8 + 4);
               v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
               v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
             }
