@@ -176,6 +176,12 @@ int svi_act_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, int32_t act
 int svi_add_rows(const float* table, const float* t, int32_t rows, int32_t rows_t, int32_t D,
                  float* out, void* stream);
 
+/*
+ * out[i] = alpha * a[i] + beta * b[i], f32, n % 4 == 0, out may alias a or b.  TeaCache bookkeeping on the token
+ * stream: residual = after - before (svi_video.py:67-69) and tokens + residual on a skipped step (:70-72).
+ */
+int svi_axpby(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------------
  * Wan 3-D causal VAE (reference diffsynth/models/wan_video_vae.py).  Activations are channels-last.

@@ -13,6 +13,7 @@ Every function cites the reference lines it restates (paths relative to the refe
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -160,8 +161,53 @@ def head_unpatchify(sd, cfg, x, t, grid):
     return x.permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(B, cfg["out_dim"], f * pt, h * ph, w * pw)
 
 
-def dit_forward(sd, cfg, x, timestep, context, clip_feature=None, y=None, dtype=torch.float32, return_tokens=False):
-    """svi_video.py:74-137 (model_fn_wan_video; no TeaCache / USP) on CPU in `dtype`."""
+class TeaCacheOracle:
+    """svi_video.py:23-72 restated: accumulate poly(rel-L1 change of t_mod) and skip the block stack while the sum stays
+    below the threshold; first and last step of a clip always compute.  Pinned to the reference class by
+    tests/golden/teacache.npz (tests/test_oracle_golden.py)."""
+
+    COEFFICIENTS = {   # svi_video.py:34-39 (fitted constants of the TeaCache release), highest power first
+        "Wan2.1-T2V-1.3B": [-5.21862437e+04, 9.23041404e+03, -5.28275948e+02, 1.36987616e+01, -4.99875664e-02],
+        "Wan2.1-T2V-14B": [-3.03318725e+05, 4.90537029e+04, -2.65530556e+03, 5.87365115e+01, -3.15583525e-01],
+        "Wan2.1-I2V-14B-480P": [2.57151496e+05, -3.54229917e+04, 1.40286849e+03, -1.35890334e+01, 1.32517977e-01],
+        "Wan2.1-I2V-14B-720P": [8.10705460e+03, 2.13393892e+03, -3.72934672e+02, 1.66203073e+01, -4.17769401e-02],
+    }
+
+    def __init__(self, num_inference_steps, rel_l1_thresh, model_id):
+        self.n, self.thresh = num_inference_steps, rel_l1_thresh
+        self.poly = np.poly1d(self.COEFFICIENTS[model_id])
+        self.step, self.acc = 0, 0.0
+        self.prev_mod = self.prev_in = self.residual = None
+        self.skipped = []
+
+    def check(self, x, t_mod):            # :41-65
+        if self.step == 0 or self.step == self.n - 1:
+            compute, self.acc = True, 0.0
+        else:
+            rel = ((t_mod - self.prev_mod).abs().mean() / self.prev_mod.abs().mean()).item()
+            self.acc += float(self.poly(rel))
+            compute = not (self.acc < self.thresh)
+            if compute:
+                self.acc = 0.0
+        self.prev_mod = t_mod.clone()
+        if not compute:
+            self.skipped.append(self.step)
+        self.step = (self.step + 1) % self.n
+        if compute:
+            self.prev_in = x.clone()
+        return not compute
+
+    def store(self, x):                   # :67-69
+        self.residual = x - self.prev_in
+        self.prev_in = None
+
+    def update(self, x):                  # :71-72
+        return x + self.residual
+
+
+def dit_forward(sd, cfg, x, timestep, context, clip_feature=None, y=None, dtype=torch.float32, return_tokens=False,
+                tea_cache=None):
+    """svi_video.py:74-137 (model_fn_wan_video; no USP) on CPU in `dtype`; tea_cache: a TeaCacheOracle or None."""
     sd = {k: v.to(dtype) if v.is_floating_point() else v for k, v in sd.items()}
     x = x.to(dtype)
     context = context.to(dtype)
@@ -171,8 +217,13 @@ def dit_forward(sd, cfg, x, timestep, context, clip_feature=None, y=None, dtype=
         x = torch.cat([x, y.to(dtype)], dim=1)
     tok, (f, h, w) = patchify(sd, cfg, x)
     angles = rope_angles_3d(cfg["dim"] // cfg["num_heads"], f, h, w)
-    for i in range(cfg["num_layers"]):
-        tok = dit_block(sd, i, tok, ctx, t_mod, angles, cfg)
+    if tea_cache is not None and tea_cache.check(tok, t_mod):          # :114-126
+        tok = tea_cache.update(tok)
+    else:
+        for i in range(cfg["num_layers"]):
+            tok = dit_block(sd, i, tok, ctx, t_mod, angles, cfg)
+        if tea_cache is not None:
+            tea_cache.store(tok)
     if return_tokens:
         return tok
     return head_unpatchify(sd, cfg, tok, t, (f, h, w))
@@ -205,15 +256,18 @@ def cfg_combine(v_cond, v_uncond, scale):
 
 
 def denoise(sd, cfg, latents, ctx_pos, ctx_neg, steps, cfg_scale=5.0, shift=5.0, num_train_timesteps=1000,
-            clip_feature=None, y=None, dtype=torch.float32):
-    """svi_video.py:392-421 — the CFG + Euler loop (test-size only: every step is 2 full DiT forwards)."""
+            clip_feature=None, y=None, dtype=torch.float32, tea_cache_l1_thresh=None, tea_cache_model_id=""):
+    """svi_video.py:392-421 — the CFG + Euler loop (test-size only: every step is 2 full DiT forwards).
+    tea_cache_l1_thresh: one TeaCacheOracle per CFG branch as in svi_video.py:500-501."""
     sig = flow_match_sigmas(steps, shift)
     x = latents.to(dtype)
+    mk = lambda: TeaCacheOracle(steps, tea_cache_l1_thresh, tea_cache_model_id) if tea_cache_l1_thresh is not None else None
+    tc_pos, tc_neg = mk(), mk()
     for i in range(steps):
         ts = (sig[i] * num_train_timesteps).reshape(1)
-        vc = dit_forward(sd, cfg, x, ts, ctx_pos, clip_feature, y, dtype)
+        vc = dit_forward(sd, cfg, x, ts, ctx_pos, clip_feature, y, dtype, tea_cache=tc_pos)
         if cfg_scale != 1.0:
-            vu = dit_forward(sd, cfg, x, ts, ctx_neg, clip_feature, y, dtype)
+            vu = dit_forward(sd, cfg, x, ts, ctx_neg, clip_feature, y, dtype, tea_cache=tc_neg)
             vc = cfg_combine(vc, vu, cfg_scale)
         x = flow_match_step(sig, i, vc, x)
     return x

@@ -268,6 +268,16 @@ __global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restric
   }
 }
 
+// out = alpha * a + beta * b (TeaCache residual bookkeeping on the [L, d] token stream)
+__global__ void axpby_kernel(const float4* __restrict__ a, float alpha, const float4* __restrict__ b, float beta,
+                             float4* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = a[i], y = b[i];
+    out[i] = make_float4(alpha * x.x + beta * y.x, alpha * x.y + beta * y.y, alpha * x.z + beta * y.z,
+                         alpha * x.w + beta * y.w);
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d,
                                      long long n, int act) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -402,6 +412,16 @@ extern "C" int svi_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void
   SVI_CUDA_LAUNCH_CHECK("svi_cast_bf16_to_f32");
   return SVI_OK;
 }
+extern "C" int svi_axpby(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, void* stream) {
+  SVI_REQUIRE(a && b && out && n > 0 && n % 4 == 0, "svi_axpby: null pointer or n not a multiple of 4");
+  SVI_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              "svi_axpby: pointers must be 16-byte aligned");
+  axpby_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(a), alpha, reinterpret_cast<const float4*>(b), beta, reinterpret_cast<float4*>(out), n / 4);
+  SVI_CUDA_LAUNCH_CHECK("svi_axpby");
+  return SVI_OK;
+}
+
 extern "C" int svi_add_rows(const float* table, const float* t, int32_t rows, int32_t rows_t, int32_t D,
                             float* out, void* stream) {
   SVI_REQUIRE(table && t && out, "svi_add_rows: null pointer");

@@ -66,6 +66,7 @@ SIGNATURES = {
     "svi_cast_bf16_to_f32": (_i32, [_vp, _vp, _i64, _vp]),
     "svi_act_f32_to_bf16": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "svi_add_rows": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "svi_axpby": (_i32, [_vp, _f32, _vp, _f32, _vp, _i64, _vp]),
     "svi_conv3d_causal": (_i32, [_c.POINTER(ConvDesc), _vp]),
     "svi_vae_norm_act": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i32, _vp]),
     "svi_vae_upsample2x": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
@@ -326,6 +327,16 @@ def add_rows(table, t, out):
     rc = load().svi_add_rows(_ptr(table, torch.float32, "table"), _ptr(t, torch.float32, "t"), rows, t.shape[0], D,
                              _ptr(out, torch.float32, "out"), _stream())
     _check(rc, "svi_add_rows")
+    return out
+
+
+def axpby(a, alpha, b, beta, out):
+    """out = alpha * a + beta * b (f32, same shape, contiguous; out may alias a or b)."""
+    if not (a.is_contiguous() and b.is_contiguous() and out.is_contiguous()) or a.shape != b.shape or a.shape != out.shape:
+        raise RuntimeError("svi_b200.axpby: a, b, out must be contiguous and of one shape")
+    rc = load().svi_axpby(_ptr(a, torch.float32, "a"), float(alpha), _ptr(b, torch.float32, "b"), float(beta),
+                          _ptr(out, torch.float32, "out"), a.numel(), _stream())
+    _check(rc, "svi_axpby")
     return out
 
 

@@ -420,10 +420,11 @@ class WanDiTEngine:
         self.k.gemm(ffn, bw.w_f2, x, bias=bw.b_f2, gate=mod[5], residual=x)
         return x
 
-    def forward(self, x, timestep, context, clip_feature=None, y=None, sp=None, out=None):
+    def forward(self, x, timestep, context, clip_feature=None, y=None, sp=None, out=None, tea_cache=None):
         """One DiT forward (svi_video.py:74-137).  x [1,C,f,Hl,Wl] (any float dtype, CUDA) -> f32 [1,16,f,Hl,Wl].
 
-        `context` may be a tensor [1,Lc,text_dim] or a ContextState from context_state()."""
+        `context` may be a tensor [1,Lc,text_dim] or a ContextState from context_state().  `tea_cache`: a
+        pipelines.svi_video.TeaCache deciding per step whether the block stack runs or the cached residual is re-used."""
         dev, d = self.device, self.dim
         if x.dim() != 5 or x.shape[0] != 1:
             raise RuntimeError(f"svi_b200: DiT forward expects x of shape [1,C,f,h,w], got {tuple(x.shape)}")
@@ -452,8 +453,13 @@ class WanDiTEngine:
             tok_l = tok[sp.row_offset: sp.row_offset + Ll]
         xr = self._buf("x", (Ll, d), torch.float32)
         self.k.gemm(tok_l, self.w_patch, xr, bias=self.b_patch)
-        for i in range(len(self.blocks)):
-            self.run_block(i, xr, t_mod, ctx, cos, sin, sp)
+        if tea_cache is not None and tea_cache.check(self.model, xr, t_mod):
+            tea_cache.update(xr)                      # skipped step: tokens + residual of the last computed step
+        else:
+            for i in range(len(self.blocks)):
+                self.run_block(i, xr, t_mod, ctx, cos, sin, sp)
+            if tea_cache is not None:
+                tea_cache.store(xr)
         # head (wan_video_dit.py:401-404) + unpatchify (:479-484)
         mod2 = self._buf("mod2", (2, d), torch.float32)
         self.k.add_rows(self.head_mod, t, mod2)

@@ -23,11 +23,82 @@ from .base import BasePipeline
 
 
 class TeaCache:
-    """Step-skipping approximation of the reference (svi_video.py:23-72); OFF by default there and not part of
-    the parity contract.  Kept as an explicit 'next' item."""
+    """Step skipping of the reference (svi_video.py:23-72): the relative L1 change of the timestep modulation between
+    consecutive steps, passed through a model-specific fitted polynomial, is accumulated; while the sum stays below
+    `rel_l1_thresh` the block stack is skipped and the token residual (output - input of the block stack) of the last
+    computed step is added instead.  First and last step always compute.  One instance per CFG branch.
+
+    The residual bookkeeping runs on the native kernels (svi_axpby); the decision needs one scalar on the host per
+    step, exactly as in the reference (`.cpu().item()`, :52)."""
+
+    # fitted rescaling polynomials, highest power first (numeric constants of the TeaCache release, reference :34-39)
+    coefficients_dict = {
+        "Wan2.1-T2V-1.3B": [-5.21862437e+04, 9.23041404e+03, -5.28275948e+02, 1.36987616e+01, -4.99875664e-02],
+        "Wan2.1-T2V-14B": [-3.03318725e+05, 4.90537029e+04, -2.65530556e+03, 5.87365115e+01, -3.15583525e-01],
+        "Wan2.1-I2V-14B-480P": [2.57151496e+05, -3.54229917e+04, 1.40286849e+03, -1.35890334e+01, 1.32517977e-01],
+        "Wan2.1-I2V-14B-720P": [8.10705460e+03, 2.13393892e+03, -3.72934672e+02, 1.66203073e+01, -4.17769401e-02],
+    }
 
     def __init__(self, num_inference_steps, rel_l1_thresh, model_id):
-        raise NotImplementedError("TeaCache is not implemented in the B200 hot path (SURVEY.md §8f.4)")
+        if model_id not in self.coefficients_dict:
+            raise ValueError(f"{model_id} is not a supported TeaCache model id. Please choose a valid model id in "
+                             f"({', '.join(self.coefficients_dict)}).")
+        self.num_inference_steps = num_inference_steps
+        self.rel_l1_thresh = rel_l1_thresh
+        self.coefficients = self.coefficients_dict[model_id]
+        self.step = 0
+        self.accumulated_rel_l1_distance = 0
+        self.previous_modulated_input = None
+        self.previous_hidden_states = None
+        self.previous_residual = None
+        self.skipped = []                 # step indices that re-used the residual (diagnostics / tests)
+
+    def _rescale(self, v):
+        acc = 0.0
+        for c in self.coefficients:       # Horner, same polynomial as np.poly1d(coefficients)(v)
+            acc = acc * v + c
+        return acc
+
+    def check(self, dit, x, t_mod):
+        """True when this step may skip the block stack.  x: token stream entering the blocks; t_mod: [6, d] modulation."""
+        cur = t_mod.detach().clone()
+        if self.step == 0 or self.step == self.num_inference_steps - 1:
+            compute = True
+            self.accumulated_rel_l1_distance = 0
+        else:
+            prev = self.previous_modulated_input
+            rel = ((cur - prev).abs().mean() / prev.abs().mean()).cpu().item()
+            self.accumulated_rel_l1_distance += self._rescale(rel)
+            compute = not (self.accumulated_rel_l1_distance < self.rel_l1_thresh)
+            if compute:
+                self.accumulated_rel_l1_distance = 0
+        self.previous_modulated_input = cur
+        if not compute:
+            self.skipped.append(self.step)
+        self.step = (self.step + 1) % self.num_inference_steps
+        if compute:
+            self.previous_hidden_states = x.clone()
+        return not compute
+
+    def store(self, hidden_states):
+        """After a computed step: residual = block-stack output - its input."""
+        if self.previous_residual is None or self.previous_residual.shape != hidden_states.shape:
+            self.previous_residual = torch.empty_like(hidden_states)
+        if hidden_states.is_cuda:
+            from .. import _native as nv
+            nv.axpby(hidden_states, 1.0, self.previous_hidden_states, -1.0, self.previous_residual)
+        else:
+            torch.sub(hidden_states, self.previous_hidden_states, out=self.previous_residual)
+        self.previous_hidden_states = None
+
+    def update(self, hidden_states):
+        """Skipped step: hidden_states += residual (in place; also returned, as the reference returns the sum)."""
+        if hidden_states.is_cuda:
+            from .. import _native as nv
+            nv.axpby(hidden_states, 1.0, self.previous_residual, 1.0, hidden_states)
+        else:
+            hidden_states.add_(self.previous_residual)
+        return hidden_states
 
 
 def model_fn_wan_video(dit: WanModel, x: torch.Tensor, timestep: torch.Tensor, context, clip_feature: Optional[torch.Tensor] = None,
@@ -35,8 +106,6 @@ def model_fn_wan_video(dit: WanModel, x: torch.Tensor, timestep: torch.Tensor, c
                        use_unified_sequence_parallel: bool = False, **kwargs):
     """Drop-in for reference svi_video.py:74-137: one DiT forward, result in x.dtype.  `context` may also be
     a ContextState (pre-projected conditioning)."""
-    if tea_cache is not None:
-        raise NotImplementedError("TeaCache is not implemented in the B200 hot path (SURVEY.md §8f.4)")
     if add_condition is not None:
         raise NotImplementedError("pose add_condition (SVI-Dance) is outside the hot-path scope (SURVEY.md §8f.2)")
     sp = None
@@ -44,7 +113,7 @@ def model_fn_wan_video(dit: WanModel, x: torch.Tensor, timestep: torch.Tensor, c
         from ..distributed.sequence_parallel import get_sp_group
         sp = get_sp_group()
     eng = dit.engine(x.device if x.is_cuda else None)
-    out = eng.forward(x, timestep, context, clip_feature, y, sp=sp)
+    out = eng.forward(x, timestep, context, clip_feature, y, sp=sp, tea_cache=tea_cache)
     return out.to(x.dtype)
 
 
@@ -162,7 +231,7 @@ class SVIVideoPipeline(BasePipeline):
 
     # ------------------------------------------------------------------ denoising
     def denoise_latents(self, latents, context_posi, context_nega, clip_feature=None, y=None, cfg_scale=5.0,
-                        progress_bar_cmd=lambda x: x, sp=None):
+                        progress_bar_cmd=lambda x: x, sp=None, tea_cache_posi=None, tea_cache_nega=None):
         """The hot loop (reference _sample_with_regular_video :392-421).  latents: f32 [1,16,f,h,w] on device,
         updated in place and returned.  Timesteps/sigmas come from self.scheduler (already set)."""
         eng = self.dit.engine(self.device)
@@ -181,9 +250,9 @@ class SVIVideoPipeline(BasePipeline):
         n = len(ts)
         for i in progress_bar_cmd(range(n)):
             t = float(ts[i])
-            eng.forward(lat, t, cp, y=y, sp=sp, out=v_c)
+            eng.forward(lat, t, cp, y=y, sp=sp, out=v_c, tea_cache=tea_cache_posi)
             if use_cfg:
-                eng.forward(lat, t, cn, y=y, sp=sp, out=v_u)
+                eng.forward(lat, t, cn, y=y, sp=sp, out=v_u, tea_cache=tea_cache_nega)
             sigma = float(sig[i])
             nxt = float(sig[i + 1]) if i + 1 < n else 0.0
             eng.k.cfg_euler_step(lat, v_c, v_u, cfg_scale, sigma, nxt)
@@ -191,8 +260,6 @@ class SVIVideoPipeline(BasePipeline):
 
     def _sample_with_regular_video(self, latents, prompt_emb_posi, prompt_emb_nega, image_emb, extra_input, tea_cache_posi,
                                    tea_cache_nega, usp_kwargs, use_controlnet, cfg_scale, progress_bar_cmd):
-        if tea_cache_posi.get("tea_cache") is not None:
-            raise NotImplementedError("TeaCache is not implemented in the B200 hot path (SURVEY.md §8f.4)")
         sp = None
         if usp_kwargs.get("use_unified_sequence_parallel"):
             from ..distributed.sequence_parallel import get_sp_group
@@ -200,7 +267,8 @@ class SVIVideoPipeline(BasePipeline):
         scale = cfg_scale["text"] if isinstance(cfg_scale, dict) else cfg_scale
         bar = (lambda r: progress_bar_cmd(r)) if progress_bar_cmd is not None else (lambda r: r)
         return self.denoise_latents(latents, prompt_emb_posi["context"], prompt_emb_nega["context"],
-                                    image_emb.get("clip_feature"), image_emb.get("y"), scale, bar, sp)
+                                    image_emb.get("clip_feature"), image_emb.get("y"), scale, bar, sp,
+                                    tea_cache_posi.get("tea_cache"), tea_cache_nega.get("tea_cache"))
 
     @torch.no_grad()
     def __call__(self, prompt, negative_prompt="", input_image=None, input_video=None, denoising_strength=1.0, seed=None,
@@ -212,8 +280,6 @@ class SVIVideoPipeline(BasePipeline):
         if num_frames % 4 != 1:
             num_frames = (num_frames + 2) // 4 * 4 + 1
             print(f"Only `num_frames % 4 != 1` is acceptable. We round it up to {num_frames}.")
-        if tea_cache_l1_thresh is not None:
-            raise NotImplementedError("TeaCache is not implemented in the B200 hot path (SURVEY.md §8f.4)")
         tiler_kwargs = {"tiled": tiled, "tile_size": tile_size, "tile_stride": tile_stride}
         self.scheduler.set_timesteps(num_inference_steps, denoising_strength=denoising_strength, shift=sigma_shift)
         noise = self.generate_noise((1, 16, (num_frames - 1) // 4 + 1, height // 8, width // 8), seed=seed,
@@ -239,8 +305,10 @@ class SVIVideoPipeline(BasePipeline):
             image_emb = {}
         scale = cfg_scale
         usp_kwargs = self.prepare_unified_sequence_parallel()
-        latents = self._sample_with_regular_video(latents, prompt_emb_posi, prompt_emb_nega, image_emb, {}, {"tea_cache": None},
-                                                  {"tea_cache": None}, usp_kwargs, use_controlnet, scale, progress_bar_cmd)
+        mk = lambda: {"tea_cache": TeaCache(num_inference_steps, rel_l1_thresh=tea_cache_l1_thresh, model_id=tea_cache_model_id)
+                      if tea_cache_l1_thresh is not None else None}
+        latents = self._sample_with_regular_video(latents, prompt_emb_posi, prompt_emb_nega, image_emb, {}, mk(), mk(),
+                                                  usp_kwargs, use_controlnet, scale, progress_bar_cmd)
         frames = self.decode_video(latents, **tiler_kwargs)
         frames = self.tensor2video(frames[0])
         if hasattr(args, "sequential_cfg") and args.sequential_cfg == "latent":

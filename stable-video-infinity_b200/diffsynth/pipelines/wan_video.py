@@ -47,8 +47,6 @@ class WanVideoPipeline(SVIVideoPipeline):
         if num_frames % 4 != 1:
             num_frames = (num_frames + 2) // 4 * 4 + 1
             print(f"Only `num_frames % 4 != 1` is acceptable. We round it up to {num_frames}.")
-        if tea_cache_l1_thresh is not None:
-            raise NotImplementedError("TeaCache is not implemented in the B200 hot path (SURVEY.md §8f.4)")
         tiler_kwargs = {"tiled": tiled, "tile_size": tile_size, "tile_stride": tile_stride}
         self.scheduler.set_timesteps(num_inference_steps, denoising_strength=denoising_strength, shift=sigma_shift)
         noise = self.generate_noise((1, 16, (num_frames - 1) // 4 + 1, height // 8, width // 8), seed=seed,
@@ -64,7 +62,10 @@ class WanVideoPipeline(SVIVideoPipeline):
         if input_image is not None and self.image_encoder is not None:
             image_emb = self.encode_image(input_image, num_frames, height, width)
         bar = (lambda r: progress_bar_cmd(r)) if progress_bar_cmd is not None else (lambda r: r)
+        from .svi_video import TeaCache
+        mk = lambda: (TeaCache(num_inference_steps, rel_l1_thresh=tea_cache_l1_thresh, model_id=tea_cache_model_id)
+                      if tea_cache_l1_thresh is not None else None)     # reference wan_video.py:261-262
         latents = self.denoise_latents(latents, pos["context"], neg["context"], image_emb.get("clip_feature"),
-                                       image_emb.get("y"), cfg_scale, bar)
+                                       image_emb.get("y"), cfg_scale, bar, tea_cache_posi=mk(), tea_cache_nega=mk())
         frames = self.decode_video(latents, **tiler_kwargs)
         return self.tensor2video(frames[0])

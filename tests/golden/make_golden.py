@@ -156,6 +156,56 @@ def golden_vae(vae_mod):
     print("vae lat", tuple(lat.shape), "dec", tuple(dec.shape), "dec std", dec.std().item())
 
 
+def teacache_inputs(steps=12, d=48, L=40, seed=5):
+    """Seeded inputs of the TeaCache fixture (shared with the tests): per-step modulation [1,6,d], block-stack input and
+    output token streams [1,L,d].  The modulation drifts by ~5 % per step with two jumps, so some steps skip."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(1, 6, d, generator=g)
+    drift = torch.randn(1, 6, d, generator=g)
+    scale = [0.0]
+    for k in range(1, steps):
+        scale.append(scale[-1] + (0.25 if k in (4, 9) else 0.05))
+    t_mods = [base + sc * drift for sc in scale]
+    xs = [torch.randn(1, L, d, generator=g) for _ in range(steps)]
+    outs = [torch.randn(1, L, d, generator=g) for _ in range(steps)]
+    return t_mods, xs, outs
+
+
+def golden_teacache(ref_root):
+    """Runs the reference's own TeaCache class (svi_video.py:23-72).  The pipeline module cannot be imported here
+    (it pulls the whole package), so the class definition alone is compiled from the reference file in place —
+    nothing is copied into this repository."""
+    import ast
+    path = os.path.join(ref_root, "diffsynth", "pipelines", "svi_video.py")
+    tree = ast.parse(open(path).read())
+    node = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "TeaCache"][0]
+    ns = {"np": np, "torch": torch, "WanModel": object}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    res = {}
+    for model_id, thresh in (("Wan2.1-T2V-1.3B", 0.3), ("Wan2.1-I2V-14B-720P", 0.2)):
+        t_mods, xs, outs = teacache_inputs()
+        tc = ns["TeaCache"](len(t_mods), rel_l1_thresh=thresh, model_id=model_id)
+        skipped, acc, finals = [], [], []
+        for k in range(2 * len(t_mods)):               # two clips back to back: the step counter wraps (:60-61)
+            i = k % len(t_mods)
+            x = xs[i].clone()
+            if tc.check(None, x, t_mods[i]):
+                skipped.append(k)
+                x = tc.update(x)
+            else:
+                x = outs[i].clone()
+                tc.store(x)
+            acc.append(float(tc.accumulated_rel_l1_distance))
+            finals.append(x.numpy())
+        key = model_id.replace(".", "_").replace("-", "_")
+        res[key + "_skipped"] = np.array(skipped, dtype=np.int64)
+        res[key + "_acc"] = np.array(acc, dtype=np.float64)
+        res[key + "_tokens"] = np.stack(finals)
+        res[key + "_thresh"] = np.array(thresh)
+        print("teacache", model_id, "skipped steps", skipped)
+    np.savez_compressed(os.path.join(HERE, "teacache.npz"), **res)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -169,5 +219,7 @@ if __name__ == "__main__":
         golden_dit(dit_mod, synth.CFG_TINY_I2V, "dit_tiny_i2v", f=2, h=6, w=10, ctx_len=24, seed=1)
     if a.only in ("", "sched"):
         golden_scheduler(fm)
+    if a.only in ("", "teacache"):
+        golden_teacache(a.ref)
     if a.only in ("", "vae") and os.path.exists(os.path.join(ROOT, "tools", "synth_vae.py")):
         golden_vae(vae_mod)

@@ -89,6 +89,39 @@ def test_model_fn_and_cfg_euler_step_match_oracle():
     assert inside > 0.5 and mx < 0.15 and rel < 2e-2
 
 
+def test_teacache_denoise_matches_oracle():
+    """8-step CFG denoise with TeaCache (reference svi_video.py:23-72,114-126): the native path must take the same
+    skip decisions as the oracle and land on the same latents.  Random-init weights make the modulation change by
+    ~100 % per step, so the fitted polynomial of the 720P model returns thousands per step; a threshold of 22000
+    yields a mixed compute / skip pattern with >= 10 % margin on every decision."""
+    from diffsynth import _native as nv
+    from diffsynth.pipelines.svi_video import TeaCache, model_fn_wan_video
+    from oracle import wan_dit_oracle as O
+    cfg = synth.CFG_TINY_T2V
+    sd = _sd(cfg, 3)
+    a = synth.make_dit_inputs(cfg, 3, 8, 8, seed=3, ctx_len=32)
+    b = synth.make_dit_inputs(cfg, 3, 8, 8, seed=4, ctx_len=32)
+    m = _build(cfg, sd)
+    steps, thresh, mid = 8, 22000.0, "Wan2.1-I2V-14B-720P"
+    sig = O.flow_match_sigmas(steps, 5.0)
+    o_pos, o_neg = O.TeaCacheOracle(steps, thresh, mid), O.TeaCacheOracle(steps, thresh, mid)
+    n_pos, n_neg = TeaCache(steps, rel_l1_thresh=thresh, model_id=mid), TeaCache(steps, rel_l1_thresh=thresh, model_id=mid)
+    ref = a["x"].clone()
+    lat = a["x"].cuda().float().clone()
+    for i in range(steps):
+        ts = (sig[i] * 1000).reshape(1)
+        vc = O.dit_forward(sd, cfg, ref, ts, a["context"], tea_cache=o_pos)
+        vu = O.dit_forward(sd, cfg, ref, ts, b["context"], tea_cache=o_neg)
+        ref = O.flow_match_step(sig, i, O.cfg_combine(vc, vu, 5.0), ref)
+        vc = model_fn_wan_video(m, lat, ts, a["context"].cuda(), tea_cache=n_pos)
+        vu = model_fn_wan_video(m, lat, ts, b["context"].cuda(), tea_cache=n_neg)
+        nv.cfg_euler_step(lat, vc, vu, 5.0, float(sig[i]), float(sig[i + 1]) if i + 1 < steps else 0.0)
+    assert n_pos.skipped == o_pos.skipped == [1, 2, 4, 6] and n_neg.skipped == o_neg.skipped
+    inside, mx, rel = _stats(lat.cpu(), ref)
+    print(f"8-step TeaCache denoise: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e} skipped={n_pos.skipped}")
+    assert inside > 0.5 and rel < 2e-2
+
+
 @pytest.mark.slow
 def test_cfg1_1p3b_one_step_matches_oracle():
     """BASELINE config 1: Wan2.1-T2V-1.3B random-init, 1 denoise step, 17x320x512 (latent [1,16,5,40,64])."""

@@ -74,3 +74,49 @@ def test_flops_formula_matches_survey():
     # cfg-2 283.0 TF, cfg-1 10.35 TF per forward
     assert abs(O.dit_forward_flops(O.CFG_T2V_1_3B, 32760) / 1e12 - 283.0) < 1.0
     assert abs(O.dit_forward_flops(O.CFG_T2V_1_3B, 3200) / 1e12 - 10.35) < 0.1
+
+
+def _teacache_inputs():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.teacache_inputs()
+
+
+@pytest.mark.parametrize("model_id", ["Wan2.1-T2V-1.3B", "Wan2.1-I2V-14B-720P"])
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+def test_teacache_matches_reference_class(model_id, impl):
+    """tests/golden/teacache.npz holds decisions, accumulated distances and token streams of the reference's own
+    TeaCache class (svi_video.py:23-72) over two back-to-back 12-step clips; both the oracle restatement and the
+    product class (its CPU-tensor path: same host logic, torch instead of svi_axpby) must reproduce them."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "teacache.npz"))
+    key = model_id.replace(".", "_").replace("-", "_")
+    t_mods, xs, outs = _teacache_inputs()
+    thresh = float(g[key + "_thresh"])
+    if impl == "oracle":
+        from oracle.wan_dit_oracle import TeaCacheOracle
+        tc = TeaCacheOracle(len(t_mods), thresh, model_id)
+        check = lambda x, tm: tc.check(x, tm)
+        acc = lambda: tc.acc
+    else:
+        from diffsynth.pipelines.svi_video import TeaCache
+        tc = TeaCache(len(t_mods), rel_l1_thresh=thresh, model_id=model_id)
+        check = lambda x, tm: tc.check(None, x, tm)
+        acc = lambda: tc.accumulated_rel_l1_distance
+    skipped, accs = [], []
+    for k in range(2 * len(t_mods)):
+        i = k % len(t_mods)
+        x = xs[i].clone()
+        if check(x, t_mods[i]):
+            skipped.append(k)
+            x = tc.update(x)
+        else:
+            x = outs[i].clone()
+            tc.store(x)
+        accs.append(float(acc()))
+        np.testing.assert_allclose(x.numpy(), g[key + "_tokens"][k], rtol=0, atol=1e-6)
+    assert skipped == g[key + "_skipped"].tolist() and len(skipped) > 4
+    np.testing.assert_allclose(np.array(accs), g[key + "_acc"], rtol=1e-9, atol=1e-12)
+    with pytest.raises((ValueError, KeyError)):
+        (TeaCacheOracle if impl == "oracle" else TeaCache)(12, 0.3, "no-such-model")
