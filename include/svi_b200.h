@@ -236,6 +236,33 @@ int svi_vae_to_planar(const float* x, int64_t ldx, int32_t C, int64_t n_pix, con
 int svi_softmax_rows(const float* s, int32_t rows, int32_t N, int64_t lds, float scale, void* p_bf16, int64_t ldp,
                      void* stream);
 
+/*
+ * ---- conditioning encoders (once per clip) -------------------------------------------------------
+ * The projections / MLPs of both encoders are svi_gemm_bf16 calls; these are the remaining ops.
+ *
+ * svi_embedding_gather  out f32 [n, dim] = table bf16 [vocab, dim] rows ids[i]     (wan_video_text_encoder.py:246)
+ * svi_rmsnorm_affine    y bf16 = w * x * rsqrt(mean(x^2) + eps), x f32 [M, D]       (T5LayerNorm :22-35)
+ * svi_layernorm_f32     y f32 = LayerNorm(x) * gamma + beta                         (ViT pre_norm,
+ *                                                                     wan_video_image_encoder.py:470-471)
+ * svi_mul_bf16          out = a * b elementwise (gated-GELU product, T5FeedForward :106)
+ * svi_attn_small        softmax(Q K^T * scale + bias) V for short sequences and any head_dim <= 128, fp32 math:
+ *                       Q,K,V,O bf16 [L, ld] with head h at columns [h*head_dim, (h+1)*head_dim);
+ *                       bias_table f32 [n_buckets, H] + bucket int32 [Lq, Lk] (T5RelativeEmbedding :159-190, the
+ *                       bucket of (query, key) is position-only and shared by all layers) or both NULL;
+ *                       key_mask int32 [Lk] (0 = masked; T5Attention :73-77) or NULL.
+ *                       Replaces T5Attention.forward :55-89 (scale 1, bias, mask) and the CLIP SelfAttention
+ *                       (wan_video_image_encoder.py:255-268: head_dim 80, scale 1/sqrt(80)).
+ */
+int svi_embedding_gather(const int64_t* ids, int32_t n, const void* table_bf16, int32_t dim, int64_t vocab, float* out,
+                         void* stream);
+int svi_rmsnorm_affine(const float* x, int32_t M, int32_t D, float eps, const float* w, void* y_bf16, void* stream);
+int svi_layernorm_f32(const float* x, int32_t M, int32_t D, float eps, const float* gamma, const float* beta, float* y,
+                      void* stream);
+int svi_mul_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+int svi_attn_small(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                   int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, int32_t head_dim, float scale,
+                   const float* bias_table, const int32_t* bucket, const int32_t* key_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -206,8 +206,9 @@ class TeaCacheOracle:
 
 
 def dit_forward(sd, cfg, x, timestep, context, clip_feature=None, y=None, dtype=torch.float32, return_tokens=False,
-                tea_cache=None):
-    """svi_video.py:74-137 (model_fn_wan_video; no USP) on CPU in `dtype`; tea_cache: a TeaCacheOracle or None."""
+                tea_cache=None, add_condition=None):
+    """svi_video.py:74-137 (model_fn_wan_video; no USP) on CPU in `dtype`; tea_cache: a TeaCacheOracle or None;
+    add_condition: [1, L, dim] added to the patch embedding (:102-103)."""
     sd = {k: v.to(dtype) if v.is_floating_point() else v for k, v in sd.items()}
     x = x.to(dtype)
     context = context.to(dtype)
@@ -216,6 +217,8 @@ def dit_forward(sd, cfg, x, timestep, context, clip_feature=None, y=None, dtype=
     if cfg["has_image_input"]:
         x = torch.cat([x, y.to(dtype)], dim=1)
     tok, (f, h, w) = patchify(sd, cfg, x)
+    if add_condition is not None:
+        tok = add_condition.to(dtype) + tok
     angles = rope_angles_3d(cfg["dim"] // cfg["num_heads"], f, h, w)
     if tea_cache is not None and tea_cache.check(tok, t_mod):          # :114-126
         tok = tea_cache.update(tok)

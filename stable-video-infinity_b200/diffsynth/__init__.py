@@ -11,6 +11,7 @@ _LAZY = {
     "save_video": ("diffsynth.data.video", "save_video"),
     "VideoData": ("diffsynth.data.video", "VideoData"),
     "FlowMatchScheduler": ("diffsynth.schedulers.flow_match", "FlowMatchScheduler"),
+    "WanPrompter": ("diffsynth.prompters.wan_prompter", "WanPrompter"),
 }
 
 

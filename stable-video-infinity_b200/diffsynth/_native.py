@@ -67,6 +67,11 @@ SIGNATURES = {
     "svi_act_f32_to_bf16": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "svi_add_rows": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "svi_axpby": (_i32, [_vp, _f32, _vp, _f32, _vp, _i64, _vp]),
+    "svi_embedding_gather": (_i32, [_vp, _i32, _vp, _i32, _i64, _vp, _vp]),
+    "svi_rmsnorm_affine": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp]),
+    "svi_layernorm_f32": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
+    "svi_mul_bf16": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "svi_attn_small": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "svi_conv3d_causal": (_i32, [_c.POINTER(ConvDesc), _vp]),
     "svi_vae_norm_act": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i32, _vp]),
     "svi_vae_upsample2x": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
@@ -337,6 +342,62 @@ def axpby(a, alpha, b, beta, out):
     rc = load().svi_axpby(_ptr(a, torch.float32, "a"), float(alpha), _ptr(b, torch.float32, "b"), float(beta),
                           _ptr(out, torch.float32, "out"), a.numel(), _stream())
     _check(rc, "svi_axpby")
+    return out
+
+
+# --------------------------------------------------------------------------------------------- encoders
+def embedding_gather(ids, table, out):
+    """out f32 [n, dim] = rows ids (int64 [n]) of table bf16 [vocab, dim]."""
+    n, (vocab, dim) = ids.numel(), table.shape
+    if ids.dtype != torch.int64 or not ids.is_contiguous() or not table.is_contiguous() or not out.is_contiguous():
+        raise RuntimeError("svi_b200.embedding_gather: ids must be contiguous int64, table / out contiguous")
+    rc = load().svi_embedding_gather(_ptr(ids, name="ids"), n, _ptr(table, torch.bfloat16, "table"), dim, vocab,
+                                     _ptr(out, torch.float32, "out"), _stream())
+    _check(rc, "svi_embedding_gather")
+    return out
+
+
+def rmsnorm_affine(x, weight, eps, out):
+    M, D = x.shape
+    if not x.is_contiguous() or not out.is_contiguous():
+        raise RuntimeError("svi_b200.rmsnorm_affine: x and out must be contiguous")
+    rc = load().svi_rmsnorm_affine(_ptr(x, torch.float32, "x"), M, D, float(eps), _ptr(weight, torch.float32, "weight"),
+                                   _ptr(out, torch.bfloat16, "out"), _stream())
+    _check(rc, "svi_rmsnorm_affine")
+    return out
+
+
+def layernorm_f32(x, gamma, beta, eps, out):
+    M, D = x.shape
+    if not x.is_contiguous() or not out.is_contiguous():
+        raise RuntimeError("svi_b200.layernorm_f32: x and out must be contiguous")
+    rc = load().svi_layernorm_f32(_ptr(x, torch.float32, "x"), M, D, float(eps), _ptr(gamma, torch.float32, "gamma"),
+                                  _ptr(beta, torch.float32, "beta"), _ptr(out, torch.float32, "out"), _stream())
+    _check(rc, "svi_layernorm_f32")
+    return out
+
+
+def mul_bf16(a, b, out):
+    if not (a.is_contiguous() and b.is_contiguous() and out.is_contiguous()) or a.shape != b.shape or a.shape != out.shape:
+        raise RuntimeError("svi_b200.mul_bf16: a, b, out must be contiguous and of one shape")
+    rc = load().svi_mul_bf16(_ptr(a, torch.bfloat16, "a"), _ptr(b, torch.bfloat16, "b"), _ptr(out, torch.bfloat16, "out"),
+                             a.numel(), _stream())
+    _check(rc, "svi_mul_bf16")
+    return out
+
+
+def attention_small(q, k, v, out, num_heads, head_dim, scale, bias_table=None, bucket=None, key_mask=None):
+    """Short-sequence attention with any head_dim <= 128, optional bucketed relative-position bias and key mask."""
+    ldq, ldk, ldv, ldo = (_rowmajor(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")))
+    if bucket is not None and (bucket.dtype != torch.int32 or tuple(bucket.shape) != (q.shape[0], k.shape[0]) or not bucket.is_contiguous()):
+        raise RuntimeError("svi_b200.attention_small: bucket must be contiguous int32 [Lq, Lk]")
+    if key_mask is not None and (key_mask.dtype != torch.int32 or key_mask.numel() != k.shape[0]):
+        raise RuntimeError("svi_b200.attention_small: key_mask must be int32 [Lk]")
+    rc = load().svi_attn_small(_ptr(q, torch.bfloat16, "q"), ldq, _ptr(k, torch.bfloat16, "k"), ldk, _ptr(v, torch.bfloat16, "v"), ldv,
+                               _ptr(out, torch.bfloat16, "out"), ldo, q.shape[0], k.shape[0], num_heads, head_dim, float(scale),
+                               _ptr(bias_table, torch.float32, "bias_table"), _ptr(bucket, name="bucket"),
+                               _ptr(key_mask, name="key_mask"), _stream())
+    _check(rc, "svi_attn_small")
     return out
 
 

@@ -15,34 +15,9 @@ from .utils import hash_state_dict_keys, init_weights_on_device, load_state_dict
 from .wan_video_dit import WanModel
 
 
-class _OutOfScopeEncoder(torch.nn.Module):
-    """umT5-XXL / CLIP ViT-H run once per clip and are outside the hot path.  Their
-    checkpoints are recognised so the failure is explicit instead of 'cannot detect the model type'."""
-    model_label = "encoder"
-
-    def __init__(self, *a, **k):
-        super().__init__()
-        raise NotImplementedError(
-            f"svi_b200: the {self.model_label} is outside the B200 hot-path scope (conditioning encoders are a "
-            f"'next' row, SURVEY.md §8f). Pass precomputed embeddings to the pipeline (prompt_emb= / image_emb=).")
-
-    @staticmethod
-    def state_dict_converter():
-        class _C:
-            def from_civitai(self, sd):
-                return sd
-        return _C()
-
-
-class WanTextEncoderStub(_OutOfScopeEncoder):
-    model_label = "umT5-XXL text encoder"
-
-
-class WanImageEncoderStub(_OutOfScopeEncoder):
-    model_label = "CLIP ViT-H image encoder"
-
-
 def _loader_table():
+    from .wan_video_image_encoder import WanImageEncoder
+    from .wan_video_text_encoder import WanTextEncoder
     from .wan_video_vae import WanVideoVAE
     return [
         # (keys_hash, keys_hash_with_shape, model_names, model_classes, resource)  — model_config.py:117-125
@@ -50,8 +25,8 @@ def _loader_table():
         (None, "aafcfd9672c3a2456dc46e1cb6e52c70", ["wan_video_dit"], [WanModel], "civitai"),
         (None, "6bfcfb3b342cb286ce886889d519a77e", ["wan_video_dit"], [WanModel], "civitai"),
         (None, "cb104773c6c2cb6df4f9529ad5c60d0b", ["wan_video_dit"], [WanModel], "diffusers"),
-        (None, "9c8818c2cbea55eca56c7b447df170da", ["wan_video_text_encoder"], [WanTextEncoderStub], "civitai"),
-        (None, "5941c53e207d62f20f9025686193c40b", ["wan_video_image_encoder"], [WanImageEncoderStub], "civitai"),
+        (None, "9c8818c2cbea55eca56c7b447df170da", ["wan_video_text_encoder"], [WanTextEncoder], "civitai"),
+        (None, "5941c53e207d62f20f9025686193c40b", ["wan_video_image_encoder"], [WanImageEncoder], "civitai"),
         (None, "1378ea763357eea97acdef78e65d6d96", ["wan_video_vae"], [WanVideoVAE], "civitai"),
         (None, "ccc42284ea13e1ad04693284c7a09be6", ["wan_video_vae"], [WanVideoVAE], "civitai"),
     ]

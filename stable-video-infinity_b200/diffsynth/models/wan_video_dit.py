@@ -420,11 +420,13 @@ class WanDiTEngine:
         self.k.gemm(ffn, bw.w_f2, x, bias=bw.b_f2, gate=mod[5], residual=x)
         return x
 
-    def forward(self, x, timestep, context, clip_feature=None, y=None, sp=None, out=None, tea_cache=None):
+    def forward(self, x, timestep, context, clip_feature=None, y=None, sp=None, out=None, tea_cache=None, add_condition=None):
         """One DiT forward (svi_video.py:74-137).  x [1,C,f,Hl,Wl] (any float dtype, CUDA) -> f32 [1,16,f,Hl,Wl].
 
         `context` may be a tensor [1,Lc,text_dim] or a ContextState from context_state().  `tea_cache`: a
-        pipelines.svi_video.TeaCache deciding per step whether the block stack runs or the cached residual is re-used."""
+        pipelines.svi_video.TeaCache deciding per step whether the block stack runs or the cached residual is re-used.
+        `add_condition`: [1, L, dim] token-space condition added to the patch embedding (SVI-Dance pose stem output,
+        reference svi_video.py:102-103)."""
         dev, d = self.device, self.dim
         if x.dim() != 5 or x.shape[0] != 1:
             raise RuntimeError(f"svi_b200: DiT forward expects x of shape [1,C,f,h,w], got {tuple(x.shape)}")
@@ -452,7 +454,14 @@ class WanDiTEngine:
             Ll = sp.local_rows(L)
             tok_l = tok[sp.row_offset: sp.row_offset + Ll]
         xr = self._buf("x", (Ll, d), torch.float32)
-        self.k.gemm(tok_l, self.w_patch, xr, bias=self.b_patch)
+        if add_condition is None:
+            self.k.gemm(tok_l, self.w_patch, xr, bias=self.b_patch)
+        else:
+            if tuple(add_condition.shape) != (1, L, d):
+                raise RuntimeError(f"svi_b200: add_condition must be [1, {L}, {d}], got {tuple(add_condition.shape)}")
+            cond = add_condition[0].to(device=dev, dtype=torch.float32).contiguous()
+            cond_l = cond if sp is None else cond[sp.row_offset: sp.row_offset + Ll]
+            self.k.gemm(tok_l, self.w_patch, xr, bias=self.b_patch, residual=cond_l)     # x = add_condition + patchify(x)
         if tea_cache is not None and tea_cache.check(self.model, xr, t_mod):
             tea_cache.update(xr)                      # skipped step: tokens + residual of the last computed step
         else:

@@ -106,14 +106,12 @@ def model_fn_wan_video(dit: WanModel, x: torch.Tensor, timestep: torch.Tensor, c
                        use_unified_sequence_parallel: bool = False, **kwargs):
     """Drop-in for reference svi_video.py:74-137: one DiT forward, result in x.dtype.  `context` may also be
     a ContextState (pre-projected conditioning)."""
-    if add_condition is not None:
-        raise NotImplementedError("pose add_condition (SVI-Dance) is outside the hot-path scope (SURVEY.md §8f.2)")
     sp = None
     if use_unified_sequence_parallel:
         from ..distributed.sequence_parallel import get_sp_group
         sp = get_sp_group()
     eng = dit.engine(x.device if x.is_cuda else None)
-    out = eng.forward(x, timestep, context, clip_feature, y, sp=sp, tea_cache=tea_cache)
+    out = eng.forward(x, timestep, context, clip_feature, y, sp=sp, tea_cache=tea_cache, add_condition=add_condition)
     return out.to(x.dtype)
 
 
@@ -121,9 +119,9 @@ class SVIVideoPipeline(BasePipeline):
     def __init__(self, device="cuda", torch_dtype=torch.float16, tokenizer_path=None, is_test=False, num_train_timesteps=1000):
         super().__init__(device=device, torch_dtype=torch_dtype)
         self.scheduler = FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True, num_train_timesteps=num_train_timesteps)
-        self.prompter = None          # callable(prompt, positive=bool) -> [1,512,4096] (umT5 is out of scope, §8f.1)
-        self.text_encoder = None
-        self.image_encoder = None     # object with encode_image([f32 1x3xHxW]) -> [1,257,1280] (CLIP, out of scope)
+        self.prompter = None          # WanPrompter once a text encoder is loaded; any callable(prompt, positive=bool) ->
+        self.text_encoder = None      # [1,512,4096] works too (precomputed embeddings)
+        self.image_encoder = None     # WanImageEncoder (or any object with encode_image([f32 1x3xHxW]) -> [1,257,1280])
         self.dit: WanModel = None
         self.vae = None
         self.model_names = ["text_encoder", "dit", "vae"]
@@ -146,8 +144,15 @@ class SVIVideoPipeline(BasePipeline):
         self.dit = model_manager.fetch_model("wan_video_dit")
         self.vae = model_manager.fetch_model("wan_video_vae")
         te = model_manager.fetch_model("wan_video_text_encoder", require_model_path=True)
-        if te is not None:
-            self.text_encoder = te[0]
+        if te is not None:        # reference :246-249: the tokenizer lives next to the T5 checkpoint
+            import os
+            from ..prompters import WanPrompter
+            self.text_encoder, te_path = te
+            self.prompter = WanPrompter()
+            self.prompter.fetch_models(self.text_encoder)
+            tok_dir = os.path.join(os.path.dirname(str(te_path)), "google/umt5-xxl")
+            if os.path.isdir(tok_dir):
+                self.prompter.fetch_tokenizer(tok_dir)
         self.image_encoder = model_manager.fetch_model("wan_video_image_encoder")
         if self.dit is not None:
             self.dit.to(self.device).eval()
@@ -176,8 +181,8 @@ class SVIVideoPipeline(BasePipeline):
     # ------------------------------------------------------------------ conditioning
     def encode_prompt(self, prompt, positive=True):
         if self.prompter is None:
-            raise RuntimeError("svi_b200: no prompt encoder attached. umT5-XXL is outside the hot-path scope "
-                               "(SURVEY.md §8f.1); set pipe.prompter = callable(prompt, positive) -> [1,512,4096].")
+            raise RuntimeError("svi_b200: no prompt encoder attached: load a wan_video_text_encoder checkpoint through the "
+                               "ModelManager or set pipe.prompter = callable(prompt, positive) -> [1,512,4096].")
         emb = self.prompter(prompt, positive=positive)
         return {"context": emb.to(self.device)}
 

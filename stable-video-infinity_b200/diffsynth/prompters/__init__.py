@@ -1,1 +1,5 @@
-"""Prompt encoding (umT5-XXL) is outside the hot-path scope; see pipelines.svi_video.encode_prompt."""
+"""Prompt encoding: WanPrompter (tokenizer + native umT5 encoder), reference diffsynth/prompters/."""
+from .base_prompter import BasePrompter
+from .wan_prompter import HuggingfaceTokenizer, WanPrompter
+
+__all__ = ["BasePrompter", "HuggingfaceTokenizer", "WanPrompter"]

@@ -156,6 +156,42 @@ def golden_vae(vae_mod):
     print("vae lat", tuple(lat.shape), "dec", tuple(dec.shape), "dec std", dec.std().item())
 
 
+def golden_encoders():
+    """Tiny umT5 text encoder and CLIP visual tower: outputs of the reference modules on seeded weights / inputs."""
+    import torchvision.transforms as T
+    from tools import synth_enc as SE
+    te = importlib.import_module("diffsynth.models.wan_video_text_encoder")
+    ie = importlib.import_module("diffsynth.models.wan_video_image_encoder")
+    res = {}
+    # ---- text encoder (wan_video_text_encoder.py:209-255), per-layer position bias (shared_pos=False), key mask
+    cfg = SE.TEXT_TINY
+    m = te.WanTextEncoder(shared_pos=False, **cfg).eval()
+    m.load_state_dict(SE.make_text_state_dict(cfg, seed=0))
+    ids, mask = SE.make_text_inputs(cfg, seq_len=24, valid=17, seed=0)
+    with torch.no_grad():
+        x0 = m.token_embedding(ids)
+        bias0 = m.blocks[0].pos_embedding(ids.shape[1], ids.shape[1])
+        blk0 = m.blocks[0](x0, mask, pos_bias=None)
+        out = m(ids, mask)
+    res.update(text_out=out.numpy(), text_bias0=bias0.numpy(), text_block0=blk0.numpy(), text_ids=ids.numpy(),
+               text_mask=mask.numpy())
+    # ---- CLIP visual tower through WanImageEncoder.encode_image (wan_video_image_encoder.py:864-880): bicubic resize,
+    #      [-1,1] -> [0,1] -> mean/std normalisation, all blocks but the last (use_31_block)
+    cfg = SE.CLIP_TINY
+    vit = ie.VisionTransformer(pool_type="token", pre_norm=True, post_norm=False, activation="gelu", **cfg).eval()
+    sd = {k[len("model.visual."):]: v for k, v in SE.make_clip_state_dict(cfg, seed=0).items()}
+    vit.load_state_dict(sd)
+    fake = types.SimpleNamespace(model=types.SimpleNamespace(image_size=cfg["image_size"], visual=vit),
+                                 transforms=T.Compose([T.Normalize(mean=SE.CLIP_MEAN, std=SE.CLIP_STD)]))
+    img = SE.make_clip_image(50, 70, seed=0)
+    with torch.no_grad():
+        out = ie.WanImageEncoder.encode_image(fake, [img.clone()])
+        pre = torch.nn.functional.interpolate(img.clone(), size=(cfg["image_size"],) * 2, mode="bicubic", align_corners=False)
+    res.update(clip_out=out.numpy(), clip_resized=pre.numpy())
+    np.savez_compressed(os.path.join(HERE, "enc_tiny.npz"), **res)
+    print("encoders: text", tuple(res["text_out"].shape), "clip", tuple(res["clip_out"].shape))
+
+
 def teacache_inputs(steps=12, d=48, L=40, seed=5):
     """Seeded inputs of the TeaCache fixture (shared with the tests): per-step modulation [1,6,d], block-stack input and
     output token streams [1,L,d].  The modulation drifts by ~5 % per step with two jumps, so some steps skip."""
@@ -221,5 +257,7 @@ if __name__ == "__main__":
         golden_scheduler(fm)
     if a.only in ("", "teacache"):
         golden_teacache(a.ref)
+    if a.only in ("", "enc"):
+        golden_encoders()
     if a.only in ("", "vae") and os.path.exists(os.path.join(ROOT, "tools", "synth_vae.py")):
         golden_vae(vae_mod)

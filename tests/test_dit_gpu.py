@@ -89,6 +89,24 @@ def test_model_fn_and_cfg_euler_step_match_oracle():
     assert inside > 0.5 and mx < 0.15 and rel < 2e-2
 
 
+def test_add_condition_is_added_to_the_patch_embedding():
+    """model_fn_wan_video(add_condition=...) — the token-space hook the SVI-Dance pose stem feeds (svi_video.py:102-103)."""
+    from diffsynth.pipelines.svi_video import model_fn_wan_video
+    from oracle import wan_dit_oracle as O
+    cfg = synth.CFG_TINY_T2V
+    sd = _sd(cfg, 6)
+    a = synth.make_dit_inputs(cfg, 3, 8, 8, seed=6, ctx_len=32)
+    m = _build(cfg, sd)
+    cond = torch.randn(1, 3 * 4 * 4, cfg["dim"], generator=torch.Generator().manual_seed(9)).to(torch.bfloat16).float()
+    ts = torch.tensor([700.0])
+    out = model_fn_wan_video(m, a["x"].cuda(), ts, a["context"].cuda(), add_condition=cond.cuda()).float().cpu()
+    ref = O.dit_forward(sd, cfg, a["x"], ts, a["context"], add_condition=cond)
+    base = O.dit_forward(sd, cfg, a["x"], ts, a["context"])
+    inside, mx, rel = _stats(out, ref)
+    print(f"add_condition: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
+    assert inside > 0.80 and rel < 4e-3 and (ref - base).abs().max() > 1e-2
+
+
 def test_teacache_denoise_matches_oracle():
     """8-step CFG denoise with TeaCache (reference svi_video.py:23-72,114-126): the native path must take the same
     skip decisions as the oracle and land on the same latents.  Random-init weights make the modulation change by

@@ -82,6 +82,44 @@ def test_models_fail_loudly_without_cuda():
         WanVideoVAE().engine("cpu")
 
 
+def test_encoders_fail_loudly_without_cuda_and_host_tables_match_the_oracle():
+    from diffsynth.models.wan_video_image_encoder import WanImageEncoder
+    from diffsynth.models.wan_video_text_encoder import WanTextEncoder, relative_position_buckets
+    from oracle import wan_encoders_oracle as E
+    from tools import synth_enc as SE
+    with pytest.raises(RuntimeError, match="CUDA"):
+        WanTextEncoder(**SE.TEXT_TINY).engine("cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        WanImageEncoder(**SE.CLIP_TINY).engine("cpu")
+    for L in (24, 512):
+        assert torch.equal(relative_position_buckets(L, L, 32).long(), E.t5_relative_buckets(L, L, 32))
+
+
+def test_encoder_key_contracts():
+    """umT5: the parameter names hash to the reference's checkpoint fingerprint (model_config.py:122).  CLIP: the real
+    checkpoint also carries the text tower, which the converter drops (wan_video_image_encoder.py:894-901); what is left
+    must be exactly the visual-tower names the reference module registers."""
+    from diffsynth.models.model_manager import ModelManager
+    from diffsynth.models.utils import hash_state_dict_keys
+    from diffsynth.models.wan_video_image_encoder import WanImageEncoder
+    from diffsynth.models.wan_video_text_encoder import WanTextEncoder
+    from tools import synth_enc as SE
+    with torch.device("meta"):
+        te = WanTextEncoder()
+        ie = WanImageEncoder()
+    sd = te.state_dict()
+    assert hash_state_dict_keys(sd, with_shape=True) == "9c8818c2cbea55eca56c7b447df170da"
+    det = ModelManager(torch_dtype=torch.bfloat16, device="cpu").model_detector[0]
+    names, classes, _ = det._lookup(sd)
+    assert names == ["wan_video_text_encoder"] and classes == [WanTextEncoder]
+    want = set(SE.clip_param_shapes(SE.CLIP_VIT_H)) | {"model.log_scale"}
+    have = {k: tuple(v.shape) for k, v in ie.state_dict().items()}
+    assert set(have) == want and all(have[k] == v for k, v in SE.clip_param_shapes(SE.CLIP_VIT_H).items())
+    ckpt = {"log_scale": 0, "visual.head": 1, "textual.token_embedding.weight": 2, "visual.transformer.0.norm1.weight": 3}
+    conv = WanImageEncoder.state_dict_converter().from_civitai(ckpt)
+    assert set(conv) == {"model.log_scale", "model.visual.head", "model.visual.transformer.0.norm1.weight"}
+
+
 # ------------------------------------------------------------------------------------------- key contracts
 def test_parameter_names_hash_to_the_reference_checkpoint_fingerprints():
     """The reference detects checkpoints by md5 of sorted 'key:shape' strings (model_config.py:117-125)."""

@@ -257,6 +257,41 @@ def sec_perf_gemm_epi():
         print(f"[PERF] gemm {name}: {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def sec_perf_ew():
+    """Row kernels at the bench shape, algorithmic bytes / time (HBM roofline: MEASURED_PEAKS.json hbm_gbps)."""
+    g = torch.Generator(device="cpu").manual_seed(8)
+    L, d = 32760, 1536
+    x = torch.randn(L, d, generator=g).to(dev)
+    sc, sh = torch.randn(d, generator=g).to(dev) * 0.1, torch.randn(d, generator=g).to(dev) * 0.1
+    h = torch.empty(L, d, device=dev, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+
+    def timed(fn, nbytes, name, cold):
+        ts = []
+        for _ in range(6):
+            if cold:
+                flush.zero_()      # evict x / h from L2 and leave 256 MB of dirty lines, as the preceding GEMM does
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = sorted(ts)[len(ts) // 2]
+        print(f"[PERF] {name} ({'after a 256 MB write' if cold else 'back to back'}): {ms * 1e3:.1f} us = {nbytes / ms / 1e6:.0f} GB/s", flush=True)
+
+    for cold in (False, True):
+        timed(lambda: nv.layernorm_modulate(x, h, 1e-6, scale=sc, shift=sh), L * d * 6, "layernorm_modulate L=32760 d=1536", cold)
+    qkv = torch.randn(L, 3 * d, generator=g).to(dev, torch.bfloat16)
+    ss = torch.rand(L, 2, generator=g).to(dev) * d
+    w = torch.randn(d, generator=g).to(dev)
+    f, hh, ww = 21, 30, 52
+    cos = torch.randn(L, 64, generator=g).to(dev)
+    sin = torch.randn(L, 64, generator=g).to(dev)
+    for cold in (False, True):
+        timed(lambda: nv.rmsnorm_rope(qkv[:, :d], ss, 0, 1e-6, w, cos, sin, 0), L * d * 4, "rmsnorm_rope (q slice of qkv)", cold)
+
+
 def sec_perf_attn():
     g = torch.Generator(device="cpu").manual_seed(6)
     scale = 128 ** -0.5
