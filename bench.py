@@ -264,8 +264,10 @@ def main():
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         step(args.warmup + i)
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps     # CPU time to ENQUEUE one step (launch-bound check)
     e1.record()
     sync()
     clocks = sampler.stop() if rank == 0 else None
@@ -364,7 +366,7 @@ def main():
                        "numerics": "bf16 operands, fp32 accumulate/residual/norm/softmax"},
             "dit_tflops": flops_step / (ms_per_step * 1e-3) / 1e12,
             "dit_tflops_frac_of_peak": flops_step / (ms_per_step * 1e-3) / 1e12 / (peak * world),
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e, "clip": clip}
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof, "e2e": e2e, "clip": clip}
     if not args.no_cpu_baseline and world == 1:
         t_blk, cores = cpu_block_baseline(cfg, L, ctx_len)
         step_s = t_blk * cfg["num_layers"] * 2

@@ -95,39 +95,42 @@ layernorm_modulate_kernel(const float* __restrict__ x, int D, float eps, const f
 constexpr int LNW_WARPS = 8;
 constexpr int LNW_MAX_VEC = 16;  // float4 per lane -> D <= 2048
 
-__global__ void __launch_bounds__(LNW_WARPS * 32)
+// NV > 0: D == 128 * NV exactly (no bounds predicates, fewer registers -> 3 blocks per SM); NV == 0: any D <= 2048.
+template <int NV>
+__global__ void __launch_bounds__(LNW_WARPS * 32, NV > 0 ? 3 : 2)
 layernorm_modulate_warp_kernel(const float* __restrict__ x, int M, int D, float eps, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const float* __restrict__ scale,
                                const float* __restrict__ shift, __nv_bfloat16* __restrict__ y) {
+  constexpr int CAP = NV > 0 ? NV : LNW_MAX_VEC;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * LNW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
   const float4* xr = reinterpret_cast<const float4*>(x + row * D);
-  const int nvec = D >> 2;
-  float4 v[LNW_MAX_VEC];
+  const int nvec = NV > 0 ? NV * 32 : (D >> 2);
+  float4 v[CAP];
 #pragma unroll
-  for (int i = 0; i < LNW_MAX_VEC; ++i) {
+  for (int i = 0; i < CAP; ++i) {
     const int idx = lane + i * 32;
-    if (idx < nvec) v[i] = __ldcs(xr + idx);   // streaming: the fp32 residual row is not re-read soon
+    if (NV > 0 || idx < nvec) v[i] = __ldcs(xr + idx);   // streaming: the fp32 residual row is not re-read soon
   }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LNW_MAX_VEC; ++i)
-    if (lane + i * 32 < nvec) s += v[i].x + v[i].y + v[i].z + v[i].w;
+  for (int i = 0; i < CAP; ++i)
+    if (NV > 0 || lane + i * 32 < nvec) s += v[i].x + v[i].y + v[i].z + v[i].w;
   const float mean = warp_sum(s) / (float)D;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LNW_MAX_VEC; ++i)
-    if (lane + i * 32 < nvec) {
+  for (int i = 0; i < CAP; ++i)
+    if (NV > 0 || lane + i * 32 < nvec) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       q += a * a + b * b + c * c + d * d;
     }
   const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
   uint2* yr = reinterpret_cast<uint2*>(y + row * D);
 #pragma unroll
-  for (int i = 0; i < LNW_MAX_VEC; ++i) {
+  for (int i = 0; i < CAP; ++i) {
     const int idx = lane + i * 32;
-    if (idx < nvec) {
+    if (NV > 0 || idx < nvec) {
       float o[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
       if (gamma) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
@@ -148,7 +151,7 @@ layernorm_modulate_warp_kernel(const float* __restrict__ x, int M, int D, float 
       uint2 pk;
       pk.x = pack_bf16x2(o[0], o[1]);
       pk.y = pack_bf16x2(o[2], o[3]);
-      yr[idx] = pk;
+      __stcs(yr + idx, pk);
     }
   }
 }
@@ -327,9 +330,15 @@ extern "C" int svi_layernorm_modulate(const float* x, int32_t M, int32_t D, floa
               "svi_layernorm_modulate: need M>0, D %% 8 == 0, D <= 8192 (M=%d D=%d)", M, D);
   SVI_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0,
               "svi_layernorm_modulate: alignment");
-  if (D <= 128 * LNW_MAX_VEC)
-    layernorm_modulate_warp_kernel<<<(M + LNW_WARPS - 1) / LNW_WARPS, LNW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, M, D, eps, gamma, beta, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16));
+  const int wgrid = (M + LNW_WARPS - 1) / LNW_WARPS;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  if (D == 1536)        // Wan 1.3B
+    layernorm_modulate_warp_kernel<12><<<wgrid, LNW_WARPS * 32, 0, st>>>(x, M, D, eps, gamma, beta, scale, shift, yb);
+  else if (D == 1280)   // CLIP ViT-H
+    layernorm_modulate_warp_kernel<10><<<wgrid, LNW_WARPS * 32, 0, st>>>(x, M, D, eps, gamma, beta, scale, shift, yb);
+  else if (D <= 128 * LNW_MAX_VEC)
+    layernorm_modulate_warp_kernel<0><<<wgrid, LNW_WARPS * 32, 0, st>>>(x, M, D, eps, gamma, beta, scale, shift, yb);
   else
     layernorm_modulate_kernel<<<M, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         x, D, eps, gamma, beta, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16));
