@@ -1,4 +1,4 @@
-# Builds the C-ABI kernel library (sm_100a only) and the C oracle helpers.
+# Builds the C-ABI kernel library (sm_100a only): stable-video-infinity_b200/lib/libsvi_b200.so
 NVCC ?= nvcc
 PKG := stable-video-infinity_b200
 CSRC := $(PKG)/csrc

@@ -179,7 +179,7 @@ def vae_clip_leg(dev, f, h, w, ms_per_step):
     return {"vae_decode_ms": out["decode"], "vae_encode_ms": out["encode"], "denoise_s": CLIP_STEPS * ms_per_step / 1e3,
             "clip_s": clip_s, "clips_per_hour": 3600.0 / clip_s, "pixel_frames_per_s": frames / clip_s,
             "note": "81f x 480x832 clip = VAE encode + 50 CFG steps (extrapolated from the timed steps) + VAE decode; "
-                    "text/CLIP encoders excluded (out of scope, SURVEY.md §8f.1)"}
+                    "the umT5 / CLIP encoders add ~57 ms per clip (2 prompts x 25 ms + 7 ms, tools/enc_bench.py) and are not timed here"}
 
 
 def main():
@@ -264,10 +264,8 @@ def main():
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    host_t0 = time.perf_counter()
     for i in range(args.steps):
         step(args.warmup + i)
-    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps     # CPU time to ENQUEUE one step (launch-bound check)
     e1.record()
     sync()
     clocks = sampler.stop() if rank == 0 else None
@@ -275,6 +273,13 @@ def main():
     launches = eng.k.launches - launches0
     attn_ms = [a.elapsed_time(b) for a, b in eng.attn_events]
     eng.attn_events = None
+    # CPU time to ENQUEUE one step, measured on an empty launch queue (inside the timed loop the CPU runs ahead until the
+    # driver's queue is full and then only measures back-pressure): must stay well below ms_per_step or the job is
+    # launch-bound
+    host_t0 = time.perf_counter()
+    step(args.warmup + args.steps)
+    host_ms = (time.perf_counter() - host_t0) * 1e3
+    sync()
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -252,11 +252,24 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tile_coords(tile, num_m, num_n, group_m, m_blk, n_blk);
       const int row = m_blk * 2 * BM + (int)rank * BM + row_in_tile;
       const bool row_ok = row < M;
-      if (ep.residual && row_ok) {
-        // the residual rows of this tile are needed only after the whole K loop: pull them into L2 now
-        const char* rp = reinterpret_cast<const char*>(ep.residual + (long long)row * ep.ldr + n_blk * BN + col_half * 128);
-        const int cols = min(128, N - (n_blk * BN + col_half * 128));
-        for (int b = 0; b < cols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
+      if (ep.residual) {
+        // Residual rows -> L2 ahead of use.  When the epilogue is the slower side (K = 1536 with an fp32 residual) it
+        // starts a tile the moment it has finished the previous one, so a prefetch of THIS tile would be issued only
+        // nanoseconds before its first loads; the tile this CTA drains NEXT is prefetched instead (one K loop ahead),
+        // and the very first tile prefetches itself.
+        auto prefetch_tile = [&](int t) {
+          int mb, nb;
+          tile_coords(t, num_m, num_n, group_m, mb, nb);
+          const int r = mb * 2 * BM + (int)rank * BM + row_in_tile;
+          const int c0 = nb * BN + col_half * 128;
+          if (r < M && c0 < N) {
+            const char* rp = reinterpret_cast<const char*>(ep.residual + (long long)r * ep.ldr + c0);
+            const int cols = min(128, N - c0);
+            for (int b = 0; b < cols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
+          }
+        };
+        if (tile == pair) prefetch_tile(tile);
+        if (tile + num_pairs < num_tiles) prefetch_tile(tile + num_pairs);
       }
       // per-column vectors of this tile -> shared memory while the K loop still runs (every lane needs the same 8
       // values at a time: an L1/L2 round trip per group of 8 columns was half of all epilogue stall samples)

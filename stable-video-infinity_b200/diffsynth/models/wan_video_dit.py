@@ -158,10 +158,13 @@ class ContextState:
     """Step-invariant conditioning of one prompt: embedded context rows and every layer's cross-attention K/V
     (reference recomputes text_embedding + K/V projections on every forward, svi_video.py:92, wan_video_dit.py:273-274)."""
 
-    def __init__(self, n_img, n_txt):
+    def __init__(self, n_img, n_txt, n_layers=0, width=0, device=None):
         self.n_img, self.n_txt = n_img, n_txt
-        self.kv_txt = []   # per layer bf16 [n_txt, 2d]  (k normalised | v)
-        self.kv_img = []   # per layer bf16 [257, 2d]
+        # one allocation for all layers (a captured CUDA graph reads a fixed copy of it: one copy_ per forward)
+        self.kv_txt_all = torch.empty(n_layers, n_txt, 2 * width, device=device, dtype=torch.bfloat16) if n_layers else None
+        self.kv_img_all = torch.empty(n_layers, 257, 2 * width, device=device, dtype=torch.bfloat16) if n_layers and n_img else None
+        self.kv_txt = [] if self.kv_txt_all is None else list(self.kv_txt_all.unbind(0))     # per layer bf16 [n_txt, 2d]  (k normalised | v)
+        self.kv_img = [] if self.kv_img_all is None else list(self.kv_img_all.unbind(0))     # per layer bf16 [257, 2d]
 
 
 class _CountingNative:
@@ -238,6 +241,9 @@ class WanDiTEngine:
         self._ws = {}
         self._ctx_cache = OrderedDict()
         self._time_cache = OrderedDict()
+        self._graphs = {}
+        import os
+        self.use_graphs = os.environ.get("SVI_CUDA_GRAPHS", "1") != "0"
         self.attn_events = None  # bench.py: list collecting (start, end) events around self-attention launches
         self.k = _CountingNative()  # every native launch goes through this proxy (bench.py reads the count)
 
@@ -318,19 +324,17 @@ class WanDiTEngine:
             self.k.gemm(c0, self.ie_w1, c1, bias=self.ie_b1, act=nv.ACT_GELU_ERF)
             self.k.gemm(c1, self.ie_w3, c2, bias=self.ie_b3)
             self.k.layernorm_modulate(c2, emb[:257], self.ie_ln4[2], gamma=self.ie_ln4[0], beta=self.ie_ln4[1])
-        st = ContextState(n_img, n_txt)
-        for bw in self.blocks:
-            kv = torch.empty(n_txt, 2 * d, device=dev, dtype=torch.bfloat16)
+        st = ContextState(n_img, n_txt, len(self.blocks), d, dev)
+        for li, bw in enumerate(self.blocks):
+            kv = st.kv_txt[li]
             ss = torch.zeros(n_txt, 1, device=dev, dtype=torch.float32)
             self.k.gemm(emb[n_img:], bw.w_ckv, kv, bias=bw.b_ckv, sumsq=ss, sumsq_group_cols=d)
             self.k.rmsnorm_rope(kv[:, :d], ss, 0, bw.eps_qk, bw.cnk)
-            st.kv_txt.append(kv)
             if n_img:
-                kvi = torch.empty(257, 2 * d, device=dev, dtype=torch.bfloat16)
+                kvi = st.kv_img[li]
                 ssi = torch.zeros(257, 1, device=dev, dtype=torch.float32)
                 self.k.gemm(emb[:257], bw.w_ckv_img, kvi, bias=bw.b_ckv_img, sumsq=ssi, sumsq_group_cols=d)
                 self.k.rmsnorm_rope(kvi[:, :d], ssi, 0, bw.eps_qk, bw.cnk_img)
-                st.kv_img.append(kvi)
         self._ctx_cache[key] = (weakref.ref(context), None if clip_feature is None else weakref.ref(clip_feature), st)
         while len(self._ctx_cache) > 8:
             self._ctx_cache.popitem(last=False)
@@ -444,6 +448,57 @@ class WanDiTEngine:
         t, t_mod = self.time_state(timestep)
         ctx = context if isinstance(context, ContextState) else self.context_state(context, clip_feature)
         cos, sin = self.rope(f, hh, ww)
+        nh = self.w_head.shape[0]
+        if out is None:
+            out = torch.empty(1, nh // 4, f, Hl, Wl, device=dev, dtype=torch.float32)
+        if (self.use_graphs and sp is None and tea_cache is None and add_condition is None and self.attn_events is None
+                and self.k.events is None and out.is_contiguous()):
+            return self._graph_forward(xs, ys, t, t_mod, ctx, cos, sin, out)
+        return self._run(xs, ys, t, t_mod, ctx, cos, sin, out, sp, tea_cache, add_condition)
+
+    # ------------------------------------------------------------------ CUDA-graph replay (single GPU)
+    def _graph_forward(self, xs, ys, t, t_mod, ctx, cos, sin, out):
+        """The whole forward is ~460 launches of fixed shape: after one eager call per input geometry it is captured into a
+        CUDA graph that reads fixed copies of (latents, y, t, t_mod, cross-attention K|V) and writes a fixed output, so a
+        step costs a handful of small copies + one replay on the host instead of ~15 ms of Python per forward
+        (`host_enqueue_ms_per_step` in bench.py).  Sequence-parallel, TeaCache and timing modes stay eager."""
+        key = (tuple(xs.shape), None if ys is None else tuple(ys.shape), ctx.n_txt, ctx.n_img)
+        ent = self._graphs.get(key)
+        if ent is None:                       # first call of this geometry: eager (allocates every work buffer)
+            self._graphs[key] = {"graph": None}
+            return self._run(xs, ys, t, t_mod, ctx, cos, sin, out, None, None, None)
+        if ent["graph"] is None:
+            st = ContextState(ctx.n_img, ctx.n_txt, len(self.blocks), self.dim, self.device)
+            ent.update(xs=torch.empty_like(xs), ys=None if ys is None else torch.empty_like(ys), t=torch.empty_like(t),
+                       t_mod=torch.empty_like(t_mod), ctx=st, out=torch.empty_like(out))
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            n0 = self.k.launches
+            with torch.cuda.graph(g):
+                self._run(ent["xs"], ent["ys"], ent["t"], ent["t_mod"], st, cos, sin, ent["out"], None, None, None)
+            ent["launches"] = self.k.launches - n0
+            self.k.launches = n0               # recorded, not executed
+            ent["graph"] = g
+        ent["xs"].copy_(xs)
+        if ys is not None:
+            ent["ys"].copy_(ys)
+        ent["t"].copy_(t)
+        ent["t_mod"].copy_(t_mod)
+        ent["ctx"].kv_txt_all.copy_(ctx.kv_txt_all)
+        if ctx.n_img:
+            ent["ctx"].kv_img_all.copy_(ctx.kv_img_all)
+        ent["graph"].replay()
+        self.k.launches += ent["launches"]
+        out.copy_(ent["out"])
+        return out
+
+    def _run(self, xs, ys, t, t_mod, ctx, cos, sin, out, sp, tea_cache, add_condition):
+        """Device work of one forward on prepared inputs (everything here is stream-ordered and allocation-free after the
+        first call of a geometry, so it can be captured)."""
+        dev, d = self.device, self.dim
+        C0, f, Hl, Wl = xs.shape
+        hh, ww = Hl // 2, Wl // 2
+        L = f * hh * ww
         # patchify: im2col gather + GEMM (Conv3d k=s=(1,2,2), wan_video_dit.py:473-477)
         tok = self._buf("tok", (L, self.kpatch), torch.bfloat16)
         self.k.patchify_gather(xs, ys, tok)
@@ -480,8 +535,6 @@ class WanDiTEngine:
         self.k.gemm(h, self.w_head, ho_l, bias=self.b_head)
         if sp is not None:
             sp.all_gather_rows(ho)
-        if out is None:
-            out = torch.empty(1, nh // 4, f, Hl, Wl, device=dev, dtype=torch.float32)
         self.k.unpatchify(ho, out[0])
         return out
 

@@ -89,6 +89,29 @@ def test_model_fn_and_cfg_euler_step_match_oracle():
     assert inside > 0.5 and mx < 0.15 and rel < 2e-2
 
 
+def test_graph_replay_equals_eager_forward():
+    """From the second call of a geometry on, the single-GPU forward is a CUDA-graph replay on fixed copies of the inputs:
+    it must return exactly what the eager kernel sequence returns, for changing latents, timesteps and prompts."""
+    cfg = synth.CFG_TINY_I2V
+    sd = _sd(cfg, 8)
+    m = _build(cfg, sd)
+    eng = m.engine("cuda")
+    cases = []
+    for k in range(4):
+        inp = synth.make_dit_inputs(cfg, 2, 8, 8, seed=20 + k, ctx_len=24)
+        cases.append((inp["x"].cuda(), 900.0 - 200.0 * k, inp["context"].cuda(), inp["clip_feature"].cuda(), inp["y"].cuda()))
+    eng.use_graphs = False
+    want = [eng.forward(x, t, c, cf, y).clone() for x, t, c, cf, y in cases]
+    eng.use_graphs = True
+    n0 = eng.k.launches
+    got = [eng.forward(x, t, c, cf, y).clone() for x, t, c, cf, y in cases]       # call 1 eager, 2 captures, 3-4 replay
+    assert len(eng._graphs) == 1 and next(iter(eng._graphs.values()))["graph"] is not None
+    for a, b in zip(got, want):      # same kernels, same order; only the fp32 atomics of the row sums may reassociate
+        assert (a - b).abs().max().item() < 1e-3
+    per_forward = next(iter(eng._graphs.values()))["launches"]
+    assert per_forward > 20 and eng.k.launches - n0 >= 4 * per_forward      # replays are counted like eager launches
+
+
 def test_add_condition_is_added_to_the_patch_embedding():
     """model_fn_wan_video(add_condition=...) — the token-space hook the SVI-Dance pose stem feeds (svi_video.py:102-103)."""
     from diffsynth.pipelines.svi_video import model_fn_wan_video
