@@ -474,7 +474,8 @@ class WanDiTEngine:
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             n0 = self.k.launches
-            with torch.cuda.graph(g):
+            # thread_local: other threads (NCCL watchdog, the bench's clock sampler) may keep calling the CUDA runtime
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._run(ent["xs"], ent["ys"], ent["t"], ent["t_mod"], st, cos, sin, ent["out"], None, None, None)
             ent["launches"] = self.k.launches - n0
             self.k.launches = n0               # recorded, not executed
