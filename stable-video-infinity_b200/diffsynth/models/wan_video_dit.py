@@ -613,10 +613,10 @@ class WanModel(nn.Module):
         return out
 
     def forward(self, x, timestep, context, clip_feature=None, y=None, **kwargs):
-        if kwargs.get("add_condition") is not None or kwargs.get("audio_embed_tuple") is not None:
-            raise NotImplementedError("pose / audio conditioning is outside the hot-path scope (SURVEY.md §8f)")
+        if kwargs.get("audio_embed_tuple") is not None:
+            raise NotImplementedError("SVI-Talk audio conditioning is outside the hot-path scope (SURVEY.md §8f.2)")
         dev = x.device if x.is_cuda else None
-        out = self.engine(dev).forward(x, timestep, context, clip_feature, y)
+        out = self.engine(dev).forward(x, timestep, context, clip_feature, y, add_condition=kwargs.get("add_condition"))
         return out.to(x.dtype) if x.is_floating_point() else out
 
     @staticmethod
