@@ -561,7 +561,8 @@ class WanModel(nn.Module):
         self.blocks = nn.ModuleList([DiTBlock(has_image_input, dim, num_heads, ffn_dim, eps, enable_multitalk)
                                      for _ in range(num_layers)])
         self.head = Head(dim, out_dim, self.patch_size, eps)
-        self.freqs = precompute_freqs_cis_3d(dim // num_heads)
+        with torch.device("cpu"):      # a table, not a parameter: must be real even when the loader constructs on "meta"
+            self.freqs = precompute_freqs_cis_3d(dim // num_heads)
         if has_image_input:
             self.img_emb = MLP(1280, dim)
         self.enable_multitalk = enable_multitalk

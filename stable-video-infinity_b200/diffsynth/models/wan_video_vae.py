@@ -497,8 +497,9 @@ class WanVideoVAE(nn.Module):
                 0.4134, -0.0715, 0.5517, -0.3632, -0.1922, -0.9497, 0.2503, -0.2921]
         std = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743,
                3.2687, 2.1526, 2.8652, 1.5579, 1.6382, 1.1253, 2.8251, 1.9160]
-        self.mean = torch.tensor(mean)
-        self.std = torch.tensor(std)
+        with torch.device("cpu"):      # constants, not parameters: must be real even when the loader constructs on "meta"
+            self.mean = torch.tensor(mean)
+            self.std = torch.tensor(std)
         self.scale = [self.mean, 1.0 / self.std]
         self.model = VideoVAE_(z_dim=z_dim).eval().requires_grad_(False)
         self.upsampling_factor = 8

@@ -95,6 +95,25 @@ def test_encoders_fail_loudly_without_cuda_and_host_tables_match_the_oracle():
         assert torch.equal(relative_position_buckets(L, L, 32).long(), E.t5_relative_buckets(L, L, 32))
 
 
+def test_meta_construction_keeps_constant_tables_real():
+    """ModelManager builds models under init_weights_on_device() (device 'meta') and then assigns the checkpoint tensors
+    (reference model_manager.py:57-105).  Tables that are not parameters — the RoPE frequencies, the VAE latent
+    statistics — must stay real tensors, or the first forward after loading a real checkpoint would read meta data."""
+    from diffsynth.models.utils import init_weights_on_device
+    from diffsynth.models.wan_video_dit import WanModel
+    from diffsynth.models.wan_video_vae import WanVideoVAE
+    from tools import synth
+    with init_weights_on_device():
+        m = WanModel(**synth.CFG_TINY_I2V)
+        v = WanVideoVAE()
+    assert all(p.is_meta for p in m.parameters())
+    assert all(not f.is_meta and f.device.type == "cpu" for f in m.freqs) and m.freqs[0].shape == (1024, 22)
+    assert not v.mean.is_meta and not v.std.is_meta and v.mean.numel() == 16
+    sd = synth.make_dit_state_dict(synth.CFG_TINY_I2V, seed=0)
+    m.load_state_dict(sd, assign=True)
+    assert not any(p.is_meta for p in m.parameters())
+
+
 def test_encoder_key_contracts():
     """umT5: the parameter names hash to the reference's checkpoint fingerprint (model_config.py:122).  CLIP: the real
     checkpoint also carries the text tower, which the converter drops (wan_video_image_encoder.py:894-901); what is left
