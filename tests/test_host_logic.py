@@ -30,6 +30,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.svi_abi_version() == 2
 
 
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: the header must compile as C99 (no C++ or torch types in the signatures)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-pedantic", os.path.join(ROOT, "include", "svi_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stderr.strip() == "", r.stderr
+
+
 def test_library_contains_blackwell_tensor_and_tma_instructions():
     """SASS evidence that the hot kernels are tcgen05 / TMA code (B200_PROFILING.md: UTC*MMA, LDTM/STTM, UTMALDG)."""
     from diffsynth import _native as nv
