@@ -290,38 +290,53 @@ def main():
 
     # ---- e2e leg: same step through the public API (model_fn_wan_video) with HOST buffers: every step copies the
     # latents and both prompt embeddings from pinned host memory and reads the updated latents back.
+    # With N > 1 every rank does the same from its own pinned buffers and the step is the public multi-GPU call
+    # (SequenceParallelGroup.cfg_parallel_step); the time is the max over ranks.
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         out_host = torch.empty_like(lat_host).pin_memory()
         lat_h = lat_host.clone().pin_memory()
 
         def e2e_step(i):
             k = i % CLIP_STEPS
             ts = sched.timesteps[k].reshape(1)
+            sigma = float(sched.sigmas[k])
+            nxt = float(sched.sigmas[k + 1]) if k + 1 < CLIP_STEPS else 0.0
             x = lat_h.to(dev, non_blocking=True)
             c1 = ctx_pos_host.to(dev, non_blocking=True)
             c2 = ctx_neg_host.to(dev, non_blocking=True)
-            vc = model_fn_wan_video(model, x, ts, c1)
-            vu = model_fn_wan_video(model, x, ts, c2)
-            nv.cfg_euler_step(x, vc, vu, CFG_SCALE, float(sched.sigmas[k]), float(sched.sigmas[k + 1]) if k + 1 < CLIP_STEPS else 0.0)
+            if sp is None:
+                vc = model_fn_wan_video(model, x, ts, c1)
+                vu = model_fn_wan_video(model, x, ts, c2)
+                nv.cfg_euler_step(x, vc, vu, CFG_SCALE, sigma, nxt)
+            else:
+                both = sp.cfg_groups == 1                     # CFG-parallel ranks need only their own branch's prompt
+                cpx = eng.context_state(c1) if both or sp.cfg_idx == 0 else None
+                cnx = eng.context_state(c2) if both or sp.cfg_idx == 1 else None
+                sp.cfg_parallel_step(eng, x, float(ts[0]), cpx, cnx, v_c, v_u, CFG_SCALE, sigma, nxt)
             out_host.copy_(x, non_blocking=True)
             torch.cuda.current_stream().synchronize()     # the caller consumes the host result every step
             lat_h.copy_(out_host)
 
         for i in range(max(1, args.warmup // 2)):
             e2e_step(i)
-        torch.cuda.synchronize()
+        sync()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(args.steps):
             e2e_step(i)
         b.record()
-        torch.cuda.synchronize()
+        sync()
         e2e_ms = a.elapsed_time(b) / args.steps
+        if world > 1:
+            tt = torch.tensor([e2e_ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_ms = tt.item()
         h2d = lat_host.numel() * 4 + 2 * ctx_pos_host.numel() * 4
+        api = ("diffsynth.pipelines.svi_video.model_fn_wan_video x2 + svi_cfg_euler_step, pinned host buffers" if sp is None else
+               "SequenceParallelGroup.cfg_parallel_step (WanDiTEngine.context_state + forward per rank), pinned host buffers per rank")
         e2e = {"value": f / (CLIP_STEPS * e2e_ms / 1e3), "unit": "latent_frames/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4,
-               "api": "diffsynth.pipelines.svi_video.model_fn_wan_video x2 + svi_cfg_euler_step, pinned host buffers"}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4, "api": api}
 
     if args.breakdown and world == 1:
         eng.k.events = []
