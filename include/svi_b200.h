@@ -224,6 +224,9 @@ int svi_vae_upsample2x(const float* x, int32_t H, int32_t W, int32_t C, void* y_
 /* space-to-depth for the stride-2 Conv2d of downsample (:108-113): x f32 [H,W,C] -> y bf16 [H/2,W/2,4C],
  * y[h,w,(dy*2+dx)*C + c] = x[2h+dy, 2w+dx, c] */
 int svi_vae_space_to_depth(const float* x, int32_t H, int32_t W, int32_t C, void* y_bf16, void* stream);
+/* Same with an activation (SVI_ACT_NONE | SVI_ACT_SILU) applied before the rearrangement: the stride-2 convolutions of
+ * the SVI-Dance pose stem consume SiLU(previous conv) (svi_video_dance.py:262-267). */
+int svi_vae_space_to_depth_act(const float* x, int32_t H, int32_t W, int32_t C, int32_t act, void* y_bf16, void* stream);
 /* planar f32 (channel c at x + c*ldc, n_pix contiguous) -> channels-last (x*scale[c] + shift[c]), f32 [n_pix, ldo]
  * or bf16 (out_is_bf16), columns [C, ldo) zero */
 int svi_vae_from_planar(const float* x, int32_t C, int64_t n_pix, int64_t ldc, const float* scale, const float* shift,

@@ -74,14 +74,17 @@ upsample2x_kernel(const float* __restrict__ x, int H, int W, int C, __nv_bfloat1
 }
 
 __global__ void __launch_bounds__(256)
-space_to_depth_kernel(const float* __restrict__ x, int H, int W, int C, __nv_bfloat16* __restrict__ y) {
+space_to_depth_kernel(const float* __restrict__ x, int H, int W, int C, int act, __nv_bfloat16* __restrict__ y) {
   const int cv = C >> 2, H2 = H >> 1, W2 = W >> 1;
   const long long total = (long long)H * W * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % cv);
     const long long pix = i / cv;
     const int ix = (int)(pix % W), iy = (int)(pix / W);
-    const float4 v = *reinterpret_cast<const float4*>(x + pix * C + c4 * 4);
+    float4 v = *reinterpret_cast<const float4*>(x + pix * C + c4 * 4);
+    if (act == SVI_ACT_SILU) {
+      v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w);
+    }
     uint2 pk;
     pk.x = pack_bf16x2(v.x, v.y);
     pk.y = pack_bf16x2(v.z, v.w);
@@ -191,8 +194,17 @@ extern "C" int svi_vae_space_to_depth(const float* x, int32_t H, int32_t W, int3
   SVI_REQUIRE(x && y && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 4 == 0,
               "svi_vae_space_to_depth: need even H, W and C %% 4 == 0");
   space_to_depth_kernel<<<grid_for((long long)H * W * (C / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
+      x, H, W, C, SVI_ACT_NONE, reinterpret_cast<__nv_bfloat16*>(y));
   SVI_CUDA_LAUNCH_CHECK("svi_vae_space_to_depth");
+  return SVI_OK;
+}
+extern "C" int svi_vae_space_to_depth_act(const float* x, int32_t H, int32_t W, int32_t C, int32_t act, void* y, void* stream) {
+  SVI_REQUIRE(x && y && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 4 == 0,
+              "svi_vae_space_to_depth_act: need even H, W and C %% 4 == 0");
+  SVI_REQUIRE(act == SVI_ACT_NONE || act == SVI_ACT_SILU, "svi_vae_space_to_depth_act: activation must be none or SiLU");
+  space_to_depth_kernel<<<grid_for((long long)H * W * (C / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, H, W, C, act, reinterpret_cast<__nv_bfloat16*>(y));
+  SVI_CUDA_LAUNCH_CHECK("svi_vae_space_to_depth_act");
   return SVI_OK;
 }
 extern "C" int svi_vae_from_planar(const float* x, int32_t C, int64_t n_pix, int64_t ldc, const float* scale,

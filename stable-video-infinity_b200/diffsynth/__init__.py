@@ -8,6 +8,7 @@ _LAZY = {
     "ModelManager": ("diffsynth.models.model_manager", "ModelManager"),
     "SVIVideoPipeline": ("diffsynth.pipelines.svi_video", "SVIVideoPipeline"),
     "WanVideoPipeline": ("diffsynth.pipelines.wan_video", "WanVideoPipeline"),
+    "SVIDanceVideoPipeline": ("diffsynth.pipelines.svi_video_dance", "SVIDanceVideoPipeline"),
     "save_video": ("diffsynth.data.video", "save_video"),
     "VideoData": ("diffsynth.data.video", "VideoData"),
     "FlowMatchScheduler": ("diffsynth.schedulers.flow_match", "FlowMatchScheduler"),

@@ -76,6 +76,7 @@ SIGNATURES = {
     "svi_vae_norm_act": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i32, _vp]),
     "svi_vae_upsample2x": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "svi_vae_space_to_depth": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "svi_vae_space_to_depth_act": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "svi_vae_from_planar": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp]),
     "svi_vae_to_planar": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
     "svi_softmax_rows": (_i32, [_vp, _i32, _i32, _i64, _f32, _vp, _i64, _vp]),
@@ -423,6 +424,12 @@ def vae_upsample2x(x, H, W, C, out):
 def vae_space_to_depth(x, H, W, C, out):
     _check(load().svi_vae_space_to_depth(_ptr(x, torch.float32, "x"), H, W, C, _ptr(out, torch.bfloat16, "out"), _stream()),
            "svi_vae_space_to_depth")
+    return out
+
+
+def vae_space_to_depth_act(x, H, W, C, act, out):
+    _check(load().svi_vae_space_to_depth_act(_ptr(x, torch.float32, "x"), H, W, C, act, _ptr(out, torch.bfloat16, "out"), _stream()),
+           "svi_vae_space_to_depth_act")
     return out
 
 

@@ -161,16 +161,21 @@ class _Conv:
             w = w.unsqueeze(2)
         O, I, kt, kh, kw = w.shape
         if s2d:
-            # stride-2 3x3 conv with ZeroPad2d((0,1,0,1))  ==  2x2 conv over the space-to-depth input [H/2,W/2,4I]:
-            # tap (bh,bw), phase (dy,dx) <- original tap (2bh+dy, 2bw+dx) when <= 2, else zero weight
-            w2 = torch.zeros(O, 4 * I, 1, 2, 2, device=device)
+            # stride-2 3x3 conv == 2x2 conv over the space-to-depth input [H/2,W/2,4I]; tap (bh,bw), phase (dy,dx) takes the
+            # original tap (a,b) when it exists, else a zero weight:
+            #   s2d=True / "after":  ZeroPad2d((0,1,0,1)) + stride 2 (the VAE's Resample): output o reads pixels 2o..2o+2 =
+            #                        blocks o, o+1                    -> a = 2bh+dy,   conv pad 0
+            #   s2d="before":        padding 1 + stride 2 (nn.Conv3d(..., stride 2, padding 1)): pixels 2o-1..2o+1 =
+            #                        blocks o-1, o                    -> a = 2bh+dy-1, conv pad 1 (block -1 is zero fill)
+            off = 1 if s2d == "before" else 0
+            w2 = torch.zeros(O, 4 * I, kt, 2, 2, device=device)
             for bh in range(2):
                 for bw in range(2):
                     for dy in range(2):
                         for dx in range(2):
-                            a, b = 2 * bh + dy, 2 * bw + dx
-                            if a <= 2 and b <= 2:
-                                w2[:, (dy * 2 + dx) * I:(dy * 2 + dx + 1) * I, 0, bh, bw] = w[:, :, 0, a, b]
+                            a, b = 2 * bh + dy - off, 2 * bw + dx - off
+                            if 0 <= a <= 2 and 0 <= b <= 2:
+                                w2[:, (dy * 2 + dx) * I:(dy * 2 + dx + 1) * I, :, bh, bw] = w[:, :, :, a, b]
             w, (O, I, kt, kh, kw) = w2, w2.shape
         self.c_in_true = I
         self.c_in = max(64, _ceil(I, 8))        # ring channel count (tiny inputs are zero-padded to one full chunk)

@@ -236,7 +236,8 @@ class SVIVideoPipeline(BasePipeline):
 
     # ------------------------------------------------------------------ denoising
     def denoise_latents(self, latents, context_posi, context_nega, clip_feature=None, y=None, cfg_scale=5.0,
-                        progress_bar_cmd=lambda x: x, sp=None, tea_cache_posi=None, tea_cache_nega=None):
+                        progress_bar_cmd=lambda x: x, sp=None, tea_cache_posi=None, tea_cache_nega=None,
+                        add_condition_posi=None, add_condition_nega=None):
         """The hot loop (reference _sample_with_regular_video :392-421).  latents: f32 [1,16,f,h,w] on device,
         updated in place and returned.  Timesteps/sigmas come from self.scheduler (already set)."""
         eng = self.dit.engine(self.device)
@@ -255,9 +256,9 @@ class SVIVideoPipeline(BasePipeline):
         n = len(ts)
         for i in progress_bar_cmd(range(n)):
             t = float(ts[i])
-            eng.forward(lat, t, cp, y=y, sp=sp, out=v_c, tea_cache=tea_cache_posi)
+            eng.forward(lat, t, cp, y=y, sp=sp, out=v_c, tea_cache=tea_cache_posi, add_condition=add_condition_posi)
             if use_cfg:
-                eng.forward(lat, t, cn, y=y, sp=sp, out=v_u, tea_cache=tea_cache_nega)
+                eng.forward(lat, t, cn, y=y, sp=sp, out=v_u, tea_cache=tea_cache_nega, add_condition=add_condition_nega)
             sigma = float(sig[i])
             nxt = float(sig[i + 1]) if i + 1 < n else 0.0
             eng.k.cfg_euler_step(lat, v_c, v_u, cfg_scale, sigma, nxt)

@@ -260,3 +260,81 @@ def test_vae_weight_packing_space_to_depth_equivalence():
     s2d = x.view(1, 3, 4, 2, 5, 2).permute(0, 3, 5, 1, 2, 4).reshape(1, 12, 4, 5)
     out = F.conv2d(F.pad(s2d, (0, 1, 0, 1)), w2)
     torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_pose_stem_strided_conv_repacking():
+    """nn.Conv3d(k=3, stride (1|2, 2, 2), padding 1) of the SVI-Dance pose stem == 2x2 spatial taps over the space-to-depth
+    input with one block of zero padding in front (models/wan_video_vae._Conv(s2d="before")); checked with torch ops."""
+    import torch.nn.functional as F
+    from diffsynth.models.wan_video_vae import _Conv
+    g = torch.Generator().manual_seed(0)
+    C, O, T, H, W = 16, 16, 5, 8, 12
+    bf = lambda t: t.to(torch.bfloat16).float()
+    w = bf(torch.randn(O, C, 3, 3, 3, generator=g) * 0.2)
+    b = torch.randn(O, generator=g)
+    x = torch.randn(1, C, T, H, W, generator=g)
+    cv = _Conv(w, b, "cpu", s2d="before")
+    assert (cv.kt, cv.kh, cv.kw, cv.c_in) == (3, 2, 2, 4 * C)
+    w2 = cv.w.float().reshape(cv.w.shape[0], 3, 2, 2, cv.cpad)[:O, :, :, :, :4 * C].permute(0, 4, 1, 2, 3)   # [O, 4C, 3, 2, 2]
+    # space-to-depth: channel (dy*2+dx)*C + c of block (by, bx) = pixel (2by+dy, 2bx+dx)
+    xs = x.reshape(1, C, T, H // 2, 2, W // 2, 2).permute(0, 4, 6, 1, 2, 3, 5).reshape(1, 4 * C, T, H // 2, W // 2)
+    xs = F.pad(xs, (1, 0, 1, 0, 1, 1))                       # one zero block before in W and H; symmetric in time
+    for ts in (1, 2):
+        want = F.conv3d(x, w, b, stride=(ts, 2, 2), padding=(1, 1, 1))
+        got = F.conv3d(xs, w2, b, stride=(ts, 1, 1))
+        assert got.shape == want.shape and (got - want).abs().max().item() < 1e-4
+
+
+def test_pose_stem_plan_reproduces_the_reference_stem_on_cpu():
+    """Everything of DWPoseEmbeddingEngine that is host logic — weight packing of the seven convolutions, frame-slot
+    tables (symmetric temporal padding, temporal stride), SiLU / space-to-depth staging order, the final projection as
+    space-to-depth + matrix product — replayed with torch ops on the CPU in place of the kernels, against the oracle."""
+    import torch.nn.functional as F
+    from diffsynth.models.dwpose_embedding import StemPlan, make_dwpose_embedding, slot_table
+    from oracle import dwpose_oracle as DO
+    g = torch.Generator().manual_seed(1)
+    dim, T, H, W = 64, 5, 16, 32
+    seq = make_dwpose_embedding(dim=dim)
+    sd = {k: (torch.randn(v.shape, generator=g) * (0.1 if k.endswith("bias") else 1.5 / v[0].numel() ** 0.5)).to(torch.bfloat16).float()
+          for k, v in seq.state_dict().items()}
+    seq.load_state_dict(sd)
+    plan = StemPlan(seq, "cpu")
+    pose = torch.randint(0, 256, (3, T, H, W), generator=g).float()
+    want = DO.pose_condition(sd, pose)
+
+    def conv(cv, frames_cl, T_out, ts):
+        """frames_cl: list of channels-last frames [H, W, C_ring] (what the ring slots hold); kernel semantics of
+        svi_conv3d_causal: out[t] = bias + sum over taps of w[o, a, kh, kw, c] * ring[slot[t][a]][y+kh-1][x+kw-1][c]."""
+        Hh, Ww, Cr = frames_cl[0].shape
+        zero = torch.zeros_like(frames_cl[0])
+        w = cv.w.float().reshape(cv.w.shape[0], cv.kt, cv.kh, cv.kw, cv.cpad)[:cv.c_out, :, :, :, :Cr]
+        table = slot_table(list(range(len(frames_cl))), len(frames_cl), T_out, ts, cv.kt)
+        outs = []
+        for t in range(T_out):
+            acc = cv.b[:cv.c_out].view(1, -1, 1, 1).expand(1, cv.c_out, Hh, Ww).clone()
+            for a in range(cv.kt):
+                src = zero if table[t][a] == len(frames_cl) else frames_cl[table[t][a]]
+                xin = F.pad(src.permute(2, 0, 1).unsqueeze(0), (1, cv.kw - 2, 1, cv.kh - 2))   # pad 1 before; after: k-2
+                acc = acc + F.conv2d(xin, w[:, a].permute(0, 3, 1, 2))
+            outs.append(acc[0].permute(1, 2, 0))
+        return outs
+
+    x = torch.cat([pose[:, :1].repeat(1, 3, 1, 1), pose], dim=1) / 255.0
+    Tn = x.shape[1]
+    frames = [F.pad(x[:, t].permute(1, 2, 0), (0, plan.full[0].c_in - 3)) for t in range(Tn)]
+    cur = conv(plan.full[0], frames, Tn, 1)
+    for cv in plan.full[1:]:
+        frames = [F.pad(F.silu(f), (0, cv.c_in - f.shape[-1])) for f in cur]
+        cur = conv(cv, frames, Tn, 1)
+
+    def s2d(f):
+        Hh, Ww, C = f.shape
+        return f.reshape(Hh // 2, 2, Ww // 2, 2, C).permute(0, 2, 1, 3, 4).reshape(Hh // 2, Ww // 2, 4 * C)
+
+    for cv, ts in zip(plan.down, plan.t_stride):
+        frames = [s2d(F.silu(f)) for f in cur]
+        cur = conv(cv, frames, (len(cur) + 2 - 3) // ts + 1, ts)
+    a = torch.stack([F.pad(s2d(F.silu(f)), (0, plan.kproj - 4 * f.shape[-1])) for f in cur]).reshape(-1, plan.kproj)
+    got = (a @ plan.w_proj.float().T + plan.b_proj).unsqueeze(0)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 1e-3 * max(1.0, want.abs().max().item())
