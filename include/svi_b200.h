@@ -27,6 +27,7 @@ extern "C" {
 #define SVI_ACT_GELU_TANH 1
 #define SVI_ACT_SILU 2
 #define SVI_ACT_GELU_ERF 3 /* nn.GELU() default (img_emb MLP, wan_video_dit.py:381) */
+#define SVI_ACT_RELU 4     /* AudioProjModel (SVI-Talk), wan_video_dit.py:97-106; GEMM epilogue only */
 
 /* ABI version of this header / library pair. */
 int svi_abi_version(void);

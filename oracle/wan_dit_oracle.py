@@ -111,8 +111,45 @@ def cross_attention(sd, pre, x, ctx, H, eps, has_image_input):
     return _lin(sd, pre + ".o", o)
 
 
-def dit_block(sd, i, x, ctx, t_mod, angles, cfg):
-    """wan_video_dit.py:354-374 (non-multitalk branch)."""
+def preprocess_audio(audio_embed, audio_window=5, vae_scale=4):
+    """svi_video_talk.py:432-446: [1, 4n+1, 5, 12, 768] window features -> (first frame [1,1,5,12,768],
+    latter frames [1, n, 8, 12, 768]): per latent frame the first video frame keeps its left half window + centre, the
+    last its centre + right half, the middle ones their centre."""
+    first = audio_embed[:, :1]
+    rest = audio_embed[:, 1:]
+    b, n4, w, s_, c = rest.shape
+    rest = rest.reshape(b, n4 // vae_scale, vae_scale, w, s_, c)
+    mid = audio_window // 2
+    a = rest[:, :, :1, :mid + 1].reshape(b, n4 // vae_scale, -1, s_, c)
+    z = rest[:, :, -1:, mid:].reshape(b, n4 // vae_scale, -1, s_, c)
+    m = rest[:, :, 1:-1, mid:mid + 1].reshape(b, n4 // vae_scale, -1, s_, c)
+    return first, torch.cat([a, m, z], dim=2)
+
+
+def audio_proj(sd, first, latter):
+    """AudioProjModel.forward wan_video_dit.py:82-112 -> audio tokens [n_latent_frames, 32, 768]."""
+    x0 = F.relu(_lin(sd, "audio_proj.proj1", first.reshape(first.shape[1], -1)))
+    x1 = F.relu(_lin(sd, "audio_proj.proj1_vf", latter.reshape(latter.shape[1], -1)))
+    x = F.relu(_lin(sd, "audio_proj.proj2", torch.cat([x0, x1], dim=0)))
+    tok = _lin(sd, "audio_proj.proj3", x).reshape(x.shape[0], 32, 768)
+    return F.layer_norm(tok, (768,), sd["audio_proj.norm.weight"], sd["audio_proj.norm.bias"])
+
+
+def audio_cross_attention(sd, pre, x, audio_tokens, H):
+    """SingleStreamAttention.forward models/attention.py:318-371 (human_num = 1, qk_norm off): every latent frame's
+    tokens attend to that frame's 32 audio tokens; scale 1/sqrt(head_dim)."""
+    n_t = audio_tokens.shape[0]
+    B, L, d = x.shape
+    xf = x.reshape(n_t, L // n_t, d)
+    q = _lin(sd, pre + ".q_linear", xf).view(n_t, -1, H, d // H).transpose(1, 2)
+    kv = _lin(sd, pre + ".kv_linear", audio_tokens).view(n_t, -1, 2, H, d // H)
+    k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
+    o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n_t, -1, d)
+    return _lin(sd, pre + ".proj", o).reshape(B, L, d)
+
+
+def dit_block(sd, i, x, ctx, t_mod, angles, cfg, audio_tokens=None):
+    """wan_video_dit.py:354-374; audio_tokens [n_t, 32, 768] enables the multitalk branch (:361-366)."""
     pre = f"blocks.{i}"
     d, H, eps = cfg["dim"], cfg["num_heads"], cfg["eps"]
     mod = sd[pre + ".modulation"].to(t_mod.dtype) + t_mod  # [1,6,d]
@@ -121,6 +158,9 @@ def dit_block(sd, i, x, ctx, t_mod, angles, cfg):
     x = x + g_a * self_attention(sd, pre + ".self_attn", h, angles, H, eps)
     h = F.layer_norm(x, (d,), sd[pre + ".norm3.weight"], sd[pre + ".norm3.bias"], eps)
     x = x + cross_attention(sd, pre + ".cross_attn", h, ctx, H, eps, cfg["has_image_input"])
+    if audio_tokens is not None:
+        h = F.layer_norm(x, (d,), sd[pre + ".norm_x.weight"], sd[pre + ".norm_x.bias"], eps)
+        x = x + audio_cross_attention(sd, pre + ".audio_cross_attn", h, audio_tokens, H)
     h = F.layer_norm(x, (d,), eps=eps) * (1 + sc_m) + sh_m
     h = _lin(sd, pre + ".ffn.2", F.gelu(_lin(sd, pre + ".ffn.0", h), approximate="tanh"))
     return x + g_m * h
@@ -206,9 +246,10 @@ class TeaCacheOracle:
 
 
 def dit_forward(sd, cfg, x, timestep, context, clip_feature=None, y=None, dtype=torch.float32, return_tokens=False,
-                tea_cache=None, add_condition=None):
+                tea_cache=None, add_condition=None, audio_embed_tuple=None):
     """svi_video.py:74-137 (model_fn_wan_video; no USP) on CPU in `dtype`; tea_cache: a TeaCacheOracle or None;
-    add_condition: [1, L, dim] added to the patch embedding (:102-103)."""
+    add_condition: [1, L, dim] added to the patch embedding (:102-103); audio_embed_tuple: the (first, latter) window
+    features of preprocess_audio for an enable_multitalk model (svi_video_talk.py:123-124)."""
     sd = {k: v.to(dtype) if v.is_floating_point() else v for k, v in sd.items()}
     x = x.to(dtype)
     context = context.to(dtype)
@@ -220,11 +261,14 @@ def dit_forward(sd, cfg, x, timestep, context, clip_feature=None, y=None, dtype=
     if add_condition is not None:
         tok = add_condition.to(dtype) + tok
     angles = rope_angles_3d(cfg["dim"] // cfg["num_heads"], f, h, w)
+    audio_tokens = None
+    if audio_embed_tuple is not None:
+        audio_tokens = audio_proj(sd, audio_embed_tuple[0].to(dtype), audio_embed_tuple[1].to(dtype))
     if tea_cache is not None and tea_cache.check(tok, t_mod):          # :114-126
         tok = tea_cache.update(tok)
     else:
         for i in range(cfg["num_layers"]):
-            tok = dit_block(sd, i, tok, ctx, t_mod, angles, cfg)
+            tok = dit_block(sd, i, tok, ctx, t_mod, angles, cfg, audio_tokens)
         if tea_cache is not None:
             tea_cache.store(tok)
     if return_tokens:

@@ -54,6 +54,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == SVI_ACT_GELU_TANH) return gelu_tanh(v);
   if (act == SVI_ACT_SILU) return silu(v);
   if (act == SVI_ACT_GELU_ERF) return gelu_erf(v);
+  if (act == SVI_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {

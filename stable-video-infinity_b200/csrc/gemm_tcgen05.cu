@@ -44,6 +44,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == SVI_ACT_GELU_TANH) return gelu_tanh(v);
   if (act == SVI_ACT_SILU) return silu(v);
   if (act == SVI_ACT_GELU_ERF) return gelu_erf(v);
+  if (act == SVI_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 
@@ -259,7 +260,7 @@ extern "C" int svi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   SVI_REQUIRE(e->ldo >= N && e->ldo % (e->out_is_f32 ? 4 : 8) == 0 &&
                   (reinterpret_cast<uintptr_t>(e->out) & 15) == 0,
               "svi_gemm_bf16: out must be 16-byte aligned with ldo >= N and 16-byte row pitch");
-  SVI_REQUIRE(e->act >= 0 && e->act <= 3, "svi_gemm_bf16: unknown activation %d", e->act);
+  SVI_REQUIRE(e->act >= 0 && e->act <= 4, "svi_gemm_bf16: unknown activation %d", e->act);
   if (e->residual)
     SVI_REQUIRE(e->ldr >= N && e->ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(e->residual) & 15) == 0,
                 "svi_gemm_bf16: residual must be 16-byte aligned with ldr >= N, ldr %% 4 == 0");

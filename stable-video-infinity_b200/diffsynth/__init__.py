@@ -9,6 +9,7 @@ _LAZY = {
     "SVIVideoPipeline": ("diffsynth.pipelines.svi_video", "SVIVideoPipeline"),
     "WanVideoPipeline": ("diffsynth.pipelines.wan_video", "WanVideoPipeline"),
     "SVIDanceVideoPipeline": ("diffsynth.pipelines.svi_video_dance", "SVIDanceVideoPipeline"),
+    "SVITalkVideoPipeline": ("diffsynth.pipelines.svi_video_talk", "SVITalkVideoPipeline"),
     "save_video": ("diffsynth.data.video", "save_video"),
     "VideoData": ("diffsynth.data.video", "VideoData"),
     "FlowMatchScheduler": ("diffsynth.schedulers.flow_match", "FlowMatchScheduler"),

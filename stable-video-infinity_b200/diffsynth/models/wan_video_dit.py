@@ -84,12 +84,43 @@ class CrossAttention(nn.Module):
             self.norm_k_img = RMSNorm(dim, eps=eps)
 
 
+class SingleStreamMutiAttention(nn.Module):
+    """Parameter container of the per-frame audio cross-attention of SVI-Talk (reference models/attention.py:282-411 with
+    qk_norm=False, qkv_bias=True as instantiated at wan_video_dit.py:340-350; the rotary / multi-person branch is only
+    taken for human_num > 1, which DiTBlock never passes)."""
+
+    def __init__(self, dim, encoder_hidden_states_dim, num_heads):
+        super().__init__()
+        self.dim, self.encoder_hidden_states_dim, self.num_heads, self.head_dim = dim, encoder_hidden_states_dim, num_heads, dim // num_heads
+        self.q_linear = nn.Linear(dim, dim, bias=True)
+        self.proj = nn.Linear(dim, dim)
+        self.kv_linear = nn.Linear(encoder_hidden_states_dim, dim * 2, bias=True)
+
+
+class AudioProjModel(nn.Module):
+    """Parameter container of the audio window projector (reference wan_video_dit.py:52-112)."""
+
+    def __init__(self, seq_len=5, seq_len_vf=12, blocks=12, channels=768, intermediate_dim=512, output_dim=768,
+                 context_tokens=32, norm_output_audio=False):
+        super().__init__()
+        self.seq_len, self.seq_len_vf, self.blocks, self.channels = seq_len, seq_len_vf, blocks, channels
+        self.input_dim, self.input_dim_vf = seq_len * blocks * channels, seq_len_vf * blocks * channels
+        self.intermediate_dim, self.context_tokens, self.output_dim = intermediate_dim, context_tokens, output_dim
+        self.proj1 = nn.Linear(self.input_dim, intermediate_dim)
+        self.proj1_vf = nn.Linear(self.input_dim_vf, intermediate_dim)
+        self.proj2 = nn.Linear(intermediate_dim, intermediate_dim)
+        self.proj3 = nn.Linear(intermediate_dim, context_tokens * output_dim)
+        self.norm = nn.LayerNorm(output_dim) if norm_output_audio else nn.Identity()
+
+
 class DiTBlock(nn.Module):
     def __init__(self, has_image_input: bool, dim: int, num_heads: int, ffn_dim: int, eps: float = 1e-6,
                  enable_multitalk: bool = False):
         super().__init__()
-        if enable_multitalk:
-            raise NotImplementedError("SVI-Talk audio cross-attention is outside the hot-path scope (SURVEY.md §8f)")
+        self.enable_multitalk = enable_multitalk
+        if enable_multitalk:                 # reference :339-352
+            self.audio_cross_attn = SingleStreamMutiAttention(dim, 768, num_heads)
+            self.norm_x = nn.LayerNorm(dim, eps=eps, elementwise_affine=True)
         self.dim, self.num_heads, self.ffn_dim = dim, num_heads, ffn_dim
         self.self_attn = SelfAttention(dim, num_heads, eps)
         self.cross_attn = CrossAttention(dim, num_heads, eps, has_image_input=has_image_input)
@@ -152,6 +183,12 @@ class _BlockWeights:
         self.w_f0, self.b_f0 = _bf16(blk.ffn[0].weight, device), _f32(blk.ffn[0].bias, device)
         self.w_f2, self.b_f2 = _bf16(blk.ffn[2].weight, device), _f32(blk.ffn[2].bias, device)
         self.mod = _f32(blk.modulation.reshape(6, blk.dim), device)
+        if getattr(blk, "enable_multitalk", False):
+            a = blk.audio_cross_attn
+            self.w_aq, self.b_aq = _bf16(a.q_linear.weight, device), _f32(a.q_linear.bias, device)
+            self.w_akv, self.b_akv = _bf16(a.kv_linear.weight, device), _f32(a.kv_linear.bias, device)
+            self.w_ap, self.b_ap = _bf16(a.proj.weight, device), _f32(a.proj.bias, device)
+            self.nxw, self.nxb = _f32(blk.norm_x.weight, device), _f32(blk.norm_x.bias, device)
 
 
 class ContextState:
@@ -165,6 +202,14 @@ class ContextState:
         self.kv_img_all = torch.empty(n_layers, 257, 2 * width, device=device, dtype=torch.bfloat16) if n_layers and n_img else None
         self.kv_txt = [] if self.kv_txt_all is None else list(self.kv_txt_all.unbind(0))     # per layer bf16 [n_txt, 2d]  (k normalised | v)
         self.kv_img = [] if self.kv_img_all is None else list(self.kv_img_all.unbind(0))     # per layer bf16 [257, 2d]
+
+
+class AudioState:
+    """Step-invariant audio conditioning of SVI-Talk: every layer's per-frame audio K|V [n_frames * tokens, 2d]."""
+
+    def __init__(self, n_frames, tokens):
+        self.n_frames, self.tokens = n_frames, tokens
+        self.kv = []          # per layer bf16 [n_frames * tokens, 2d]
 
 
 class _CountingNative:
@@ -237,6 +282,14 @@ class WanDiTEngine:
             self.ie_w1, self.ie_b1 = _bf16(p[1].weight, self.device), _f32(p[1].bias, self.device)
             self.ie_w3, self.ie_b3 = _bf16(p[3].weight, self.device), _f32(p[3].bias, self.device)
             self.ie_ln4 = (_f32(p[4].weight, self.device), _f32(p[4].bias, self.device), p[4].eps)
+        if getattr(model, "enable_multitalk", False):
+            ap = model.audio_proj
+            self.ap_w1, self.ap_b1 = _bf16(ap.proj1.weight, self.device), _f32(ap.proj1.bias, self.device)
+            self.ap_w1v, self.ap_b1v = _bf16(ap.proj1_vf.weight, self.device), _f32(ap.proj1_vf.bias, self.device)
+            self.ap_w2, self.ap_b2 = _bf16(ap.proj2.weight, self.device), _f32(ap.proj2.bias, self.device)
+            self.ap_w3, self.ap_b3 = _bf16(ap.proj3.weight, self.device), _f32(ap.proj3.bias, self.device)
+            self.ap_ln = (_f32(ap.norm.weight, self.device), _f32(ap.norm.bias, self.device), ap.norm.eps)
+            self.ap_tokens, self.ap_dim = ap.context_tokens, ap.output_dim
         self._rope = {}
         self._ws = {}
         self._ctx_cache = OrderedDict()
@@ -340,13 +393,41 @@ class WanDiTEngine:
             self._ctx_cache.popitem(last=False)
         return st
 
+    def audio_state(self, audio_embed_tuple) -> AudioState:
+        """SVI-Talk: AudioProjModel (reference wan_video_dit.py:82-112) on the (first-frame, latter-frames) wav2vec window
+        features, then every layer's audio K|V projection (models/attention.py:333-337) — all step-invariant, computed
+        once per clip and branch.  audio_embed_tuple: ([1,1,5,12,768], [1,n,8,12,768])."""
+        if not getattr(self.model, "enable_multitalk", False):
+            raise RuntimeError("svi_b200: audio conditioning needs a WanModel built with enable_multitalk=True")
+        dev, d = self.device, self.dim
+        a0, a1 = audio_embed_tuple
+        x0 = a0.to(device=dev, dtype=torch.bfloat16).reshape(a0.shape[1], -1).contiguous()
+        x1 = a1.to(device=dev, dtype=torch.bfloat16).reshape(a1.shape[1], -1).contiguous()
+        n = x0.shape[0] + x1.shape[0]
+        mid = self.ap_w2.shape[0]
+        h1 = torch.empty(n, mid, device=dev, dtype=torch.bfloat16)
+        self.k.gemm(x0, self.ap_w1, h1[:x0.shape[0]], bias=self.ap_b1, act=nv.ACT_RELU)
+        self.k.gemm(x1, self.ap_w1v, h1[x0.shape[0]:], bias=self.ap_b1v, act=nv.ACT_RELU)
+        h2 = torch.empty(n, mid, device=dev, dtype=torch.bfloat16)
+        self.k.gemm(h1, self.ap_w2, h2, bias=self.ap_b2, act=nv.ACT_RELU)
+        tok = torch.empty(n, self.ap_tokens * self.ap_dim, device=dev, dtype=torch.float32)
+        self.k.gemm(h2, self.ap_w3, tok, bias=self.ap_b3)
+        tokb = torch.empty(n * self.ap_tokens, self.ap_dim, device=dev, dtype=torch.bfloat16)
+        self.k.layernorm_modulate(tok.view(n * self.ap_tokens, self.ap_dim), tokb, self.ap_ln[2], gamma=self.ap_ln[0], beta=self.ap_ln[1])
+        st = AudioState(n, self.ap_tokens)
+        for bw in self.blocks:
+            kv = torch.empty(n * self.ap_tokens, 2 * d, device=dev, dtype=torch.bfloat16)
+            self.k.gemm(tokb, bw.w_akv, kv, bias=bw.b_akv)
+            st.kv.append(kv)
+        return st
+
     def _attn_workspace(self, Lq, Lk):
         """Scratch for the sliced last wave of the self-attention launch (svi_attn_fwd workspace)."""
         n = nv.attention_workspace_bytes(Lq, Lk, self.H)
         return self._buf("attn_ws", ((n + 3) // 4,), torch.float32)
 
     # ------------------------------------------------------------------ block stack
-    def run_block(self, i, x, t_mod, ctx: ContextState, cos, sin, sp=None):
+    def run_block(self, i, x, t_mod, ctx: ContextState, cos, sin, sp=None, audio: Optional[AudioState] = None):
         """x f32 [L,d] updated in place.  Reference DiTBlock.forward wan_video_dit.py:354-374."""
         bw = self.blocks[i]
         L, d, H = x.shape[0], self.dim, self.H
@@ -418,19 +499,33 @@ class WanDiTEngine:
             kvi = ctx.kv_img[i]
             self.k.attention(cq, kvi[:, :d], kvi[:, d:], att, H, accumulate=True)
         self.k.gemm(att, bw.w_co, x, bias=bw.b_co, residual=x)
+        # --- audio cross-attention (SVI-Talk, wan_video_dit.py:361-366): tokens of latent frame f attend to that frame's
+        #     audio tokens (models/attention.py:318-371); 1/sqrt(head_dim) scale, no q/k norm
+        if audio is not None:
+            S, Ta = L // audio.n_frames, audio.tokens
+            self.k.layernorm_modulate(x, h, bw.eps, gamma=bw.nxw, beta=bw.nxb)
+            aq = qkv[:, :d]
+            self.k.gemm(h, bw.w_aq, aq, bias=bw.b_aq)
+            kva = audio.kv[i]
+            for fr in range(audio.n_frames):
+                kf = kva[fr * Ta:(fr + 1) * Ta]
+                self.k.attention(aq[fr * S:(fr + 1) * S], kf[:, :d], kf[:, d:], att[fr * S:(fr + 1) * S], H)
+            self.k.gemm(att, bw.w_ap, x, bias=bw.b_ap, residual=x)
         # --- FFN
         self.k.layernorm_modulate(x, h, bw.eps, scale=mod[4], shift=mod[3])
         self.k.gemm(h, bw.w_f0, ffn, bias=bw.b_f0, act=nv.ACT_GELU_TANH)
         self.k.gemm(ffn, bw.w_f2, x, bias=bw.b_f2, gate=mod[5], residual=x)
         return x
 
-    def forward(self, x, timestep, context, clip_feature=None, y=None, sp=None, out=None, tea_cache=None, add_condition=None):
+    def forward(self, x, timestep, context, clip_feature=None, y=None, sp=None, out=None, tea_cache=None, add_condition=None,
+                audio=None):
         """One DiT forward (svi_video.py:74-137).  x [1,C,f,Hl,Wl] (any float dtype, CUDA) -> f32 [1,16,f,Hl,Wl].
 
         `context` may be a tensor [1,Lc,text_dim] or a ContextState from context_state().  `tea_cache`: a
         pipelines.svi_video.TeaCache deciding per step whether the block stack runs or the cached residual is re-used.
         `add_condition`: [1, L, dim] token-space condition added to the patch embedding (SVI-Dance pose stem output,
-        reference svi_video.py:102-103)."""
+        reference svi_video.py:102-103).  `audio`: an AudioState (audio_state()) or the (first, latter) window-feature tuple
+        of an enable_multitalk model (SVI-Talk, svi_video_talk.py:123-124)."""
         dev, d = self.device, self.dim
         if x.dim() != 5 or x.shape[0] != 1:
             raise RuntimeError(f"svi_b200: DiT forward expects x of shape [1,C,f,h,w], got {tuple(x.shape)}")
@@ -451,10 +546,17 @@ class WanDiTEngine:
         nh = self.w_head.shape[0]
         if out is None:
             out = torch.empty(1, nh // 4, f, Hl, Wl, device=dev, dtype=torch.float32)
-        if (self.use_graphs and sp is None and tea_cache is None and add_condition is None and self.attn_events is None
-                and self.k.events is None and out.is_contiguous()):
+        if audio is not None:
+            if sp is not None:
+                raise NotImplementedError("svi_b200: audio cross-attention under sequence parallelism is not implemented")
+            if not isinstance(audio, AudioState):
+                audio = self.audio_state(audio)
+            if L % audio.n_frames or audio.n_frames != f:
+                raise RuntimeError(f"svi_b200: {audio.n_frames} audio frames for {f} latent frames")
+        if (self.use_graphs and sp is None and tea_cache is None and add_condition is None and audio is None
+                and self.attn_events is None and self.k.events is None and out.is_contiguous()):
             return self._graph_forward(xs, ys, t, t_mod, ctx, cos, sin, out)
-        return self._run(xs, ys, t, t_mod, ctx, cos, sin, out, sp, tea_cache, add_condition)
+        return self._run(xs, ys, t, t_mod, ctx, cos, sin, out, sp, tea_cache, add_condition, audio)
 
     # ------------------------------------------------------------------ CUDA-graph replay (single GPU)
     def _graph_forward(self, xs, ys, t, t_mod, ctx, cos, sin, out):
@@ -466,7 +568,7 @@ class WanDiTEngine:
         ent = self._graphs.get(key)
         if ent is None:                       # first call of this geometry: eager (allocates every work buffer)
             self._graphs[key] = {"graph": None}
-            return self._run(xs, ys, t, t_mod, ctx, cos, sin, out, None, None, None)
+            return self._run(xs, ys, t, t_mod, ctx, cos, sin, out, None, None, None, None)
         if ent["graph"] is None:
             st = ContextState(ctx.n_img, ctx.n_txt, len(self.blocks), self.dim, self.device)
             ent.update(xs=torch.empty_like(xs), ys=None if ys is None else torch.empty_like(ys), t=torch.empty_like(t),
@@ -476,7 +578,7 @@ class WanDiTEngine:
             n0 = self.k.launches
             # thread_local: other threads (NCCL watchdog, the bench's clock sampler) may keep calling the CUDA runtime
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._run(ent["xs"], ent["ys"], ent["t"], ent["t_mod"], st, cos, sin, ent["out"], None, None, None)
+                self._run(ent["xs"], ent["ys"], ent["t"], ent["t_mod"], st, cos, sin, ent["out"], None, None, None, None)
             ent["launches"] = self.k.launches - n0
             self.k.launches = n0               # recorded, not executed
             ent["graph"] = g
@@ -493,7 +595,7 @@ class WanDiTEngine:
         out.copy_(ent["out"])
         return out
 
-    def _run(self, xs, ys, t, t_mod, ctx, cos, sin, out, sp, tea_cache, add_condition):
+    def _run(self, xs, ys, t, t_mod, ctx, cos, sin, out, sp, tea_cache, add_condition, audio=None):
         """Device work of one forward on prepared inputs (everything here is stream-ordered and allocation-free after the
         first call of a geometry, so it can be captured)."""
         dev, d = self.device, self.dim
@@ -522,7 +624,7 @@ class WanDiTEngine:
             tea_cache.update(xr)                      # skipped step: tokens + residual of the last computed step
         else:
             for i in range(len(self.blocks)):
-                self.run_block(i, xr, t_mod, ctx, cos, sin, sp)
+                self.run_block(i, xr, t_mod, ctx, cos, sin, sp, audio)
             if tea_cache is not None:
                 tea_cache.store(xr)
         # head (wan_video_dit.py:401-404) + unpatchify (:479-484)
@@ -566,6 +668,9 @@ class WanModel(nn.Module):
         if has_image_input:
             self.img_emb = MLP(1280, dim)
         self.enable_multitalk = enable_multitalk
+        if enable_multitalk:        # reference :455-470: audio_window 5, vae_scale 4 -> windows of 5 and 8 wav2vec frames
+            self.audio_proj = AudioProjModel(seq_len=5, seq_len_vf=8, intermediate_dim=512, output_dim=768, context_tokens=32,
+                                             norm_output_audio=True)
         self._engine: Optional[WanDiTEngine] = None
 
     # -- engine management -------------------------------------------------------------------
@@ -614,10 +719,9 @@ class WanModel(nn.Module):
         return out
 
     def forward(self, x, timestep, context, clip_feature=None, y=None, **kwargs):
-        if kwargs.get("audio_embed_tuple") is not None:
-            raise NotImplementedError("SVI-Talk audio conditioning is outside the hot-path scope (SURVEY.md §8f.2)")
         dev = x.device if x.is_cuda else None
-        out = self.engine(dev).forward(x, timestep, context, clip_feature, y, add_condition=kwargs.get("add_condition"))
+        out = self.engine(dev).forward(x, timestep, context, clip_feature, y, add_condition=kwargs.get("add_condition"),
+                                       audio=kwargs.get("audio_embed_tuple"))
         return out.to(x.dtype) if x.is_floating_point() else out
 
     @staticmethod
@@ -638,6 +742,10 @@ _CIVITAI_CONFIGS = {
     "6bfcfb3b342cb286ce886889d519a77e": dict(has_image_input=True, patch_size=[1, 2, 2], in_dim=36, dim=5120,
                                              ffn_dim=13824, freq_dim=256, text_dim=4096, out_dim=16, num_heads=40,
                                              num_layers=40, eps=1e-6),
+    # SVI-Talk / MultiTalk checkpoint: 14B-I2V + audio cross-attention (reference :670-684)
+    "b6caaaa1388107ec24d25592901ca489": dict(has_image_input=True, patch_size=[1, 2, 2], in_dim=36, dim=5120,
+                                             ffn_dim=13824, freq_dim=256, text_dim=4096, out_dim=16, num_heads=40,
+                                             num_layers=40, eps=1e-6, enable_multitalk=True),
 }
 
 

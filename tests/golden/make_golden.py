@@ -156,6 +156,39 @@ def golden_vae(vae_mod):
     print("vae lat", tuple(lat.shape), "dec", tuple(dec.shape), "dec std", dec.std().item())
 
 
+def golden_talk(dit_mod):
+    """Tiny enable_multitalk WanModel (SVI-Talk): the reference forward with audio window features
+    (wan_video_dit.py:486-567 with audio_embed_tuple; AudioProjModel :52-112, SingleStreamMutiAttention models/attention.py).
+    xformers is absent here: its memory_efficient_attention ([B, M, H, K] layout, no bias) is replaced by torch SDPA."""
+    import torch.nn.functional as F
+    att_mod = importlib.import_module("diffsynth.models.attention")
+
+    def mea(q, k, v, attn_bias=None, op=None):
+        assert attn_bias is None
+        return F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
+    sys.modules["xformers.ops"].memory_efficient_attention = mea
+    att_mod.xformers.ops = sys.modules["xformers.ops"]
+    from oracle import wan_dit_oracle as O
+    cfg = synth.CFG_TINY_TALK
+    model = dit_mod.WanModel(**cfg).eval()
+    sd = synth.make_dit_state_dict(cfg, seed=5)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("rope_1d" in k or "norm" in k for k in missing), (missing, unexpected)
+    f, h, w = 3, 8, 8
+    inp = synth.make_dit_inputs(cfg, f, h, w, seed=5, ctx_len=24)
+    audio = synth.make_audio_embed(4 * (f - 1) + 1, seed=5)
+    first, latter = O.preprocess_audio(audio)
+    ts = torch.tensor([600.0])
+    with torch.no_grad():
+        tokens = model.audio_proj(first, latter)
+        out = model(inp["x"], ts, inp["context"], clip_feature=inp["clip_feature"], y=inp["y"], audio_embed_tuple=(first, latter))
+        base = model(inp["x"], ts, inp["context"], clip_feature=inp["clip_feature"], y=inp["y"])
+    np.savez_compressed(os.path.join(HERE, "dit_tiny_talk.npz"), out=out.numpy(), out_no_audio=base.numpy(),
+                        audio_tokens=tokens.numpy(), first=first.numpy(), latter=latter.numpy(), fhw=np.array([f, h, w]),
+                        seed=np.array(5), ctx_len=np.array(24), timestep=ts.numpy())
+    print("talk: out", tuple(out.shape), "audio tokens", tuple(tokens.shape), "max|out - no_audio|", float((out - base).abs().max()))
+
+
 def golden_encoders():
     """Tiny umT5 text encoder and CLIP visual tower: outputs of the reference modules on seeded weights / inputs."""
     import torchvision.transforms as T
@@ -259,5 +292,7 @@ if __name__ == "__main__":
         golden_teacache(a.ref)
     if a.only in ("", "enc"):
         golden_encoders()
+    if a.only in ("", "talk"):
+        golden_talk(dit_mod)
     if a.only in ("", "vae") and os.path.exists(os.path.join(ROOT, "tools", "synth_vae.py")):
         golden_vae(vae_mod)

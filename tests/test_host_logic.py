@@ -338,3 +338,29 @@ def test_pose_stem_plan_reproduces_the_reference_stem_on_cpu():
     got = (a @ plan.w_proj.float().T + plan.b_proj).unsqueeze(0)
     assert got.shape == want.shape
     assert (got - want).abs().max().item() < 1e-3 * max(1.0, want.abs().max().item())
+
+
+def test_talk_model_key_contract_and_audio_windows():
+    """SVI-Talk: the enable_multitalk 14B-I2V parameter names hash to the reference fingerprint (model_config.py:120,
+    wan_video_dit.py:670-684) and the detector hands WanModel the multitalk config; preprocess_audio equals the oracle's
+    window selection (itself pinned to svi_video_talk.py:432-446 by the golden fixture)."""
+    from diffsynth.models.model_manager import ModelManager
+    from diffsynth.models.utils import hash_state_dict_keys
+    from diffsynth.models.wan_video_dit import WanModel
+    from diffsynth.pipelines.svi_video_talk import preprocess_audio
+    from oracle import wan_dit_oracle as O
+    from tools import synth
+    with torch.device("meta"):
+        m = WanModel(**dict(synth.CFG_I2V_14B, enable_multitalk=True))
+    sd = m.state_dict()
+    assert hash_state_dict_keys(sd, with_shape=True) == "b6caaaa1388107ec24d25592901ca489"
+    det = ModelManager(torch_dtype=torch.bfloat16, device="cpu").model_detector[0]
+    names, classes, resource = det._lookup(sd)
+    assert names == ["wan_video_dit"] and classes == [WanModel] and resource == "civitai"
+    _, cfg = WanModel.state_dict_converter().from_civitai(sd)
+    assert cfg["enable_multitalk"] is True and cfg["dim"] == 5120 and cfg["has_image_input"] is True
+    a = synth.make_audio_embed(13, seed=2)
+    for x, y in zip(preprocess_audio(a), O.preprocess_audio(a)):
+        assert torch.equal(x, y)
+    with pytest.raises(ValueError):
+        preprocess_audio(synth.make_audio_embed(11))

@@ -120,3 +120,28 @@ def test_teacache_matches_reference_class(model_id, impl):
     np.testing.assert_allclose(np.array(accs), g[key + "_acc"], rtol=1e-9, atol=1e-12)
     with pytest.raises((ValueError, KeyError)):
         (TeaCacheOracle if impl == "oracle" else TeaCache)(12, 0.3, "no-such-model")
+
+
+def test_talk_oracle_matches_reference_model():
+    """SVI-Talk: AudioProjModel tokens and the enable_multitalk forward (audio cross-attention per latent frame) against
+    the reference WanModel (tests/golden/dit_tiny_talk.npz); also preprocess_audio's window selection."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dit_tiny_talk.npz"))
+    cfg = synth.CFG_TINY_TALK
+    f, h, w = (int(v) for v in g["fhw"])
+    sd = synth.make_dit_state_dict(cfg, seed=int(g["seed"]))
+    inp = synth.make_dit_inputs(cfg, f, h, w, seed=int(g["seed"]), ctx_len=int(g["ctx_len"]))
+    audio = synth.make_audio_embed(4 * (f - 1) + 1, seed=int(g["seed"]))
+    first, latter = O.preprocess_audio(audio)
+    assert first.shape == (1, 1, 5, 12, 768) and latter.shape == (1, f - 1, 8, 12, 768)
+    np.testing.assert_array_equal(first.numpy(), g["first"])
+    np.testing.assert_array_equal(latter.numpy(), g["latter"])
+    # latent frame 1 = video frames 1..4: frame 1 windows 0..2, frames 2,3 centre window, frame 4 windows 2..4
+    assert torch.equal(latter[0, 0, :3], audio[0, 1, :3]) and torch.equal(latter[0, 0, 3], audio[0, 2, 2])
+    assert torch.equal(latter[0, 0, 4], audio[0, 3, 2]) and torch.equal(latter[0, 0, 5:], audio[0, 4, 2:])
+    tokens = O.audio_proj(sd, first, latter)
+    np.testing.assert_allclose(tokens.numpy(), g["audio_tokens"][0], rtol=1e-4, atol=1e-4)
+    ts = torch.from_numpy(g["timestep"])
+    out = O.dit_forward(sd, cfg, inp["x"], ts, inp["context"], inp["clip_feature"], inp["y"], audio_embed_tuple=(first, latter))
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=2e-4, atol=2e-4)
+    base = O.dit_forward(sd, cfg, inp["x"], ts, inp["context"], inp["clip_feature"], inp["y"])
+    np.testing.assert_allclose(base.numpy(), g["out_no_audio"], rtol=2e-4, atol=2e-4)

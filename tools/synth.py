@@ -14,6 +14,7 @@ CFG_TINY_T2V = dict(has_image_input=False, patch_size=(1, 2, 2), in_dim=16, dim=
                     freq_dim=64, text_dim=96, out_dim=16, num_heads=2, num_layers=2, eps=1e-6)
 CFG_TINY_I2V = dict(has_image_input=True, patch_size=(1, 2, 2), in_dim=36, dim=256, ffn_dim=512,
                     freq_dim=64, text_dim=96, out_dim=16, num_heads=2, num_layers=2, eps=1e-6)
+CFG_TINY_TALK = dict(CFG_TINY_I2V, enable_multitalk=True)
 CFG_T2V_1_3B = dict(has_image_input=False, patch_size=(1, 2, 2), in_dim=16, dim=1536, ffn_dim=8960,
                     freq_dim=256, text_dim=4096, out_dim=16, num_heads=12, num_layers=30, eps=1e-6)
 CFG_I2V_14B = dict(has_image_input=True, patch_size=(1, 2, 2), in_dim=36, dim=5120, ffn_dim=13824,
@@ -51,6 +52,12 @@ def dit_param_shapes(cfg):
         lin(f"{p}.ffn.0", ffn, d)
         lin(f"{p}.ffn.2", d, ffn)
         sh[f"{p}.modulation"] = (1, 6, d)
+        if cfg.get("enable_multitalk"):          # SVI-Talk audio cross-attention (wan_video_dit.py:339-352)
+            lin(f"{p}.audio_cross_attn.q_linear", d, d)
+            lin(f"{p}.audio_cross_attn.proj", d, d)
+            lin(f"{p}.audio_cross_attn.kv_linear", 2 * d, 768)
+            sh[f"{p}.norm_x.weight"] = (d,)
+            sh[f"{p}.norm_x.bias"] = (d,)
     lin("head.head", cfg["out_dim"] * math.prod(cfg["patch_size"]), d)
     sh["head.modulation"] = (1, 2, d)
     if cfg["has_image_input"]:
@@ -60,6 +67,13 @@ def dit_param_shapes(cfg):
         lin("img_emb.proj.3", d, 1280)
         sh["img_emb.proj.4.weight"] = (d,)
         sh["img_emb.proj.4.bias"] = (d,)
+    if cfg.get("enable_multitalk"):              # AudioProjModel (wan_video_dit.py:455-470: windows 5 / 8, 12 x 768 wav2vec blocks)
+        lin("audio_proj.proj1", 512, 5 * 12 * 768)
+        lin("audio_proj.proj1_vf", 512, 8 * 12 * 768)
+        lin("audio_proj.proj2", 512, 512)
+        lin("audio_proj.proj3", 32 * 768, 512)
+        sh["audio_proj.norm.weight"] = (768,)
+        sh["audio_proj.norm.bias"] = (768,)
     return sh
 
 
@@ -81,6 +95,12 @@ def make_dit_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
             t = torch.randn(shape, generator=g) / math.sqrt(fan_in)
         sd[name] = t.to(device=device, dtype=dtype)
     return sd
+
+
+def make_audio_embed(num_frames, seed=0, scale=1.0):
+    """wav2vec-style window features of a clip: [1, num_frames, 5, 12, 768] (svi_video_talk.py:412-430), seeded."""
+    g = torch.Generator(device="cpu").manual_seed(4321 + seed)
+    return torch.randn(1, num_frames, 5, 12, 768, generator=g) * scale
 
 
 def make_dit_state_dict_fast(cfg, seed=0, device="cuda", dtype=torch.bfloat16):
