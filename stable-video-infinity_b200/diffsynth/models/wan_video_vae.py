@@ -527,9 +527,9 @@ class WanVideoVAE(nn.Module):
         return e
 
     def encode(self, videos, device, tiled=False, tile_size=(34, 34), tile_stride=(18, 16)):
-        if tiled:
-            raise NotImplementedError("tiled VAE encode changes numerics (blend ramps) and exists for <80 GB GPUs; "
-                                      "untiled is the B200 path (SURVEY.md §5)")
+        # tiled=True (the pipelines' default for video-to-video input): the reference's tiling (:643-744) is a memory
+        # workaround whose blend ramps change the latents; with 180 GB of HBM the untiled encode fits and is used, exactly
+        # as decode() does
         eng = self.engine(device)
         return torch.stack([eng.encode(v) for v in videos])
 
