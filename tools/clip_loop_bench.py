@@ -1,0 +1,106 @@
+"""Measured whole-clip time through the public pipeline call (reduced to 2 chained clips):
+SVIVideoPipeline.__call__ on an 81-frame 480x832 clip, 50 CFG steps, with every stage the reference runs per clip —
+umT5 prompt encoding (positive + negative), CLIP image encoding, VAE encode of the conditioning video, 100 DiT forwards,
+VAE decode, uint8 frame conversion — and the clip loop of test_svi.py:424-485 (last frames recycled as the next clip's
+conditioning).  Random-init weights: a 1.3B-width image-to-video DiT (d 1536, 30 layers, in_dim 36, CLIP branch), the
+full-size umT5-XXL and CLIP ViT-H encoders, the Wan VAE.
+
+    python tools/clip_loop_bench.py [--clips 2] [--steps 50] [--motion-frames 5]
+
+Prints one JSON object with per-clip wall seconds (time.perf_counter around pipe(...), synchronised) and clips/hour."""
+import argparse
+import json
+import os
+import sys
+import time
+import types
+
+import numpy as np
+import torch
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "stable-video-infinity_b200")):
+    sys.path.insert(0, p)
+from tools import synth, synth_enc, synth_vae  # noqa: E402
+from tools.enc_bench import device_init  # noqa: E402
+
+
+class TokenPrompter:
+    """WanPrompter front end without a tokenizer directory (none in this image): seeded token ids of a fixed prompt
+    length go through the real text encoder + zero fill, exactly like WanPrompter.encode_prompt after tokenisation."""
+
+    def __init__(self, prompter, vocab):
+        self.prompter, self.vocab = prompter, vocab
+
+    def __call__(self, prompt, positive=True):
+        g = torch.Generator().manual_seed(hash(prompt) % 100000 + (0 if positive else 1))
+        n = 60 if positive else 90
+        ids = torch.zeros(1, 512, dtype=torch.int64)
+        ids[0, :n] = torch.randint(2, self.vocab, (n,), generator=g)
+        mask = (ids > 0).long()
+        return self.prompter.encode_ids(ids, mask, device="cuda").to(torch.float32)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--clips", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--motion-frames", type=int, default=5)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=832)
+    a = ap.parse_args()
+    from diffsynth import ModelManager, SVIVideoPipeline
+    from diffsynth.models.wan_video_dit import WanModel, precompute_freqs_cis_3d
+    from diffsynth.models.wan_video_image_encoder import WanImageEncoder
+    from diffsynth.models.wan_video_text_encoder import WanTextEncoder
+    from diffsynth.models.wan_video_vae import WanVideoVAE
+    from diffsynth.prompters import WanPrompter
+    dev = "cuda"
+    cfg = dict(synth.CFG_T2V_1_3B, has_image_input=True, in_dim=36)
+    with torch.device("meta"):
+        dit = WanModel(**cfg)
+    dit.load_state_dict(synth.make_dit_state_dict_fast(cfg, seed=0, device=dev, dtype=torch.bfloat16), assign=True)
+    dit.freqs = precompute_freqs_cis_3d(128)
+    dit.eval()
+    vae = WanVideoVAE().eval()
+    vae.load_state_dict(synth_vae.make_vae_state_dict(seed=0))
+    vae.to(dev)
+    with torch.device("meta"):
+        te = WanTextEncoder(**synth_enc.TEXT_UMT5_XXL).to(torch.bfloat16)
+        ie = WanImageEncoder(**synth_enc.CLIP_VIT_H).to(torch.bfloat16)
+    te, ie = device_init(te, 0), device_init(ie, 1)
+    mm = ModelManager(torch_dtype=torch.bfloat16, device=dev)
+    mm.add_model("wan_video_dit", dit)
+    mm.add_model("wan_video_vae", vae)
+    mm.add_model("wan_video_image_encoder", ie)
+    pipe = SVIVideoPipeline.from_model_manager(mm, torch_dtype=torch.bfloat16, device=dev, is_test=True)
+    wp = WanPrompter()
+    wp.fetch_models(te)
+    pipe.text_encoder = te
+    pipe.prompter = TokenPrompter(wp, synth_enc.TEXT_UMT5_XXL["vocab"])
+    img = Image.fromarray(np.random.default_rng(5).integers(0, 255, size=(a.height, a.width, 3), dtype=np.uint8))
+    ref = torch.from_numpy(np.array(img))
+    args = types.SimpleNamespace(ref_pad_cfg=False, ref_pad_num=-1, sequential_cfg="none")
+    cond, video_list, secs = img, [], []
+    for k in range(a.clips):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        video = pipe(prompt=f"prompt {k}", negative_prompt="negative", input_image=cond, num_inference_steps=a.steps,
+                     cfg_scale={"text": 5.0}, seed=42 * k, tiled=False, random_ref_frame=ref, height=a.height, width=a.width,
+                     num_frames=81, args=args, progress_bar_cmd=lambda x: x)
+        torch.cuda.synchronize()
+        secs.append(time.perf_counter() - t0)
+        cond = video[-a.motion_frames:]
+        video_list += video[:-a.motion_frames] if k < a.clips - 1 else video
+    steady = secs[1:] if len(secs) > 1 else secs
+    print(json.dumps({"workload": f"{a.clips} chained SVI clips, 81f x {a.height}x{a.width}, {a.steps} CFG steps, "
+                                  f"{a.motion_frames} recycled motion frames", "clip_seconds": secs,
+                      "steady_clip_s": sum(steady) / len(steady), "clips_per_hour": 3600.0 * len(steady) / sum(steady),
+                      "frames_kept": len(video_list), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                      "models": "1.3B-width I2V DiT + umT5-XXL + CLIP ViT-H + Wan VAE, random init",
+                      "note": "first clip includes one-time engine builds, graph capture and kernel attribute setup"}))
+
+
+if __name__ == "__main__":
+    main()
