@@ -309,9 +309,6 @@ class WanDiTEngine:
             self._ws[key] = t
         return t
 
-    def _gemm(self, *a, **k):
-        return self.k.gemm(*a, **k)
-
     def rope(self, f, h, w):
         key = (f, h, w)
         if key not in self._rope:

@@ -20,7 +20,6 @@ The streaming semantics (which conv has which history on which chunk) are those 
 ``oracle/wan_vae_oracle.py``.  Precision: bf16 conv operands, fp32 accumulation, fp32 activations and norms
 (the reference runs the VAE in fp32, svi_video.py:378,386; parity is reported in uint8 levels).
 """
-import math
 
 import torch
 import torch.nn as nn

@@ -8,7 +8,6 @@ Public surface follows the reference (``diffsynth/pipelines/svi_video.py``: ``SV
   one fused CFG+Euler kernel (reference: 2 sequential forwards + 4 elementwise launches, :392-421);
 * nothing is offloaded or copied through the CPU (reference VAE round trip, wan_video_vae.py:761-786).
 """
-import types
 from typing import Optional
 
 import numpy as np
@@ -17,7 +16,7 @@ from PIL import Image
 from tqdm import tqdm
 
 from .. import _native as nv
-from ..models.wan_video_dit import ContextState, WanModel
+from ..models.wan_video_dit import WanModel
 from ..schedulers.flow_match import FlowMatchScheduler
 from .base import BasePipeline
 

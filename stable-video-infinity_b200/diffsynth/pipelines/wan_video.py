@@ -5,7 +5,6 @@ Same hot loop as SVIVideoPipeline (shared implementation); differences follow th
 The pose / replace variants of that file (:411-1583) are out of scope.
 """
 import torch
-from PIL import Image
 from tqdm import tqdm
 
 from .svi_video import SVIVideoPipeline, model_fn_wan_video  # noqa: F401  (re-exported like the reference)
