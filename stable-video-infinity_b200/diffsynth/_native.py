@@ -107,6 +107,14 @@ def load():
     return lib
 
 
+def require_cuda(device, what):
+    """Every engine calls this first: the kernels exist for sm_100a only, so anything but a CUDA device is an error (there is
+    no CPU path), and the library must be loadable."""
+    if torch.device(device).type != "cuda":
+        raise RuntimeError(f"svi_b200: {what} runs only on a CUDA device (sm_100a kernels; no CPU fallback)")
+    load()
+
+
 def _check(rc, name):
     if rc != 0:
         msg = load().svi_last_error().decode("utf-8", "replace")

@@ -73,9 +73,7 @@ class DWPoseEmbeddingEngine:
     MAX_T = 4      # output frames per conv launch (slot table of svi_conv_desc)
 
     def __init__(self, seq: nn.Sequential, device):
-        if torch.device(device).type != "cuda":
-            raise RuntimeError("svi_b200: the pose stem runs only on a CUDA device (sm_100a kernels; no CPU fallback)")
-        nv.load()
+        nv.require_cuda(device, "the pose stem")
         self.device = torch.device(device)
         plan = StemPlan(seq, self.device)
         self.c, self.full, self.down, self.t_stride = plan.c, plan.full, plan.down, plan.t_stride

@@ -255,9 +255,7 @@ class WanDiTEngine:
     """Runs WanModel's arithmetic on the native kernels.  One instance per (model, device)."""
 
     def __init__(self, model: "WanModel", device):
-        if torch.device(device).type != "cuda":
-            raise RuntimeError("svi_b200: the Wan DiT runs only on a CUDA device (sm_100a kernels; no CPU fallback)")
-        nv.load()
+        nv.require_cuda(device, "the Wan DiT")
         self.device = torch.device(device)
         self.model = model
         self.dim, self.H = model.dim, model.num_heads

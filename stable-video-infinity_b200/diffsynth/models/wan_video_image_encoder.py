@@ -69,9 +69,7 @@ class _Clip(nn.Module):
 
 class WanImageEncoderEngine:
     def __init__(self, vit: VisionTransformer, device):
-        if torch.device(device).type != "cuda":
-            raise RuntimeError("svi_b200: the image encoder runs only on a CUDA device (sm_100a kernels; no CPU fallback)")
-        nv.load()
+        nv.require_cuda(device, "the image encoder")
         self.device = torch.device(device)
         self.dim, self.H, self.hd = vit.dim, vit.num_heads, vit.dim // vit.num_heads
         self.image_size, self.patch, self.eps = vit.image_size, vit.patch_size, vit.norm_eps

@@ -82,9 +82,7 @@ class WanTextEncoderEngine:
     """Kernel-ready weights of one WanTextEncoder on one device + the forward that drives the native kernels."""
 
     def __init__(self, model: "WanTextEncoder", device):
-        if torch.device(device).type != "cuda":
-            raise RuntimeError("svi_b200: the text encoder runs only on a CUDA device (sm_100a kernels; no CPU fallback)")
-        nv.load()
+        nv.require_cuda(device, "the text encoder")
         self.device = torch.device(device)
         self.dim, self.dim_attn, self.H = model.dim, model.dim_attn, model.num_heads
         self.hd = model.dim_attn // model.num_heads

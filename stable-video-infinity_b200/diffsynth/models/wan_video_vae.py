@@ -209,9 +209,7 @@ class _Ring:
 
 class WanVAEEngine:
     def __init__(self, vae: "WanVideoVAE", device):
-        if torch.device(device).type != "cuda":
-            raise RuntimeError("svi_b200: the Wan VAE runs only on a CUDA device (sm_100a kernels; no CPU fallback)")
-        nv.load()
+        nv.require_cuda(device, "the Wan VAE")
         self.device = torch.device(device)
         self.sig = vae._param_signature()
         m = vae.model

@@ -1,0 +1,140 @@
+"""Torch stand-ins for the DiT kernels of diffsynth._native — TEST INFRASTRUCTURE ONLY.
+
+The product has no CPU path: every engine starts with `_native.require_cuda`, and every wrapper refuses CPU tensors.
+To test the HOST logic of the engines on the CPU-only build box (operation order, buffer aliasing, fused-weight layouts,
+the sequence-parallel row bookkeeping under a 2-process gloo group), `install(monkeypatch)` swaps the wrappers of the
+module for the functions below, which restate what each kernel computes (include/svi_b200.h) with torch on whatever
+device the tensors live on, rounding to bf16 exactly where the kernel stores bf16.  Nothing under
+stable-video-infinity_b200/ imports this file.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def _act(v, act):
+    if act == 1:
+        return F.gelu(v, approximate="tanh")
+    if act == 2:
+        return F.silu(v)
+    if act == 3:
+        return F.gelu(v)
+    if act == 4:
+        return F.relu(v)
+    return v
+
+
+def gemm(a, w, out, bias=None, act=0, gate=None, residual=None, sumsq=None, sumsq_group_cols=0):
+    v = a.float() @ w.float().T
+    if bias is not None:
+        v = v + bias
+    v = _act(v, act)
+    if sumsq is not None:                          # atomicAdd of the row sum of squares per column group
+        for g in range(sumsq.shape[1]):
+            cols = v[:, g * sumsq_group_cols:(g + 1) * sumsq_group_cols]
+            if cols.numel():
+                sumsq[:, g] += (cols * cols).sum(dim=1)
+    if gate is not None:
+        v = v * gate
+    if residual is not None:
+        v = v + residual
+    out.copy_(v.to(out.dtype))
+    return out
+
+
+def attention(q, k, v, out, num_heads, scale=None, accumulate=False, workspace=None):
+    H, hd = num_heads, q.shape[1] // num_heads
+    scale = hd ** -0.5 if scale is None else scale
+    qf, kf, vf = (t.float().reshape(t.shape[0], H, hd).transpose(0, 1) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    p = torch.exp(s - s.amax(dim=-1, keepdim=True))
+    o = (p.to(torch.bfloat16).float() @ vf) / p.sum(dim=-1, keepdim=True)      # P is consumed as bf16, the row sum in fp32
+    o = o.transpose(0, 1).reshape(q.shape[0], H * hd)
+    if accumulate:
+        o = o + out.float()
+    out.copy_(o.to(out.dtype))
+    return out
+
+
+def attention_workspace_bytes(Lq, Lk, num_heads):
+    return 0
+
+
+def layernorm_modulate(x, out, eps, gamma=None, beta=None, scale=None, shift=None):
+    y = F.layer_norm(x, (x.shape[1],), gamma, beta, eps)
+    if scale is not None:
+        y = y * (1 + scale)
+    if shift is not None:
+        y = y + shift
+    out.copy_(y.to(out.dtype))
+    return out
+
+
+def rmsnorm_rope(t, sumsq, sumsq_col, eps, weight, rope_cos=None, rope_sin=None, row_offset=0):
+    M, D = t.shape
+    rs = torch.rsqrt(sumsq[:, sumsq_col] / D + eps).unsqueeze(1)
+    v = t.float() * rs * weight
+    if rope_cos is not None:
+        rows = torch.arange(M) + row_offset
+        cos = rope_cos[rows].repeat(1, D // 128)                # [M, D/2]: pair p of head h uses table column p
+        sin = rope_sin[rows].repeat(1, D // 128)
+        re, im = v[:, 0::2], v[:, 1::2]
+        v = torch.stack([re * cos - im * sin, re * sin + im * cos], dim=-1).reshape(M, D)
+    t.copy_(v.to(t.dtype))
+    return t
+
+
+def patchify_gather(x, y, tokens):
+    src = x if y is None else torch.cat([x, y], dim=0)
+    C, Fr, H, W = src.shape
+    p = src.reshape(C, Fr, H // 2, 2, W // 2, 2).permute(1, 2, 4, 0, 3, 5).reshape(Fr * (H // 2) * (W // 2), C * 4)
+    tokens.zero_()
+    tokens[:, :C * 4] = p.to(tokens.dtype)
+    return tokens
+
+
+def unpatchify(head_out, out):
+    C, Fr, H, W = out.shape
+    v = head_out[:, :4 * C].reshape(Fr, H // 2, W // 2, 2, 2, C).permute(5, 0, 1, 3, 2, 4).reshape(C, Fr, H, W)
+    out.copy_(v)
+    return out
+
+
+def cfg_euler_step(latents, v_cond, v_uncond, cfg, sigma, sigma_next):
+    v = v_cond if v_uncond is None else v_uncond + cfg * (v_cond - v_uncond)
+    latents.add_(v * (sigma_next - sigma))
+    return latents
+
+
+def cast_f32_to_bf16(src, dst, act=0):
+    dst.copy_(_act(src, act).to(dst.dtype))
+    return dst
+
+
+def cast_bf16_to_f32(src, dst):
+    dst.copy_(src.float())
+    return dst
+
+
+def add_rows(table, t, out):
+    out.copy_(table + t)
+    return out
+
+
+def axpby(a, alpha, b, beta, out):
+    out.copy_(alpha * a + beta * b)
+    return out
+
+
+_NAMES = ("gemm", "attention", "attention_workspace_bytes", "layernorm_modulate", "rmsnorm_rope", "patchify_gather",
+          "unpatchify", "cfg_euler_step", "cast_f32_to_bf16", "cast_bf16_to_f32", "add_rows", "axpby")
+
+
+def install(monkeypatch=None):
+    """Replace the wrappers of diffsynth._native by the functions above and lift the CUDA requirement.  With pytest's
+    monkeypatch the change is undone after the test; without (spawned worker processes) it stays for the process."""
+    from diffsynth import _native as nv
+    put = (lambda n, v: monkeypatch.setattr(nv, n, v)) if monkeypatch is not None else (lambda n, v: setattr(nv, n, v))
+    for name in _NAMES:
+        put(name, globals()[name])
+    put("require_cuda", lambda device, what: None)
+    put("load", lambda: None)
