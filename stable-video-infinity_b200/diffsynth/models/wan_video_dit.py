@@ -497,14 +497,18 @@ class WanDiTEngine:
         # --- audio cross-attention (SVI-Talk, wan_video_dit.py:361-366): tokens of latent frame f attend to that frame's
         #     audio tokens (models/attention.py:318-371); 1/sqrt(head_dim) scale, no q/k norm
         if audio is not None:
-            S, Ta = L // audio.n_frames, audio.tokens
+            Ta = audio.tokens
+            r0 = 0 if sp is None else sp.sp_rank * L                       # first global token row of this rank
+            S = (L if sp is None else L * sp.sp_size) // audio.n_frames     # tokens per latent frame
             self.k.layernorm_modulate(x, h, bw.eps, gamma=bw.nxw, beta=bw.nxb)
             aq = qkv[:, :d]
             self.k.gemm(h, bw.w_aq, aq, bias=bw.b_aq)
             kva = audio.kv[i]
-            for fr in range(audio.n_frames):
-                kf = kva[fr * Ta:(fr + 1) * Ta]
-                self.k.attention(aq[fr * S:(fr + 1) * S], kf[:, :d], kf[:, d:], att[fr * S:(fr + 1) * S], H)
+            for fr in range(audio.n_frames):                                # the rank's rows may start / end inside a frame
+                lo, hi = max(fr * S, r0) - r0, min((fr + 1) * S, r0 + L) - r0
+                if lo < hi:
+                    kf = kva[fr * Ta:(fr + 1) * Ta]
+                    self.k.attention(aq[lo:hi], kf[:, :d], kf[:, d:], att[lo:hi], H)
             self.k.gemm(att, bw.w_ap, x, bias=bw.b_ap, residual=x)
         # --- FFN
         self.k.layernorm_modulate(x, h, bw.eps, scale=mod[4], shift=mod[3])
@@ -541,9 +545,7 @@ class WanDiTEngine:
         nh = self.w_head.shape[0]
         if out is None:
             out = torch.empty(1, nh // 4, f, Hl, Wl, device=dev, dtype=torch.float32)
-        if audio is not None:
-            if sp is not None:
-                raise NotImplementedError("svi_b200: audio cross-attention under sequence parallelism is not implemented")
+        if audio is not None:       # audio K|V are tiny and replicated: under sequence parallelism every rank computes them
             if not isinstance(audio, AudioState):
                 audio = self.audio_state(audio)
             if L % audio.n_frames or audio.n_frames != f:

@@ -39,10 +39,12 @@ def model_fn_wan_talk_video(dit, x, timestep, context, clip_feature=None, y=None
                             audio_embed_tuple=None, use_unified_sequence_parallel=False, use_controlnet=False, **kwargs):
     """Drop-in for reference svi_video_talk.py:82-157: one forward of the enable_multitalk DiT, result in x.dtype.
     `audio_embed_tuple` may also be an AudioState (pre-projected audio)."""
+    sp = None
     if use_unified_sequence_parallel:
-        raise NotImplementedError("svi_b200: SVI-Talk under sequence parallelism is not implemented")
+        from ..distributed.sequence_parallel import get_sp_group
+        sp = get_sp_group()
     eng = dit.engine(x.device if x.is_cuda else None)
-    out = eng.forward(x, timestep, context, clip_feature, y, tea_cache=tea_cache, add_condition=add_condition,
+    out = eng.forward(x, timestep, context, clip_feature, y, sp=sp, tea_cache=tea_cache, add_condition=add_condition,
                       audio=audio_embed_tuple)
     return out.to(x.dtype)
 
@@ -54,12 +56,14 @@ class SVITalkVideoPipeline(SVIVideoPipeline):
 
     @staticmethod
     def from_model_manager(model_manager, torch_dtype=None, device=None, use_usp=False, is_test=False, wav2vec_path=None):
-        if use_usp:
-            raise NotImplementedError("svi_b200: SVI-Talk under sequence parallelism is not implemented")
         device = model_manager.device if device is None else device
         torch_dtype = model_manager.torch_dtype if torch_dtype is None else torch_dtype
         pipe = SVITalkVideoPipeline(device=device, torch_dtype=torch_dtype, wav2vec_path=wav2vec_path, is_test=is_test)
         pipe.fetch_models(model_manager)
+        if use_usp:
+            from ..distributed.sequence_parallel import get_sp_group
+            pipe.sp_size = get_sp_group().world
+            pipe.use_unified_sequence_parallel = True
         return pipe
 
     def get_audio_embedding(self, audio_path, num_frames, audio_start_idx=0):
@@ -75,6 +79,11 @@ class SVITalkVideoPipeline(SVIVideoPipeline):
                              cfg_scale, progress_bar_cmd=lambda x: x, tea_cache_posi=None, tea_cache_nega=None, condition=None):
         """reference _sample_with_multitalk :448-466 (three forwards per step unless both scales are 1)."""
         eng = self.dit.engine(self.device)
+        sp = None
+        if self.use_unified_sequence_parallel:
+            from ..distributed.sequence_parallel import get_sp_group
+            sp = get_sp_group()
+            sp = sp if sp.sp_size > 1 else None
         lat = latents if latents.dtype == torch.float32 and latents.is_contiguous() else latents.to(torch.float32).contiguous()
         if y is not None:
             y = y.to(device=self.device, dtype=torch.float32).contiguous()
@@ -88,11 +97,11 @@ class SVITalkVideoPipeline(SVIVideoPipeline):
         n = len(ts)
         for i in progress_bar_cmd(range(n)):
             t = float(ts[i])
-            eng.forward(lat, t, cp, y=y, out=v_c, tea_cache=tea_cache_posi, add_condition=condition, audio=audio)
+            eng.forward(lat, t, cp, y=y, sp=sp, out=v_c, tea_cache=tea_cache_posi, add_condition=condition, audio=audio)
             if st != 1.0 or sa != 1.0:
                 # the reference hands the SAME nega TeaCache to both of these calls (:457-458); kept
-                eng.forward(lat, t, cn, y=y, out=v_u, tea_cache=tea_cache_nega, audio=silent)
-                eng.forward(lat, t, cn, y=y, out=v_d, tea_cache=tea_cache_nega, add_condition=condition, audio=audio)
+                eng.forward(lat, t, cn, y=y, sp=sp, out=v_u, tea_cache=tea_cache_nega, audio=silent)
+                eng.forward(lat, t, cn, y=y, sp=sp, out=v_d, tea_cache=tea_cache_nega, add_condition=condition, audio=audio)
                 # v = v_u + st (v_c - v_d) + sa (v_d - v_u) = st v_c + (sa - st) v_d + (1 - sa) v_u
                 eng.k.axpby(v_c, st, v_d, sa - st, v_c)
                 eng.k.axpby(v_c, 1.0, v_u, 1.0 - sa, v_c)

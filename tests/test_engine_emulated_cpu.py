@@ -111,6 +111,17 @@ def _sp_worker(rank, world, port, q):
                 eng.forward(lat_b, 500.0, cn, y=kw.get("y"), out=vu)
                 eng.k.cfg_euler_step(lat_b, vc, vu, 5.0, 0.9, 0.8)
                 res[f"{tag} {sp.describe()} step"] = (lat_a - lat_b).abs().max().item()
+        # SVI-Talk under the token split: 3 latent frames x 16 tokens over 2 ranks -> rank rows start / end inside frame 1
+        from diffsynth.pipelines.svi_video_talk import preprocess_audio
+        cfg = synth.CFG_TINY_TALK
+        sd = {k: v.to(torch.bfloat16).float() for k, v in synth.make_dit_state_dict(cfg, seed=5).items()}
+        eng = _model(cfg, sd).engine("cpu")
+        inp = synth.make_dit_inputs(cfg, 3, 8, 8, seed=5, ctx_len=24)
+        tup = preprocess_audio(synth.make_audio_embed(9, seed=5).to(torch.bfloat16).float())
+        ref = eng.forward(inp["x"], 500.0, inp["context"], inp["clip_feature"], inp["y"], audio=tup).clone()
+        sp = SequenceParallelGroup(world, rank, cfg_parallel=False)
+        out = eng.forward(inp["x"], 500.0, inp["context"], inp["clip_feature"], inp["y"], sp=sp, audio=tup)
+        res["talk cfg1xsp2 forward"] = (out - ref).abs().max().item()
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -131,6 +142,6 @@ def test_sequence_and_cfg_parallel_plan_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, res in got:
-        assert len(res) == 6, res                     # 2 models x (sp2 forward, sp2 step, cfg2 step)
+        assert len(res) == 7, res                     # 2 models x (sp2 forward, sp2 step, cfg2 step) + talk sp2 forward
         for name, err in res.items():
             assert err < 2e-2, (rank, name, err)
