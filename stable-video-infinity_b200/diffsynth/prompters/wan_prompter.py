@@ -19,42 +19,38 @@ except ImportError:       # not in this image: plain prompts are unaffected
     _fix_text = lambda s: s
 
 
-def basic_clean(text):
-    text = _fix_text(text)
-    return html.unescape(html.unescape(text)).strip()
-
-
-def whitespace_clean(text):
-    return re.sub(r"\s+", " ", text).strip()
+def clean_prompt(text, lower=False):
+    """'whitespace' / 'lower' cleaning of the reference tokenizer wrapper (:12-21, :74-81): repair mojibake (ftfy, when
+    installed), undo doubly escaped HTML entities, collapse runs of whitespace."""
+    text = html.unescape(html.unescape(_fix_text(text)))
+    text = re.sub(r"\s+", " ", text.strip()).strip()
+    return text.lower() if lower else text
 
 
 class HuggingfaceTokenizer:
-    """Fixed-length tokenisation (reference :35-82, 'whitespace' / 'lower' cleaning modes)."""
+    """Fixed-length front end of a HuggingFace tokenizer directory (reference :35-82): prompts are cleaned, padded /
+    truncated to `seq_len` tokens, and returned as int64 ids (and the attention mask on request)."""
+
+    CLEAN_MODES = (None, "whitespace", "lower")
 
     def __init__(self, name, seq_len=None, clean=None, **kwargs):
-        if clean not in (None, "whitespace", "lower"):
-            raise ValueError(f"unsupported clean mode {clean!r}")
+        if clean not in self.CLEAN_MODES:
+            raise ValueError(f"clean must be one of {self.CLEAN_MODES}, got {clean!r}")
         from transformers import AutoTokenizer
         self.name, self.seq_len, self.clean = name, seq_len, clean
         self.tokenizer = AutoTokenizer.from_pretrained(name, **kwargs)
         self.vocab_size = self.tokenizer.vocab_size
 
-    def _clean(self, text):
-        text = whitespace_clean(basic_clean(text))
-        return text.lower() if self.clean == "lower" else text
-
-    def __call__(self, sequence, **kwargs):
-        return_mask = kwargs.pop("return_mask", False)
-        opts = {"return_tensors": "pt"}
+    def __call__(self, sequence, return_mask=False, **tokenizer_kwargs):
+        texts = [sequence] if isinstance(sequence, str) else list(sequence)
+        if self.clean is not None:
+            texts = [clean_prompt(t, lower=self.clean == "lower") for t in texts]
+        options = dict(return_tensors="pt")
         if self.seq_len is not None:
-            opts.update(padding="max_length", truncation=True, max_length=self.seq_len)
-        opts.update(kwargs)
-        if isinstance(sequence, str):
-            sequence = [sequence]
-        if self.clean:
-            sequence = [self._clean(s) for s in sequence]
-        enc = self.tokenizer(sequence, **opts)
-        return (enc.input_ids, enc.attention_mask) if return_mask else enc.input_ids
+            options.update(padding="max_length", truncation=True, max_length=self.seq_len)
+        options.update(tokenizer_kwargs)
+        batch = self.tokenizer(texts, **options)
+        return (batch.input_ids, batch.attention_mask) if return_mask else batch.input_ids
 
 
 class WanPrompter(BasePrompter):
