@@ -364,3 +364,34 @@ def test_talk_model_key_contract_and_audio_windows():
         assert torch.equal(x, y)
     with pytest.raises(ValueError):
         preprocess_audio(synth.make_audio_embed(11))
+
+
+def test_model_manager_loads_a_sharded_vae_checkpoint_end_to_end(tmp_path):
+    """The whole checkpoint path of test_svi.py:253-262 on a real-size file set: a Wan VAE state dict (un-prefixed keys,
+    fingerprint ccc42284…) written as two safetensors shards -> ModelManager.load_models([[shard, shard]]) merges them
+    (reference model_manager.py:660-663), detects the model by its key hash, constructs on 'meta', converts the keys,
+    assigns the tensors and casts -> fetch_model returns a usable WanVideoVAE whose constant tables are real tensors."""
+    from safetensors.torch import save_file
+    from diffsynth import ModelManager
+    from diffsynth.models.wan_video_vae import WanVideoVAE
+    from tools import synth_vae
+    sd = {k[len("model."):]: v.to(torch.bfloat16).contiguous() for k, v in synth_vae.make_vae_state_dict(seed=0).items()}
+    keys = sorted(sd)
+    a, b = str(tmp_path / "vae-00001-of-00002.safetensors"), str(tmp_path / "vae-00002-of-00002.safetensors")
+    save_file({k: sd[k] for k in keys[::2]}, a)
+    save_file({k: sd[k] for k in keys[1::2]}, b)
+    mm = ModelManager(torch_dtype=torch.float32, device="cpu")
+    mm.load_models([[a, b]])
+    hit = mm.fetch_model("wan_video_vae", require_model_path=True)
+    assert hit is not None and isinstance(hit[0], WanVideoVAE) and hit[1] == [a, b]
+    vae = hit[0]
+    assert not any(p.is_meta for p in vae.parameters()) and all(p.dtype == torch.float32 for p in vae.parameters())
+    assert not vae.mean.is_meta and vae.mean.shape == (16,)
+    got = dict(vae.named_parameters())
+    for k in (keys[0], keys[len(keys) // 2], keys[-1]):
+        assert torch.equal(got["model." + k], sd[k].float())
+    assert mm.fetch_model("wan_video_dit") is None
+    with pytest.raises(RuntimeError, match="cannot detect"):
+        bad = str(tmp_path / "other.safetensors")
+        save_file({"foo.weight": torch.zeros(2, 2)}, bad)
+        mm.load_models([bad])
