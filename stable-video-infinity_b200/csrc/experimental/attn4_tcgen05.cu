@@ -1,0 +1,561 @@
+// EXPERIMENT (not built into the library, not yet run on a GPU): attn_tcgen05.cu with ONE MMA-ISSUING WARP PER Q TILE.
+//
+// Why: in the product kernel a single warp issues the MMAs of both Q tiles in a fixed order (PV0 half 0, PV0 half 1,
+// QK0(j+1), PV1 ...).  When the softmax of tile 0 is late the warp blocks on p_ready[0] although tile 1's P may be
+// ready: head-of-line blocking; the ncu source view shows the softmax warps waiting for S in 29 % of the samples while the
+// tensor pipe is busy only ~50 % of the cycles.  Here warp 9 issues for tile 0 and warp 10 for tile 1; each blocks only on
+// its own tile's barriers and the tensor pipe interleaves the two streams.  The K / V stage barriers are released by BOTH
+// warps (arrival count 2), because a tcgen05.commit only tracks the MMAs of the issuing thread.
+// To try it: add the file to the Makefile, export launch_attn4 through a test entry point and time it with
+// tools/gpu_check.py perf_attn.
+//
+// Non-causal flash attention forward for sm_100a, head_dim 128, bf16 operands, fp32 softmax.
+//
+// One CTA owns TWO 128-row Q tiles of one head and streams K/V tiles of 128 rows past them:
+//
+//   warps 0-3 : softmax warpgroup for Q tile 0 (thread = row; TMEM lane quadrant = warp % 4)
+//   warps 4-7 : softmax warpgroup for Q tile 1
+//   warp  8   : TMA producer (Q once, then K_j / V_j into 2-stage rings, 128B-swizzled boxes)
+//   warp  9   : tcgen05.mma issuer of Q tile 0 + TMEM owner
+//   warp 10   : tcgen05.mma issuer of Q tile 1
+//
+// TMEM (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,384) | O1 [384,512); P_i (bf16, 64 columns)
+// aliases the front of S_i and is consumed straight from TMEM by the P*V MMA (A operand in TMEM).
+// The issue order  PV_i(j) ; QK_i(j+1)  per tile ping-pongs the two softmax warpgroups against the
+// tensor pipe: while warpgroup 0 exponentiates S0(j+1), the tensor core runs PV1(j) and QK1(j+1).
+// Online softmax uses the lazy-rescale rule (O is only rescaled when a row max grows by > 2^8).
+//
+// Work units are (head, pair of Q tiles).  The launch plan (plan_split, host side) runs `n_full` units whole and cuts
+// each of the remaining ones into `split` slices of the K/V stream, so the last, partly filled wave of CTAs is spread
+// over all SMs; sliced units leave (unnormalised O, row max, row sum) in a workspace and attn_merge_kernel combines
+// them.  Without a workspace every unit runs whole.
+// Replaces flash_attention(), reference wan_video_dit.py:116-147.
+#include "../common.cuh"
+#include "../../../include/svi_b200.h"
+
+namespace svi {
+namespace attn4 {
+
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int HD = 128;
+constexpr int KV_STAGES = 2;
+constexpr int HALF_BYTES = 128 * 64 * 2;   // one 128-row x 64-col swizzled box (16 KB)
+constexpr int TILE_BYTES = 2 * HALF_BYTES;  // 128 x 128 bf16 (32 KB)
+constexpr int NUM_THREADS = 352;   // + one MMA warp
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exp2 of two values on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial on [-0.5, 0.5],
+// max relative error 7.5e-5 — invisible after the bf16 rounding of P).  MUFU.EX2 issues at 16 lanes/clk/SM, i.e. the
+// 2 x 128 x 128 exponentials of one K/V step cost as many cycles as its four MMAs; moving ~3/8 of them here balances
+// the XU, FMA and ALU pipes.  Uses the sm_100 packed-pair fp32 instructions (FFMA2 / FADD2).
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));   // 1.5 * 2^23: round(x) lands in the mantissa
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);             // x - round(x) in [-0.5, 0.5]
+  float2 q = __ffma2_rn(f, make_float2(0.055170949548482895f, 0.055170949548482895f),
+                        make_float2(0.2426096349954605f, 0.2426096349954605f));
+  q = __ffma2_rn(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  q = __ffma2_rn(q, f, make_float2(0.9999281764030457f, 0.9999281764030457f));
+  q.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));   // * 2^round(x)
+  q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return q;
+}
+
+struct Params {
+  __nv_bfloat16* O;
+  long long ldo;
+  int Lq, Lk;
+  float scale_log2;  // softmax scale * log2(e)
+  int accumulate;
+  // sequence-parallel K/V stream (sp_exchange.cu); kv_flags == nullptr: plain attention
+  const uint32_t* kv_flags;  // [n_chunks] arrival flag of each source rank's rows, written by that rank's push
+  uint32_t kv_epoch;         // value a flag holds once the rows of this launch have landed
+  int kv_chunk_rows;         // rows owned by each rank
+  int kv_self_chunk;         // this rank's chunk: produced locally, never waited for
+  int kv_first_tile;         // KV tile the stream starts on (first tile fully inside the local chunk)
+  // launch plan: units [0, n_full) whole; unit n_full + t/split gets slice t%split of the K/V stream
+  int n_qpairs;              // Q-tile pairs per head
+  int n_full;
+  int split;
+  float* ws_o;               // [slices][256 rows][128] unnormalised partial O
+  float2* ws_ml;             // [slices][256 rows] (row max in scaled log2 units, row sum)
+};
+
+// KV tile visited at iteration j: the stream starts on the rank's own rows and wraps around
+__device__ __forceinline__ int kv_tile_at(int j, int first_tile, int n_kv) {
+  const int t = j + first_tile;
+  return t >= n_kv ? t - n_kv : t;
+}
+
+// Producer side of the K/V exchange: block until the rows of `chunk` have been pushed into this GPU's buffer.
+__device__ __forceinline__ void wait_kv_chunk(const uint32_t* flags, int chunk, uint32_t epoch) {
+  const uint32_t* f = flags + chunk;
+  uint32_t v;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v == epoch) break;
+    __nanosleep(64);
+    if (++spins > (1u << 25)) {   // > 2 s: a peer died or the protocol is broken -> visible error, not a hang
+      printf("svi: K/V exchange timeout block(%d,%d) chunk %d flag %u want %u\n", blockIdx.x, blockIdx.y, chunk, v, epoch);
+      __trap();
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");   // later TMA (async proxy) reads see the pushed rows
+}
+
+// 10 warps over 4 SM sub-partitions put 3 warps on one 16K-register partition: 168 registers/thread is the ceiling
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_q = smem;                               // [2][TILE_BYTES]
+  uint8_t* smem_k = smem + 2 * TILE_BYTES;              // [KV_STAGES][TILE_BYTES]
+  uint8_t* smem_v = smem_k + KV_STAGES * TILE_BYTES;    // [KV_STAGES][TILE_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + KV_STAGES * TILE_BYTES);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* k_full = bars + 2;     // [2]
+  uint64_t* k_empty = bars + 4;    // [2]
+  uint64_t* v_full = bars + 6;     // [2]
+  uint64_t* v_empty = bars + 8;    // [2]
+  uint64_t* s_full = bars + 10;    // [2]  MMA -> softmax_i : S_i(j) ready (and PV_i(j-1) retired)
+  uint64_t* p_ready = bars + 12;   // [2][2] softmax_i -> MMA : half h (64 keys) of P_i(j) in TMEM, O_i rescaled; the P*V of
+                                   //        the first half overlaps the exponentials of the second half
+  uint64_t* o_full = bars + 16;    // [2]  MMA -> softmax_i : O_i final
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_kv_total = (p.Lk + BKV - 1) / BKV;
+  int unit = blockIdx.x, j_begin = 0, n_kv = n_kv_total;   // n_kv: K/V tiles THIS CTA streams, starting at j_begin
+  const int slice_slot = (int)blockIdx.x - p.n_full;        // >= 0: this CTA computes one slice of a unit
+  if (slice_slot >= 0) {
+    unit = p.n_full + slice_slot / p.split;
+    const int sl = slice_slot % p.split;
+    j_begin = (int)((long long)n_kv_total * sl / p.split);
+    n_kv = (int)((long long)n_kv_total * (sl + 1) / p.split) - j_begin;
+  }
+  const int head = unit / p.n_qpairs;
+  const int q_row0 = (unit % p.n_qpairs) * (2 * BQ);
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&q_full[i], 1);
+        mbar_init(&k_full[i], 1);
+        mbar_init(&k_empty[i], 2);     // released by both MMA warps
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], 2);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_ready[i * 2 + 0], 4);  // one arrive per softmax warp
+        mbar_init(&p_ready[i * 2 + 1], 4);
+        mbar_init(&o_full[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 8) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (lane == 0) {
+      const int col0 = head * HD;
+      auto load_tile = [&](uint8_t* dst, const CUtensorMap* m, uint64_t* bar, int row) {
+        mbar_expect_tx(bar, TILE_BYTES);
+        tma_load_2d(dst, m, bar, col0, row);
+        tma_load_2d(dst + HALF_BYTES, m, bar, col0 + 64, row);
+      };
+      load_tile(smem_q, &tmap_q, &q_full[0], q_row0);
+      int landed = p.kv_self_chunk;   // most recent remote chunk known to be present (chunks are visited in runs)
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        const int row = kv_tile_at(j_begin + j, p.kv_first_tile, n_kv_total) * BKV;
+        if (p.kv_flags) {
+          const int c0 = row / p.kv_chunk_rows;
+          const int c1 = (min(row + BKV, p.Lk) - 1) / p.kv_chunk_rows;
+          for (int c = c0; c <= c1; ++c) {
+            if (c == p.kv_self_chunk || c == landed) continue;
+            wait_kv_chunk(p.kv_flags, c, p.kv_epoch);
+            landed = c;
+          }
+        }
+        mbar_wait(&k_empty[s], ph ^ 1);
+        load_tile(smem_k + s * TILE_BYTES, &tmap_k, &k_full[s], row);
+        if (j == 0) load_tile(smem_q + TILE_BYTES, &tmap_q, &q_full[1], q_row0 + BQ);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        load_tile(smem_v + s * TILE_BYTES, &tmap_v, &v_full[s], row);
+      }
+    }
+  } else if (warp >= 9) {
+    // ------------------------------------ MMA issuers (one per Q tile) ---------------------
+    constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major (d contiguous)
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);   // P K-major (TMEM), V MN-major
+    constexpr uint32_t hi_kmaj = smem_desc_hi(1024, 2);            // SBO 1024 B (8 rows x 128 B), 128B swizzle
+    const uint32_t lead = (lane == 0) ? 1u : 0u;
+    const uint32_t q_lo = smem_desc_lo(smem_u32(smem_q), 16);
+    const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
+    const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), HALF_BYTES);  // MN-major: LBO = distance of the 64-col atoms
+    // whole warp executes (uniform operands -> uniform registers); `lead` predicates the single issuing lane
+    auto issue_qk = [&](int i, int ks) {   // 8 K-steps = 2 swizzle boxes x 4 (batched issue)
+      const uint32_t a0 = q_lo + ((i * TILE_BYTES) >> 4), b0 = k_lo + ((ks * TILE_BYTES) >> 4);
+      tc_mma_ss_k4(tmem_base + i * 128, a0, hi_kmaj, b0, hi_kmaj, idesc_qk, 0);
+      tc_mma_ss_k4(tmem_base + i * 128, a0 + (HALF_BYTES >> 4), hi_kmaj, b0 + (HALF_BYTES >> 4), hi_kmaj, idesc_qk, 1);
+    };
+    auto issue_pv_half = [&](int i, int vs, int h, uint32_t accumulate) {   // 4 K-steps = 64 K/V rows of half h
+      tc_mma_ts_k4(tmem_base + 256 + i * 128, tmem_base + i * 128 + h * 32, v_lo + ((vs * TILE_BYTES + h * 4 * 2048) >> 4),
+                   hi_kmaj, idesc_pv, accumulate);
+    };
+
+    // this warp owns Q tile i: prologue S_i(0) = Q_i K_0^T, then per K/V step  PV_i(j) ; QK_i(j+1)
+    const int i = warp - 9;
+    mbar_wait(&k_full[0], 0);
+    mbar_wait(&q_full[i], 0);
+    tc_fence_after();
+    issue_qk(i, 0);
+    tc_commit_p(lead, &s_full[i]);
+    tc_commit_p(lead, &k_empty[0]);
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int vs = j % KV_STAGES;
+      const int ks = (j + 1) % KV_STAGES;
+      const bool has_next = (j + 1) < n_kv;
+      mbar_wait(&v_full[vs], (j / KV_STAGES) & 1);
+      mbar_wait(&p_ready[i * 2 + 0], j & 1);
+      tc_fence_after();
+      issue_pv_half(i, vs, 0, j > 0);
+      if (has_next) mbar_wait(&k_full[ks], ((j + 1) / KV_STAGES) & 1);
+      mbar_wait(&p_ready[i * 2 + 1], j & 1);
+      tc_fence_after();
+      issue_pv_half(i, vs, 1, 1);
+      if (has_next) {
+        issue_qk(i, ks);
+        tc_commit_p(lead, &s_full[i]);
+      } else {
+        tc_commit_p(lead, &o_full[i]);
+      }
+      tc_commit_p(lead, &v_empty[vs]);
+      if (has_next) tc_commit_p(lead, &k_empty[ks]);
+    }
+  } else {
+    // ------------------------------------ softmax warpgroups ------------------------------
+    const int i = warp >> 2;    // which Q tile
+    const int quad = warp & 3;  // TMEM lane quadrant
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + i * 128 + lane_sel;
+    const uint32_t tO = tmem_base + 256 + i * 128 + lane_sel;
+    const float c = p.scale_log2;
+    float m_cur = -INFINITY;  // running row max (scaled, log2 domain); reference point of P and O
+    float l = 0.f;            // running row sum of P
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[i], j & 1);
+      tc_fence_after();
+      const int limit = p.Lk - kv_tile_at(j_begin + j, p.kv_first_tile, n_kv_total) * BKV;  // valid key columns (>=128: all)
+      // single pass: the whole 128-wide S row of this thread lives in registers (4 TMEM loads in flight, one wait)
+      uint32_t sr[4][32];
+      tmem_ld32(tS + 0, sr[0]);
+      tmem_ld32(tS + 32, sr[1]);
+      tmem_ld32(tS + 64, sr[2]);
+      tmem_ld32(tS + 96, sr[3]);
+      tmem_ld_wait();
+      if (limit < BKV) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (cc * 32 + e >= limit) sr[cc][e] = 0xff800000u;  // -inf: masked key column
+      }
+      // row max: 8 independent chains (the 128-long serial fmax chain was the critical path)
+      float m8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) m8[u] = fmaxf(__uint_as_float(sr[0][u]), __uint_as_float(sr[0][u + 8]));
+#pragma unroll
+      for (int e = 16; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[0][e]));
+#pragma unroll
+      for (int cc = 1; cc < 4; ++cc) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[cc][e]));
+      }
+      float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+      mx *= c;
+      // lazy rescale (warp-uniform decision because tcgen05.ld/st are warp-collective)
+      const bool need = (j > 0) && (mx > m_cur + RESCALE_THRESHOLD);
+      if (j == 0) {
+        m_cur = mx;
+      } else if (__any_sync(0xffffffffu, need)) {
+        const float m_new = fmaxf(m_cur, mx);
+        const float alpha = ex2(m_cur - m_new);
+        l *= alpha;
+        m_cur = m_new;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(tO + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+          tmem_st32(tO + cc * 32, r);
+        }
+      }
+      // P = exp2(S*c - m) (masked columns: exp2(-inf) = 0), 4 independent row-sum chains, bf16 pack into TMEM
+      float2 l4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_cur, -m_cur);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const int pr = e >> 1;   // pair index 0..15 inside the chunk
+          float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[cc][e]), __uint_as_float(sr[cc][e + 1])), c2, nm2);
+          float2 pv;
+          if ((pr & 7) < 3) {      // 6 of 16 pairs: FMA/ALU-pipe exponential
+            pv = exp2_poly2(x);
+          } else {                 // MUFU exponential
+            pv.x = ex2(x.x);
+            pv.y = ex2(x.y);
+          }
+          l4[pr & 3] = __fadd2_rn(l4[pr & 3], pv);
+          pk[pr] = pack_bf16x2(pv.x, pv.y);
+        }
+        tmem_st16(tS + cc * 16, pk);
+        if (cc & 1) {   // a 64-key half of P is complete: hand it to the MMA warp now
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[i * 2 + (cc >> 1)]);
+        }
+      }
+      {
+        const float2 a = __fadd2_rn(__fadd2_rn(l4[0], l4[1]), __fadd2_rn(l4[2], l4[3]));
+        l += a.x + a.y;
+      }
+    }
+
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(&o_full[i], 0);
+    tc_fence_after();
+    const int row = q_row0 + i * BQ + quad * 32 + lane;
+    if (slice_slot >= 0 && p.split > 1) {
+      // one slice of the K/V stream: leave (O, m, l) for attn_merge_kernel
+      const long long prow = (long long)slice_slot * (2 * BQ) + i * BQ + quad * 32 + lane;
+      float4* dst = reinterpret_cast<float4*>(p.ws_o + prow * HD);
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tO + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          dst[cc * 8 + g] = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                        __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+      }
+      p.ws_ml[prow] = make_float2(m_cur, l);
+    } else {
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* orow = p.O + (long long)row * p.ldo + head * HD;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(tO + cc * 32, r);
+      tmem_ld_wait();
+      if (row < p.Lq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]) * inv_l;
+          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + g * 8);
+          if (p.accumulate) {
+            const uint4 old = *dst;
+            const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(ob[e]);
+              v[2 * e] += f.x;
+              v[2 * e + 1] += f.y;
+            }
+          }
+          uint4 pk;
+          pk.x = pack_bf16x2(v[0], v[1]);
+          pk.y = pack_bf16x2(v[2], v[3]);
+          pk.z = pack_bf16x2(v[4], v[5]);
+          pk.w = pack_bf16x2(v[6], v[7]);
+          *dst = pk;
+        }
+      }
+    }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace attn4
+}  // namespace svi
+
+namespace svi {
+namespace attn4 {
+
+constexpr size_t SLICE_BYTES = (size_t)2 * BQ * HD * 4 + (size_t)2 * BQ * 8;   // partial O + (m, l) of one slice
+constexpr int MAX_SPLIT = 8;
+constexpr int MIN_SLICE_TILES = 8;   // a slice shorter than this is dominated by its prologue / epilogue
+
+// Combines the slices of the sliced units: one warp per Q row (lane = 4 output columns), 8 rows per block.
+__global__ void __launch_bounds__(256)
+attn_merge_kernel(const float* __restrict__ ws_o, const float2* __restrict__ ws_ml, int split, int n_full, int n_qpairs,
+                  int Lq, __nv_bfloat16* __restrict__ O, long long ldo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x / (2 * BQ / 8);                       // sliced unit
+  const int r = (blockIdx.x % (2 * BQ / 8)) * 8 + warp;          // row inside the unit's 256
+  const int unit = n_full + t;
+  const int head = unit / n_qpairs;
+  const int row = (unit % n_qpairs) * (2 * BQ) + r;
+  if (row >= Lq) return;
+  float m = -INFINITY;
+  for (int s = 0; s < split; ++s) m = fmaxf(m, ws_ml[((long long)t * split + s) * (2 * BQ) + r].x);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float l = 0.f;
+  for (int s = 0; s < split; ++s) {
+    const long long prow = ((long long)t * split + s) * (2 * BQ) + r;
+    const float2 ml = ws_ml[prow];
+    const float w = ex2(ml.x - m);
+    const float4 o = __ldcs(reinterpret_cast<const float4*>(ws_o + prow * HD) + lane);
+    acc.x += o.x * w; acc.y += o.y * w; acc.z += o.z * w; acc.w += o.w * w;
+    l += ml.y * w;
+  }
+  const float inv = 1.0f / l;
+  uint2 pk;
+  pk.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+  pk.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+  *reinterpret_cast<uint2*>(O + (long long)row * ldo + head * HD + lane * 4) = pk;
+}
+
+// Launch plan: `units` equal CTAs on `sms` SMs cost ceil(units/sms) rounds.  Running r rounds of whole units and cutting
+// the remaining t units into S slices costs r + ceil(t*S/sms)/S rounds (+ a little for the merge).  Returns the cheapest
+// (n_full, split) that fits the workspace; (units, 1) when slicing does not pay.
+static void plan_split(int units, int n_kv, int sms, size_t ws_bytes, int* n_full, int* split) {
+  *n_full = units;
+  *split = 1;
+  if (ws_bytes < SLICE_BYTES || units <= 0) return;
+  const int rounds = units / sms;
+  double best = (double)((units + sms - 1) / sms);
+  const double need = best * 0.985;   // must save at least 1.5 %
+  for (int r = rounds; r >= 0 && r >= rounds - 1; --r) {
+    const int t = units - r * sms;
+    if (t <= 0) continue;
+    for (int S = 2; S <= MAX_SPLIT; ++S) {
+      if (n_kv / S < MIN_SLICE_TILES) break;
+      const long long slices = (long long)t * S;
+      if ((size_t)slices * SLICE_BYTES > ws_bytes) break;
+      const double cost = r + (double)((slices + sms - 1) / sms) / S + 0.04 * (double)t / sms + 0.01 * S;
+      if (cost < best && cost < need) {
+        best = cost;
+        *n_full = units - t;
+        *split = S;
+      }
+    }
+  }
+}
+
+int launch_attn4(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                       int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale, int32_t accumulate,
+                       const uint32_t* kv_flags, uint32_t kv_epoch, int kv_chunk_rows, int kv_self_chunk, void* workspace,
+                       size_t workspace_bytes, void* stream, const char* who) {
+  SVI_REQUIRE(Q && K && V && O, "%s: null pointer", who);
+  SVI_REQUIRE(Lq > 0 && Lk > 0 && num_heads > 0, "%s: Lq, Lk, num_heads must be positive", who);
+  const int64_t width = (int64_t)num_heads * HD;
+  SVI_REQUIRE(ldq >= width && ldk >= width && ldv >= width && ldo >= width,
+              "%s: leading dimensions must be >= num_heads*128", who);
+  SVI_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+              "%s: leading dimensions must be multiples of 8 elements", who);
+  SVI_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) |
+                reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(O)) & 15) == 0,
+              "%s: pointers must be 16-byte aligned", who);
+  CUtensorMap tq, tk, tv;
+  int rc = make_tmap_2d(&tq, Q, 2, (uint64_t)width, (uint64_t)Lq, (uint64_t)ldq * 2, 64, BQ);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tk, K, 2, (uint64_t)width, (uint64_t)Lk, (uint64_t)ldk * 2, 64, BKV);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tv, V, 2, (uint64_t)width, (uint64_t)Lk, (uint64_t)ldv * 2, 64, BKV);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          SMEM_BYTES);
+    if (ce != cudaSuccess) {
+      set_last_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(ce));
+      return SVI_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  Params p;
+  p.O = reinterpret_cast<__nv_bfloat16*>(O);
+  p.ldo = ldo;
+  p.Lq = Lq;
+  p.Lk = Lk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.accumulate = accumulate;
+  p.kv_flags = kv_flags;
+  p.kv_epoch = kv_epoch;
+  p.kv_chunk_rows = kv_chunk_rows;
+  p.kv_self_chunk = kv_self_chunk;
+  p.kv_first_tile = 0;
+  if (kv_flags) {
+    const int n_kv = (Lk + BKV - 1) / BKV;
+    const int first = (int)(((int64_t)kv_self_chunk * kv_chunk_rows + BKV - 1) / BKV);
+    p.kv_first_tile = first >= n_kv ? 0 : first;
+  }
+  p.n_qpairs = (Lq + 2 * BQ - 1) / (2 * BQ);
+  const int units = p.n_qpairs * num_heads;
+  const int sms = sm_count();
+  if (sms <= 0) return SVI_ERR_DRIVER;
+  SVI_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "%s: workspace must be 16-byte aligned", who);
+  plan_split(units, (Lk + BKV - 1) / BKV, sms, (workspace && !accumulate) ? workspace_bytes : 0, &p.n_full, &p.split);
+  const int n_sliced = units - p.n_full;
+  const long long slices = (long long)n_sliced * p.split;
+  p.ws_o = static_cast<float*>(workspace);
+  p.ws_ml = reinterpret_cast<float2*>(static_cast<char*>(workspace) + (size_t)slices * 2 * BQ * HD * 4);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  attn_fwd_kernel<<<(unsigned)(p.n_full + slices), NUM_THREADS, SMEM_BYTES, st>>>(tq, tk, tv, p);
+  SVI_CUDA_LAUNCH_CHECK(who);
+  if (p.split > 1) {
+    attn_merge_kernel<<<n_sliced * (2 * BQ / 8), 256, 0, st>>>(p.ws_o, p.ws_ml, p.split, p.n_full, p.n_qpairs, Lq, p.O, ldo);
+    SVI_CUDA_LAUNCH_CHECK(who);
+  }
+  return SVI_OK;
+}
+
+}  // namespace attn4
+}  // namespace svi
+
