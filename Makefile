@@ -17,6 +17,13 @@ $(LIB): $(OBJS)
 	@mkdir -p $(PKG)/lib
 	$(NVCC) -shared -o $@ $(OBJS) -cudart shared
 
+# experimental kernels (csrc/experimental/README.md): a separate library, never loaded by the package
+EXP_LIB := $(PKG)/lib/libsvi_b200_exp.so
+EXP_SRCS := $(CSRC)/runtime.cu $(CSRC)/experimental/attn4_tcgen05.cu $(CSRC)/experimental/exp_entry.cu
+exp:
+	@mkdir -p $(PKG)/lib build
+	$(NVCC) $(NVFLAGS) -shared -o $(EXP_LIB) $(EXP_SRCS) -cudart shared
+
 clean:
-	rm -rf build $(LIB)
-.PHONY: all clean
+	rm -rf build $(LIB) $(EXP_LIB)
+.PHONY: all clean exp

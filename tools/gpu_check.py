@@ -257,6 +257,38 @@ def sec_perf_gemm_epi():
         print(f"[PERF] gemm {name}: {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def sec_perf_attn4():
+    """EXPERIMENTAL (`make exp`): attention with one MMA-issuing warp per Q tile, correctness + timing against the product."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "stable-video-infinity_b200", "lib", "libsvi_b200_exp.so"))
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    lib.svi_exp_attn4.restype = i32
+    lib.svi_exp_attn4.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, ctypes.c_float, vp, ctypes.c_size_t, vp]
+    lib.svi_last_error.restype = ctypes.c_char_p
+
+    def attn4(q, k, v, out, H, scale):
+        rc = lib.svi_exp_attn4(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
+                               out.stride(0), q.shape[0], k.shape[0], H, scale, None, 0, torch.cuda.current_stream().cuda_stream)
+        if rc:
+            raise RuntimeError(lib.svi_last_error().decode())
+
+    g = torch.Generator(device="cpu").manual_seed(9)
+    scale = 128 ** -0.5
+    for (Lq, Lk, H) in [(256, 128, 1), (300, 333, 2), (3200, 3200, 3)]:
+        q, k, v = (torch.randn(L, H * 128, generator=g).to(dev, torch.bfloat16) for L in (Lq, Lk, Lk))
+        out = torch.full((Lq, H * 128), float("nan"), device=dev, dtype=torch.bfloat16)
+        attn4(q, k, v, out, H, scale)
+        torch.cuda.synchronize()
+        report(f"attn4 Lq={Lq} Lk={Lk} H={H}", out, attn_ref(q, k, v, H, scale), 2e-2)
+    L, H = 32760, 12
+    q, k, v = (torch.randn(L, H * 128, generator=g).to(dev, torch.bfloat16) for _ in range(3))
+    out = torch.empty(L, H * 128, device=dev, dtype=torch.bfloat16)
+    fl = 4.0 * L * L * H * 128
+    for name, fn in (("product", lambda: nv.attention(q, k, v, out, H, scale)), ("attn4 (2 MMA warps)", lambda: attn4(q, k, v, out, H, scale))):
+        ms = time_ms(fn, iters=5, warm=2)
+        print(f"[PERF] {name} L={L} H={H}: {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def sec_perf_ew():
     """Row kernels at the bench shape, algorithmic bytes / time (HBM roofline: MEASURED_PEAKS.json hbm_gbps)."""
     g = torch.Generator(device="cpu").manual_seed(8)
