@@ -3,7 +3,7 @@ NVCC ?= nvcc
 PKG := stable-video-infinity_b200
 CSRC := $(PKG)/csrc
 LIB := $(PKG)/lib/libsvi_b200.so
-NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --use_fast_math
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 SRCS := $(CSRC)/runtime.cu $(CSRC)/gemm_tcgen05.cu $(CSRC)/gemm2_tcgen05.cu $(CSRC)/attn_tcgen05.cu $(CSRC)/sp_exchange.cu $(CSRC)/elementwise.cu $(CSRC)/conv3d_tcgen05.cu $(CSRC)/vae_elementwise.cu $(CSRC)/encoder_kernels.cu
 OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 
@@ -24,6 +24,12 @@ exp:
 	@mkdir -p $(PKG)/lib build
 	$(NVCC) $(NVFLAGS) -shared -o $(EXP_LIB) $(EXP_SRCS) -cudart shared
 
+# A/B build with --use_fast_math (measurement only: SVI_B200_LIB=<this file> selects it; never the default)
+FM_LIB := $(PKG)/lib/libsvi_b200_fastmath.so
+fastmath:
+	@mkdir -p $(PKG)/lib build
+	$(NVCC) $(NVFLAGS) --use_fast_math -shared -o $(FM_LIB) $(SRCS) -cudart shared
+
 clean:
 	rm -rf build $(LIB) $(EXP_LIB)
-.PHONY: all clean exp
+.PHONY: all clean exp fastmath

@@ -83,6 +83,17 @@ int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const v
                  void* O, int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale,
                  int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
 size_t svi_attn_workspace_bytes(int32_t Lq, int32_t Lk, int32_t num_heads);
+/*
+ * svi_attn_fwd with the full-width RMSNorm of Q folded into the softmax scale: row r of Q is used as
+ * Q[r,:] * rsqrt(q_sumsq[r * q_ss_ld] / q_dim + q_eps), i.e. Q holds the UN-normalised projection and q_sumsq the row
+ * sums of squares the GEMM epilogue accumulated (svi_gemm_epilogue.sumsq).  The norm's per-channel weight commutes with
+ * the dot product and is applied to K by the caller (K' = K * w_q).  Replaces norm_q of CrossAttention.forward,
+ * wan_video_dit.py:272, without a pass over Q.
+ */
+int svi_attn_fwd_qscale(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                        void* O, int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale,
+                        int32_t accumulate, const float* q_sumsq, int32_t q_ss_ld, int32_t q_dim, float q_eps,
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* The launch plan svi_attn_fwd uses (pure host function, no device needed): `units` = num_heads * ceil(Lq/256) equal
  * CTAs, kv_tiles = ceil(Lk/128), on `sms` SMs with a workspace of workspace_bytes -> units [0, n_full) run whole, the
  * rest are cut into `split` K/V slices each (split == 1: nothing is sliced). */
@@ -129,6 +140,15 @@ int svi_layernorm_modulate(const float* x, int32_t M, int32_t D, float eps, cons
                            void* stream);
 
 /*
+ * Split-precision variant for the head GEMM's A operand: y[m, 0:D] = bf16(v), y[m, lo_col : lo_col + D] = bf16(v - bf16(v))
+ * (row pitch ldy elements).  Feeding the GEMM the two halves in two accumulating passes gives the A operand ~16 mantissa
+ * bits; used where a bf16 A operand is the dominant parity error and the GEMM is tiny.
+ */
+int svi_layernorm_modulate_split(const float* x, int32_t M, int32_t D, float eps, const float* gamma,
+                                 const float* beta, const float* scale, const float* shift, void* y_bf16,
+                                 int64_t ldy, int32_t lo_col, void* stream);
+
+/*
  * In place on bf16 rows t[m, 0:D] (leading dim ldt):  t = t * rsqrt(sumsq[m*sumsq_ld + sumsq_col]/D + eps) * w[:]
  * then, if rope_cos != NULL, the interleaved-pair rotation of every head (head_dim 128):
  *   (t[2i], t[2i+1]) <- (t[2i] c_i - t[2i+1] s_i,  t[2i] s_i + t[2i+1] c_i),  c,s = rope[(m + row_offset), i], i<64.
@@ -137,6 +157,12 @@ int svi_layernorm_modulate(const float* x, int32_t M, int32_t D, float eps, cons
 int svi_rmsnorm_rope(void* t_bf16, int64_t ldt, int32_t M, int32_t D, const float* sumsq,
                      int32_t sumsq_ld, int32_t sumsq_col, float eps, const float* w,
                      const float* rope_cos, const float* rope_sin, int32_t row_offset, void* stream);
+
+/* svi_rmsnorm_rope on q and k of the fused QKV buffer in ONE launch: row m holds q at [0, D) and k at [D, 2D);
+ * sumsq[m*sumsq_ld + 0] / [.. + 1] are their row sums of squares, wq / wk the norm weights (wan_video_dit.py:227-231). */
+int svi_qk_norm_rope(void* qk_bf16, int64_t ld, int32_t M, int32_t D, const float* sumsq, int32_t sumsq_ld,
+                     float eps, const float* wq, const float* wk, const float* rope_cos, const float* rope_sin,
+                     int32_t row_offset, void* stream);
 
 /*
  * Patchify gather (im2col of the k=s=(1,2,2) Conv3d): x f32 [C, F, H, W] -> tokens bf16 [L, Kpad],
@@ -147,6 +173,10 @@ int svi_rmsnorm_rope(void* t_bf16, int64_t ldt, int32_t M, int32_t D, const floa
  */
 int svi_patchify_gather(const float* x, int32_t C0, const float* y, int32_t C1, int32_t F, int32_t H,
                         int32_t W, void* tokens_bf16, int32_t Kpad, void* stream);
+
+/* Split-precision variant: tokens bf16 [L, 2*Kpad], columns [0, Kpad) = bf16(v), [Kpad, 2 Kpad) = bf16(v - bf16(v)). */
+int svi_patchify_gather_split(const float* x, int32_t C0, const float* y, int32_t C1, int32_t F, int32_t H,
+                              int32_t W, void* tokens_bf16, int32_t Kpad, void* stream);
 
 /*
  * Unpatchify scatter: head output f32 [L, ldh] (first 4*C columns = (dy, dx, c)) -> out f32 [C, F, H, W]
@@ -167,12 +197,20 @@ int svi_cfg_euler_step(float* latents, const float* v_cond, const float* v_uncon
 int svi_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 int svi_cast_bf16_to_f32(const void* src_bf16, float* dst, int64_t n, void* stream);
 
+/* dst[m, k] = bf16(v), dst[m, lo_col + k] = bf16(v - bf16(v)) with v = act(src[m, k]) (act: NONE | SILU | GELU_TANH |
+ * GELU_ERF): the two-term bf16 form of an f32 GEMM input (time / text / image embedding MLPs, wan_video_dit.py:429-452). */
+int svi_split_f32_to_bf16x2(const float* src, int64_t lds, int32_t M, int32_t K, int32_t act, void* dst_bf16,
+                            int64_t ldd, int32_t lo_col, void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (row-sum accumulators of a whole forward in one node). */
+int svi_zero(void* ptr, size_t bytes, void* stream);
+
 /* out[i] = act(in[i]) on f32 (SiLU in front of time_projection, wan_video_dit.py:441-442) -> bf16 */
 int svi_act_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, int32_t act, void* stream);
 
 /*
  * mod[j, :] = table[j, :] + t[:] (j < rows) — AdaLN modulation rows (wan_video_dit.py:356-357, 402).
- * table f32 [rows, D], t f32 [rows_t, D] with rows_t in {1, rows}; out f32 [rows, D].
+ * table f32 [rows, D], t f32 [rows_t, D] with rows % rows_t == 0 (row j uses t[j % rows_t]: one launch covers the
+ * modulation tables of all layers); out f32 [rows, D].
  */
 int svi_add_rows(const float* table, const float* t, int32_t rows, int32_t rows_t, int32_t D,
                  float* out, void* stream);

@@ -78,6 +78,11 @@ struct Params {
   int split;
   float* ws_o;               // [slices][256 rows][128] unnormalised partial O
   float2* ws_ml;             // [slices][256 rows] (row max in scaled log2 units, row sum)
+  // optional per-row RMS scale of Q (full-width RMSNorm folded into the softmax scale): row r of Q is used as
+  // Q[r] * rsqrt(q_sumsq[r * q_ss_ld] * q_inv_d + q_eps); nullptr: none
+  const float* q_sumsq;
+  int q_ss_ld;
+  float q_inv_d, q_eps;
 };
 
 // KV tile visited at iteration j: the stream starts on the rank's own rows and wraps around
@@ -260,7 +265,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + i * 128 + lane_sel;
     const uint32_t tO = tmem_base + 256 + i * 128 + lane_sel;
-    const float c = p.scale_log2;
+    float c = p.scale_log2;
+    if (p.q_sumsq) {          // this thread's Q row carries its RMSNorm factor in the softmax scale
+      const int qrow = min(q_row0 + i * BQ + quad * 32 + lane, p.Lq - 1);
+      c *= rsqrtf(__ldg(p.q_sumsq + (long long)qrow * p.q_ss_ld) * p.q_inv_d + p.q_eps);
+    }
     float m_cur = -INFINITY;  // running row max (scaled, log2 domain); reference point of P and O
     float l = 0.f;            // running row sum of P
 
@@ -479,10 +488,17 @@ static void plan_split(int units, int n_kv, int sms, size_t ws_bytes, int* n_ful
   }
 }
 
+struct QScale {
+  const float* sumsq = nullptr;
+  int ld = 0;
+  int dim = 1;
+  float eps = 0.f;
+};
+
 static int launch_attn(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                        int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale, int32_t accumulate,
                        const uint32_t* kv_flags, uint32_t kv_epoch, int kv_chunk_rows, int kv_self_chunk, void* workspace,
-                       size_t workspace_bytes, void* stream, const char* who) {
+                       size_t workspace_bytes, void* stream, const char* who, QScale qs = QScale()) {
   SVI_REQUIRE(Q && K && V && O, "%s: null pointer", who);
   SVI_REQUIRE(Lq > 0 && Lk > 0 && num_heads > 0, "%s: Lq, Lk, num_heads must be positive", who);
   const int64_t width = (int64_t)num_heads * HD;
@@ -522,6 +538,10 @@ static int launch_attn(const void* Q, int64_t ldq, const void* K, int64_t ldk, c
   p.kv_epoch = kv_epoch;
   p.kv_chunk_rows = kv_chunk_rows;
   p.kv_self_chunk = kv_self_chunk;
+  p.q_sumsq = qs.sumsq;
+  p.q_ss_ld = qs.ld;
+  p.q_inv_d = 1.0f / (float)qs.dim;
+  p.q_eps = qs.eps;
   p.kv_first_tile = 0;
   if (kv_flags) {
     const int n_kv = (Lk + BKV - 1) / BKV;
@@ -557,6 +577,21 @@ extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t l
                             size_t workspace_bytes, void* stream) {
   return svi::attn::launch_attn(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, num_heads, scale, accumulate, nullptr, 0, 1, 0,
                                 workspace, workspace_bytes, stream, "svi_attn_fwd");
+}
+
+extern "C" int svi_attn_fwd_qscale(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                                   void* O, int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale,
+                                   int32_t accumulate, const float* q_sumsq, int32_t q_ss_ld, int32_t q_dim, float q_eps,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace svi;
+  SVI_REQUIRE(q_sumsq && q_ss_ld >= 1 && q_dim >= 1, "svi_attn_fwd_qscale: need q_sumsq, q_ss_ld >= 1, q_dim >= 1");
+  svi::attn::QScale qs;
+  qs.sumsq = q_sumsq;
+  qs.ld = q_ss_ld;
+  qs.dim = q_dim;
+  qs.eps = q_eps;
+  return svi::attn::launch_attn(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, num_heads, scale, accumulate, nullptr, 0, 1, 0,
+                                workspace, workspace_bytes, stream, "svi_attn_fwd_qscale", qs);
 }
 
 extern "C" void svi_attn_plan(int32_t units, int32_t kv_tiles, int32_t sms, size_t workspace_bytes, int32_t* n_full,

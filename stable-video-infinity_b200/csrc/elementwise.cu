@@ -28,10 +28,13 @@ __device__ __forceinline__ float block_sum_128(float v, float* red /*[4]*/) {
 constexpr int LN_THREADS = 128;
 constexpr int LN_MAX_VEC = 16;  // float4 per thread -> D <= 8192
 
+// y_lo != nullptr: split output — y holds bf16(v), y_lo holds bf16(v - bf16(v)), so that y + y_lo carries ~16 mantissa
+// bits of v (the A operand of the head GEMM is fed as two bf16 passes).
 __global__ void __launch_bounds__(LN_THREADS)
 layernorm_modulate_kernel(const float* __restrict__ x, int D, float eps, const float* __restrict__ gamma,
                           const float* __restrict__ beta, const float* __restrict__ scale,
-                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ y) {
+                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, long long ldy,
+                          __nv_bfloat16* __restrict__ y_lo) {
   __shared__ float red[4];
   const long long row = blockIdx.x;
   const float4* xr = reinterpret_cast<const float4*>(x + row * D);
@@ -57,7 +60,8 @@ layernorm_modulate_kernel(const float* __restrict__ x, int D, float eps, const f
     }
   }
   const float rstd = rsqrtf(block_sum_128(q, red) / (float)D + eps);
-  uint2* yr = reinterpret_cast<uint2*>(y + row * D);
+  uint2* yr = reinterpret_cast<uint2*>(y + row * ldy);
+  uint2* yl = y_lo ? reinterpret_cast<uint2*>(y_lo + row * ldy) : nullptr;
 #pragma unroll
   for (int i = 0; i < LN_MAX_VEC; ++i) {
     const int idx = threadIdx.x + i * LN_THREADS;
@@ -84,6 +88,14 @@ layernorm_modulate_kernel(const float* __restrict__ x, int D, float eps, const f
       pk.x = pack_bf16x2(o[0], o[1]);
       pk.y = pack_bf16x2(o[2], o[3]);
       yr[idx] = pk;
+      if (yl) {
+        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&pk);
+        const float2 h0 = __bfloat1622float2(hb[0]), h1 = __bfloat1622float2(hb[1]);
+        uint2 lo;
+        lo.x = pack_bf16x2(o[0] - h0.x, o[1] - h0.y);
+        lo.y = pack_bf16x2(o[2] - h1.x, o[3] - h1.y);
+        yl[idx] = lo;
+      }
     }
   }
 }
@@ -160,23 +172,29 @@ layernorm_modulate_warp_kernel(const float* __restrict__ x, int M, int D, float 
 // full-width RMSNorm (row sum of squares supplied by the GEMM epilogue) + interleaved-pair RoPE,
 // in place on bf16.  One thread = 8 consecutive columns (4 rotation pairs).
 // ---------------------------------------------------------------------------------------------
+// groups == 2: the row holds two D-wide vectors side by side (q | k of the fused QKV buffer), normalised with
+// sumsq columns sumsq_col / sumsq_col + 1 and weights w / w2 — one launch instead of two.
 __global__ void __launch_bounds__(256)
-rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D,
+rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D, int groups,
                     const float* __restrict__ sumsq, int sumsq_ld, int sumsq_col, float eps,
-                    const float* __restrict__ w, const float* __restrict__ rope_cos,
+                    const float* __restrict__ w, const float* __restrict__ w2, const float* __restrict__ rope_cos,
                     const float* __restrict__ rope_sin, int row_offset) {
-  const int vec_per_row = D >> 3;
+  const int vec_per_row = (D >> 3) * groups;
   const long long total = (long long)M * vec_per_row;
+  const float inv_d = 1.0f / (float)D;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / vec_per_row);
-    const int c0 = (int)(i % vec_per_row) * 8;
-    const float rs = rsqrtf(sumsq[(long long)m * sumsq_ld + sumsq_col] / (float)D + eps);
-    uint4* ptr = reinterpret_cast<uint4*>(t + (long long)m * ldt + c0);
+    const int cc = (int)(i % vec_per_row) * 8;      // column inside the row (both groups)
+    const int grp = cc >= D ? 1 : 0;
+    const int c0 = cc - grp * D;                     // column inside the group
+    const float rs = rsqrtf(sumsq[(long long)m * sumsq_ld + sumsq_col + grp] * inv_d + eps);
+    uint4* ptr = reinterpret_cast<uint4*>(t + (long long)m * ldt + cc);
     const uint4 raw = *ptr;
     const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c0));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + c0 + 4));
+    const float* wg = grp ? w2 : w;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wg + c0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wg + c0 + 4));
     float v[8];
     {
       const float2 a = __bfloat1622float2(b2[0]), b = __bfloat1622float2(b2[1]),
@@ -210,9 +228,10 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D,
 // ---------------------------------------------------------------------------------------------
 // patchify gather / unpatchify scatter
 // ---------------------------------------------------------------------------------------------
+// split != 0: tok has 2*Kpad columns, [0, Kpad) = bf16(v), [Kpad, 2 Kpad) = bf16(v - bf16(v))
 __global__ void __launch_bounds__(256)
 patchify_gather_kernel(const float* __restrict__ x, int C0, const float* __restrict__ y, int C1, int F,
-                       int H, int W, __nv_bfloat16* __restrict__ tok, int Kpad) {
+                       int H, int W, __nv_bfloat16* __restrict__ tok, int Kpad, int split) {
   const int h2 = H >> 1, w2 = W >> 1;
   const long long L = (long long)F * h2 * w2;
   const int C = C0 + C1;
@@ -222,7 +241,7 @@ patchify_gather_kernel(const float* __restrict__ x, int C0, const float* __restr
        i += (long long)gridDim.x * blockDim.x) {
     const long long tokn = i % L;  // token fastest -> coalesced reads along w
     const int c = (int)(i / L);
-    uint2 pk = make_uint2(0u, 0u);
+    uint2 pk = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
     if (c < C) {
       const int f = (int)(tokn / (h2 * w2));
       const int rem = (int)(tokn % (h2 * w2));
@@ -233,8 +252,16 @@ patchify_gather_kernel(const float* __restrict__ x, int C0, const float* __restr
       const float2 r1 = *reinterpret_cast<const float2*>(p0 + W);
       pk.x = pack_bf16x2(r0.x, r0.y);
       pk.y = pack_bf16x2(r1.x, r1.y);
+      if (split) {
+        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&pk);
+        const float2 h0 = __bfloat1622float2(hb[0]), h1 = __bfloat1622float2(hb[1]);
+        lo.x = pack_bf16x2(r0.x - h0.x, r0.y - h0.y);
+        lo.y = pack_bf16x2(r1.x - h1.x, r1.y - h1.y);
+      }
     }
-    *reinterpret_cast<uint2*>(tok + tokn * Kpad + c * 4) = pk;
+    const long long ld = split ? 2LL * Kpad : Kpad;
+    *reinterpret_cast<uint2*>(tok + tokn * ld + c * 4) = pk;
+    if (split) *reinterpret_cast<uint2*>(tok + tokn * ld + Kpad + c * 4) = lo;
   }
 }
 
@@ -292,6 +319,21 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16*
     d[i] = __float2bfloat16_rn(v);
   }
 }
+// dst[m, k] = bf16(v), dst[m, lo_col + k] = bf16(v - bf16(v)), v = act(src[m, k])
+__global__ void split_f32_bf16x2_kernel(const float* __restrict__ s, long long lds, int M, int K, int act,
+                                        __nv_bfloat16* __restrict__ d, long long ldd, int lo_col) {
+  const long long n = (long long)M * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / K), k = (int)(i % K);
+    float v = s[(long long)m * lds + k];
+    if (act == SVI_ACT_SILU) v = silu(v);
+    else if (act == SVI_ACT_GELU_TANH) v = gelu_tanh(v);
+    else if (act == SVI_ACT_GELU_ERF) v = gelu_erf(v);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    d[(long long)m * ldd + k] = hi;
+    d[(long long)m * ldd + lo_col + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d,
                                      long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -304,7 +346,7 @@ __global__ void add_rows_kernel(const float* __restrict__ table, const float* __
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / D), c = (int)(i % D);
-    out[i] = table[i] + t[(rows_t == 1 ? 0 : (long long)r * D) + c];
+    out[i] = table[i] + t[(long long)(r % rows_t) * D + c];
   }
 }
 
@@ -341,8 +383,25 @@ extern "C" int svi_layernorm_modulate(const float* x, int32_t M, int32_t D, floa
     layernorm_modulate_warp_kernel<0><<<wgrid, LNW_WARPS * 32, 0, st>>>(x, M, D, eps, gamma, beta, scale, shift, yb);
   else
     layernorm_modulate_kernel<<<M, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, D, eps, gamma, beta, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16));
+        x, D, eps, gamma, beta, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16), D, nullptr);
   SVI_CUDA_LAUNCH_CHECK("svi_layernorm_modulate");
+  return SVI_OK;
+}
+
+extern "C" int svi_layernorm_modulate_split(const float* x, int32_t M, int32_t D, float eps, const float* gamma,
+                                            const float* beta, const float* scale, const float* shift,
+                                            void* y_bf16, int64_t ldy, int32_t lo_col, void* stream) {
+  SVI_REQUIRE(x && y_bf16, "svi_layernorm_modulate_split: null pointer");
+  SVI_REQUIRE(M > 0 && D > 0 && D % 8 == 0 && D <= 4 * LN_THREADS * LN_MAX_VEC,
+              "svi_layernorm_modulate_split: need M>0, D %% 8 == 0, D <= 8192 (M=%d D=%d)", M, D);
+  SVI_REQUIRE(lo_col >= D && lo_col % 4 == 0 && ldy >= (int64_t)lo_col + D && ldy % 4 == 0,
+              "svi_layernorm_modulate_split: need lo_col >= D, ldy >= lo_col + D, both multiples of 4");
+  SVI_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0,
+              "svi_layernorm_modulate_split: alignment");
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  layernorm_modulate_kernel<<<M, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, D, eps, gamma, beta, scale, shift,
+                                                                                    yb, ldy, yb + lo_col);
+  SVI_CUDA_LAUNCH_CHECK("svi_layernorm_modulate_split");
   return SVI_OK;
 }
 
@@ -359,9 +418,25 @@ extern "C" int svi_rmsnorm_rope(void* t_bf16, int64_t ldt, int32_t M, int32_t D,
               "svi_rmsnorm_rope: alignment");
   const long long total = (long long)M * (D / 8);
   rmsnorm_rope_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(t_bf16), ldt, M, D, sumsq, sumsq_ld, sumsq_col, eps, w, rope_cos,
+      reinterpret_cast<__nv_bfloat16*>(t_bf16), ldt, M, D, 1, sumsq, sumsq_ld, sumsq_col, eps, w, w, rope_cos,
       rope_sin, row_offset);
   SVI_CUDA_LAUNCH_CHECK("svi_rmsnorm_rope");
+  return SVI_OK;
+}
+
+extern "C" int svi_qk_norm_rope(void* qk_bf16, int64_t ld, int32_t M, int32_t D, const float* sumsq, int32_t sumsq_ld,
+                                float eps, const float* wq, const float* wk, const float* rope_cos,
+                                const float* rope_sin, int32_t row_offset, void* stream) {
+  SVI_REQUIRE(qk_bf16 && sumsq && wq && wk && rope_cos && rope_sin, "svi_qk_norm_rope: null pointer");
+  SVI_REQUIRE(M > 0 && D > 0 && D % 128 == 0 && ld >= 2 * (int64_t)D && ld % 8 == 0 && sumsq_ld >= 2,
+              "svi_qk_norm_rope: need D %% 128 == 0, ld %% 8 == 0, ld >= 2 D, sumsq_ld >= 2");
+  SVI_REQUIRE(((reinterpret_cast<uintptr_t>(qk_bf16) | reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(wk)) & 15) == 0,
+              "svi_qk_norm_rope: alignment");
+  const long long total = (long long)M * (D / 4);
+  rmsnorm_rope_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(qk_bf16), ld, M, D, 2, sumsq, sumsq_ld, 0, eps, wq, wk, rope_cos, rope_sin,
+      row_offset);
+  SVI_CUDA_LAUNCH_CHECK("svi_qk_norm_rope");
   return SVI_OK;
 }
 
@@ -373,8 +448,21 @@ extern "C" int svi_patchify_gather(const float* x, int32_t C0, const float* y, i
   SVI_REQUIRE(Kpad % 8 == 0 && Kpad >= 4 * (C0 + C1), "svi_patchify_gather: Kpad must be a multiple of 8 >= 4*C");
   const long long total = (long long)F * (H / 2) * (W / 2) * (Kpad / 4);
   patchify_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, C0, y, C1, F, H, W, reinterpret_cast<__nv_bfloat16*>(tokens_bf16), Kpad);
+      x, C0, y, C1, F, H, W, reinterpret_cast<__nv_bfloat16*>(tokens_bf16), Kpad, 0);
   SVI_CUDA_LAUNCH_CHECK("svi_patchify_gather");
+  return SVI_OK;
+}
+
+extern "C" int svi_patchify_gather_split(const float* x, int32_t C0, const float* y, int32_t C1, int32_t F, int32_t H,
+                                         int32_t W, void* tokens_bf16, int32_t Kpad, void* stream) {
+  SVI_REQUIRE(x && tokens_bf16, "svi_patchify_gather_split: null pointer");
+  SVI_REQUIRE(C0 > 0 && C1 >= 0 && (C1 == 0 || y), "svi_patchify_gather_split: bad channel split");
+  SVI_REQUIRE(F > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "svi_patchify_gather_split: H, W must be even");
+  SVI_REQUIRE(Kpad % 8 == 0 && Kpad >= 4 * (C0 + C1), "svi_patchify_gather_split: Kpad must be a multiple of 8 >= 4*C");
+  const long long total = (long long)F * (H / 2) * (W / 2) * (Kpad / 4);
+  patchify_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, C0, y, C1, F, H, W, reinterpret_cast<__nv_bfloat16*>(tokens_bf16), Kpad, 1);
+  SVI_CUDA_LAUNCH_CHECK("svi_patchify_gather_split");
   return SVI_OK;
 }
 
@@ -414,6 +502,25 @@ extern "C" int svi_act_f32_to_bf16(const float* src, void* dst, int64_t n, int32
   SVI_CUDA_LAUNCH_CHECK("svi_act_f32_to_bf16");
   return SVI_OK;
 }
+extern "C" int svi_split_f32_to_bf16x2(const float* src, int64_t lds, int32_t M, int32_t K, int32_t act, void* dst_bf16,
+                                       int64_t ldd, int32_t lo_col, void* stream) {
+  SVI_REQUIRE(src && dst_bf16 && M > 0 && K > 0, "svi_split_f32_to_bf16x2: null pointer / empty");
+  SVI_REQUIRE(act >= 0 && act <= 3, "svi_split_f32_to_bf16x2: unknown activation %d", act);
+  SVI_REQUIRE(lds >= K && lo_col >= K && ldd >= (int64_t)lo_col + K, "svi_split_f32_to_bf16x2: need lds >= K, lo_col >= K, ldd >= lo_col + K");
+  split_f32_bf16x2_kernel<<<grid_for((long long)M * K, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, lds, M, K, act, reinterpret_cast<__nv_bfloat16*>(dst_bf16), ldd, lo_col);
+  SVI_CUDA_LAUNCH_CHECK("svi_split_f32_to_bf16x2");
+  return SVI_OK;
+}
+extern "C" int svi_zero(void* ptr, size_t bytes, void* stream) {
+  SVI_REQUIRE(ptr && bytes > 0, "svi_zero: null pointer / empty");
+  cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    set_last_error("svi_zero: cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    return SVI_ERR_LAUNCH;
+  }
+  return SVI_OK;
+}
 extern "C" int svi_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
   SVI_REQUIRE(src && dst && n > 0, "svi_cast_bf16_to_f32: null pointer / empty");
   cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -434,7 +541,7 @@ extern "C" int svi_axpby(const float* a, float alpha, const float* b, float beta
 extern "C" int svi_add_rows(const float* table, const float* t, int32_t rows, int32_t rows_t, int32_t D,
                             float* out, void* stream) {
   SVI_REQUIRE(table && t && out, "svi_add_rows: null pointer");
-  SVI_REQUIRE(rows > 0 && D > 0 && (rows_t == 1 || rows_t == rows), "svi_add_rows: rows_t must be 1 or rows");
+  SVI_REQUIRE(rows > 0 && D > 0 && rows_t > 0 && rows % rows_t == 0, "svi_add_rows: rows must be a multiple of rows_t");
   add_rows_kernel<<<grid_for((long long)rows * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       table, t, rows, rows_t, D, out);
   SVI_CUDA_LAUNCH_CHECK("svi_add_rows");

@@ -85,6 +85,6 @@ int sm_count() {
 
 }  // namespace svi
 
-extern "C" int svi_abi_version(void) { return 2; }  // 2: attention workspace arguments, sp_*, encoder entry points
+extern "C" int svi_abi_version(void) { return 3; }  // 3: split-precision staging, q|k norm in one launch, attention with a per-row Q scale
 extern "C" const char* svi_last_error(void) { return svi::g_err; }
 extern "C" int svi_sm_count(void) { return svi::sm_count(); }

@@ -45,7 +45,7 @@ norm_act_kernel(const float* __restrict__ x, long long n_pix, int C, long long l
         }
         if (do_silu) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = o[j] / (1.f + __expf(-o[j]));
+          for (int j = 0; j < 4; ++j) o[j] = silu(o[j]);
         }
         uint2 pk;
         pk.x = pack_bf16x2(o[0], o[1]);

@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsvi_b200.so")
+# SVI_B200_LIB: another build of the same library (A/B measurements of compiler flags / kernel variants)
+_LIB_PATH = os.environ.get("SVI_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libsvi_b200.so")
 
 ACT_NONE, ACT_GELU_TANH, ACT_SILU, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3, 4
 
@@ -50,6 +51,8 @@ SIGNATURES = {
     "svi_gemm_bf16": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _c.POINTER(GemmEpilogue), _vp]),
     "svi_attn_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp, _c.c_size_t, _vp]),
     "svi_attn_workspace_bytes": (_c.c_size_t, [_i32, _i32, _i32]),
+    "svi_attn_fwd_qscale": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp, _i32, _i32, _f32,
+                                   _vp, _c.c_size_t, _vp]),
     "svi_attn_plan": (None, [_i32, _i32, _i32, _c.c_size_t, _c.POINTER(_i32), _c.POINTER(_i32)]),
     "svi_attn_fwd_sp": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _c.c_uint32, _i32, _i32, _vp, _c.c_size_t, _vp]),
     "svi_sp_alloc": (_i32, [_c.c_size_t, _c.POINTER(_vp), _c.c_char_p]),
@@ -58,7 +61,12 @@ SIGNATURES = {
     "svi_sp_close": (_i32, [_vp]),
     "svi_sp_push": (_i32, [_vp, _c.POINTER(_vp), _c.POINTER(_vp), _i32, _c.c_size_t, _vp, _vp]),
     "svi_layernorm_modulate": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "svi_layernorm_modulate_split": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "svi_rmsnorm_rope": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _i32, _vp]),
+    "svi_qk_norm_rope": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "svi_patchify_gather_split": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "svi_split_f32_to_bf16x2": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _vp]),
+    "svi_zero": (_i32, [_vp, _c.c_size_t, _vp]),
     "svi_patchify_gather": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "svi_unpatchify": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "svi_cfg_euler_step": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp]),
@@ -191,6 +199,23 @@ def attention(q, k, v, out, num_heads, scale=None, accumulate=False, workspace=N
     return out
 
 
+def attention_qscale(q, k, v, out, num_heads, q_sumsq, q_dim, q_eps, scale=None, accumulate=False, workspace=None):
+    """attention() on an UN-normalised q whose full-width RMSNorm factor rsqrt(q_sumsq[r] / q_dim + q_eps) is applied inside
+    the softmax (svi_attn_fwd_qscale); q_sumsq f32 [Lq, n] (column 0 is used)."""
+    ldq, ldk, ldv, ldo = (_rowmajor(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")))
+    if scale is None:
+        scale = 128 ** -0.5
+    if q_sumsq.shape[0] != q.shape[0]:
+        raise RuntimeError("svi_b200.attention_qscale: q_sumsq must have one row per query row")
+    rc = load().svi_attn_fwd_qscale(_ptr(q, torch.bfloat16, "q"), ldq, _ptr(k, torch.bfloat16, "k"), ldk,
+                                    _ptr(v, torch.bfloat16, "v"), ldv, _ptr(out, torch.bfloat16, "out"), ldo,
+                                    q.shape[0], k.shape[0], num_heads, float(scale), int(bool(accumulate)),
+                                    _ptr(q_sumsq, torch.float32, "q_sumsq"), _rowmajor(q_sumsq, "q_sumsq"), int(q_dim),
+                                    float(q_eps), *_workspace(workspace), _stream())
+    _check(rc, "svi_attn_fwd_qscale")
+    return out
+
+
 def _workspace(ws):
     if ws is None:
         return None, 0
@@ -277,6 +302,51 @@ def layernorm_modulate(x, out, eps, gamma=None, beta=None, scale=None, shift=Non
     return out
 
 
+def layernorm_modulate_split(x, out, eps, gamma=None, beta=None, scale=None, shift=None):
+    """out bf16 [M, 2D]: columns [0, D) = bf16(v), [D, 2D) = bf16(v - bf16(v)), v = layernorm_modulate(x)."""
+    M, D = x.shape
+    if not x.is_contiguous() or not out.is_contiguous() or tuple(out.shape) != (M, 2 * D):
+        raise RuntimeError("svi_b200.layernorm_modulate_split: x [M,D] and out [M,2D] must be contiguous")
+    rc = load().svi_layernorm_modulate_split(_ptr(x, torch.float32, "x"), M, D, float(eps),
+                                             _ptr(gamma, torch.float32, "gamma"), _ptr(beta, torch.float32, "beta"),
+                                             _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"),
+                                             _ptr(out, torch.bfloat16, "out"), 2 * D, D, _stream())
+    _check(rc, "svi_layernorm_modulate_split")
+    return out
+
+
+def qk_norm_rope(qk, sumsq, eps, wq, wk, rope_cos, rope_sin, row_offset=0):
+    """In place on bf16 qk[M, 2D] (q | k side by side, row-strided view allowed): RMSNorm + RoPE of both in one launch;
+    sumsq f32 [M, >=2] (columns 0, 1)."""
+    ld = _rowmajor(qk, "qk")
+    M, D2 = qk.shape
+    rc = load().svi_qk_norm_rope(_ptr(qk, torch.bfloat16, "qk"), ld, M, D2 // 2, _ptr(sumsq, torch.float32, "sumsq"),
+                                 _rowmajor(sumsq, "sumsq"), float(eps), _ptr(wq, torch.float32, "wq"),
+                                 _ptr(wk, torch.float32, "wk"), _ptr(rope_cos, torch.float32, "rope_cos"),
+                                 _ptr(rope_sin, torch.float32, "rope_sin"), row_offset, _stream())
+    _check(rc, "svi_qk_norm_rope")
+    return qk
+
+
+def split_f32_to_bf16x2(src, dst, act=ACT_NONE):
+    """dst bf16 [M, 2K] = [bf16(v) | bf16(v - bf16(v))], v = act(src f32 [M, K]) (row-strided views allowed)."""
+    M, K = src.shape
+    if tuple(dst.shape) != (M, 2 * K):
+        raise RuntimeError("svi_b200.split_f32_to_bf16x2: dst must be [M, 2K]")
+    rc = load().svi_split_f32_to_bf16x2(_ptr(src, torch.float32, "src"), _rowmajor(src, "src"), M, K, act,
+                                        _ptr(dst, torch.bfloat16, "dst"), _rowmajor(dst, "dst"), K, _stream())
+    _check(rc, "svi_split_f32_to_bf16x2")
+    return dst
+
+
+def zero_(t):
+    """t.zero_() as one cudaMemsetAsync node on the current stream (contiguous CUDA tensor)."""
+    if not t.is_cuda or not t.is_contiguous():
+        raise RuntimeError("svi_b200.zero_: contiguous CUDA tensor required (no CPU fallback)")
+    _check(load().svi_zero(_vp(t.data_ptr()), t.numel() * t.element_size(), _stream()), "svi_zero")
+    return t
+
+
 def rmsnorm_rope(t, sumsq, sumsq_col, eps, weight, rope_cos=None, rope_sin=None, row_offset=0):
     """In place on bf16 t[M, D] (row-strided view allowed): full-width RMSNorm + optional RoPE."""
     ldt = _rowmajor(t, "t")
@@ -289,14 +359,15 @@ def rmsnorm_rope(t, sumsq, sumsq_col, eps, weight, rope_cos=None, rope_sin=None,
     return t
 
 
-def patchify_gather(x, y, tokens):
-    """x f32 [C0,F,H,W] (+ y f32 [C1,F,H,W]) -> tokens bf16 [L, Kpad]."""
+def patchify_gather(x, y, tokens, split=False):
+    """x f32 [C0,F,H,W] (+ y f32 [C1,F,H,W]) -> tokens bf16 [L, Kpad]; split: tokens [L, 2 Kpad] = [hi | lo] two-term form."""
     C0, F, H, W = x.shape
     C1 = 0 if y is None else y.shape[0]
     if not x.is_contiguous() or (y is not None and not y.is_contiguous()) or not tokens.is_contiguous():
         raise RuntimeError("svi_b200.patchify_gather: tensors must be contiguous")
-    rc = load().svi_patchify_gather(_ptr(x, torch.float32, "x"), C0, _ptr(y, torch.float32, "y"), C1, F, H, W,
-                                    _ptr(tokens, torch.bfloat16, "tokens"), tokens.shape[1], _stream())
+    fn = load().svi_patchify_gather_split if split else load().svi_patchify_gather
+    rc = fn(_ptr(x, torch.float32, "x"), C0, _ptr(y, torch.float32, "y"), C1, F, H, W,
+            _ptr(tokens, torch.bfloat16, "tokens"), tokens.shape[1] // (2 if split else 1), _stream())
     _check(rc, "svi_patchify_gather")
     return tokens
 
@@ -338,6 +409,8 @@ def cast_bf16_to_f32(src, dst):
 
 def add_rows(table, t, out):
     rows, D = table.shape
+    if not (table.is_contiguous() and t.is_contiguous() and out.is_contiguous()) or rows % t.shape[0]:
+        raise RuntimeError("svi_b200.add_rows: contiguous tensors with rows % rows_t == 0 required")
     rc = load().svi_add_rows(_ptr(table, torch.float32, "table"), _ptr(t, torch.float32, "t"), rows, t.shape[0], D,
                              _ptr(out, torch.float32, "out"), _stream())
     _check(rc, "svi_add_rows")

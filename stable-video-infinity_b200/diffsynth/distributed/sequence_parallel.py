@@ -196,8 +196,11 @@ class SequenceParallelGroup:
             all_gather_inplace(full, self.local_slice(full), self.sp_group)
         return full
 
-    def cfg_parallel_step(self, eng, lat, t, cp, cn, v_c, v_u, cfg_scale, sigma, nxt, y=None):
-        """One denoise step under the plan above; lat is replicated on every rank and updated identically."""
+    def cfg_parallel_step(self, eng, lat, t, cp, cn, v_c, v_u, cfg_scale, sigma, nxt, y=None, tea=(None, None),
+                          add_condition=(None, None)):
+        """One denoise step under the plan above; lat is replicated on every rank and updated identically.
+        cp / cn: the conditional / unconditional ContextState (a CFG-parallel rank needs only its own branch's; the other
+        may be None); tea / add_condition: (conditional, unconditional) TeaCache objects and token-space conditions."""
         inner = self if self.sp_size > 1 else None
         if self.cfg_groups == 2:
             key = ("vpair", tuple(lat.shape))
@@ -205,14 +208,19 @@ class SequenceParallelGroup:
             if vp is None:
                 vp = torch.empty((2,) + tuple(lat.shape), device=lat.device, dtype=torch.float32)
                 self._bufs[key] = vp
-            eng.forward(lat, t, cp if self.cfg_idx == 0 else cn, y=y, sp=inner, out=vp[self.cfg_idx])
-            all_gather_inplace(vp, vp[self.cfg_idx], self.cfg_group)
+            b = self.cfg_idx
+            eng.forward(lat, t, cp if b == 0 else cn, y=y, sp=inner, out=vp[b], tea_cache=tea[b], add_condition=add_condition[b])
+            all_gather_inplace(vp, vp[b], self.cfg_group)
             eng.k.cfg_euler_step(lat, vp[0], vp[1], cfg_scale, sigma, nxt)
         else:
-            eng.forward(lat, t, cp, y=y, sp=inner, out=v_c)
-            eng.forward(lat, t, cn, y=y, sp=inner, out=v_u)
+            eng.forward(lat, t, cp, y=y, sp=inner, out=v_c, tea_cache=tea[0], add_condition=add_condition[0])
+            eng.forward(lat, t, cn, y=y, sp=inner, out=v_u, tea_cache=tea[1], add_condition=add_condition[1])
             eng.k.cfg_euler_step(lat, v_c, v_u, cfg_scale, sigma, nxt)
         return lat
+
+    def owns_branch(self, b):
+        """True when this rank computes CFG branch b (0 = conditional, 1 = unconditional) under the plan."""
+        return self.cfg_groups == 1 or self.cfg_idx == b
 
 
 def init_sp_groups(world=None, rank=None, cfg_parallel=True):
@@ -224,8 +232,12 @@ def init_sp_groups(world=None, rank=None, cfg_parallel=True):
 
 
 def get_sp_group():
+    """The process-wide plan behind `use_usp=True` (reference: xfuser's get_sp_group(), svi_video.py:266-273).  Default =
+    the measured plan: CFG-parallel x sequence-parallel for an even world size (N=2: cfg2 x sp1, N=8: cfg2 x sp4);
+    SVI_SP_PLAN=sp splits only the token axis (sp = N), like the reference."""
     if _GROUP is None:
         if not dist.is_initialized():
             raise RuntimeError("sequence parallelism requested but torch.distributed is not initialised")
-        return init_sp_groups(cfg_parallel=False)
+        import os
+        return init_sp_groups(cfg_parallel=os.environ.get("SVI_SP_PLAN", "cfg") != "sp")
     return _GROUP

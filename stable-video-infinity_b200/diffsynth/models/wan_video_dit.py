@@ -173,16 +173,17 @@ class _BlockWeights:
         self.w_ckv = _bf16(torch.cat([ca.k.weight, ca.v.weight], 0), device)
         self.b_ckv = _f32(torch.cat([ca.k.bias, ca.v.bias], 0), device)
         self.w_co, self.b_co = _bf16(ca.o.weight, device), _f32(ca.o.bias, device)
-        self.cnq, self.cnk = _f32(ca.norm_q.weight, device), _f32(ca.norm_k.weight, device)
+        # cross-attention q is never normalised in memory: its RMS factor rides in the attention's softmax scale
+        # (svi_attn_fwd_qscale) and norm_q's channel weight is folded into the (step-invariant) K:  q.w_q . k = q . (w_q k)
+        self.cnk_q = _f32(ca.norm_k.weight.detach().float() * ca.norm_q.weight.detach().float(), device)
         if ca.has_image_input:
             self.w_ckv_img = _bf16(torch.cat([ca.k_img.weight, ca.v_img.weight], 0), device)
             self.b_ckv_img = _f32(torch.cat([ca.k_img.bias, ca.v_img.bias], 0), device)
-            self.cnk_img = _f32(ca.norm_k_img.weight, device)
+            self.cnk_img_q = _f32(ca.norm_k_img.weight.detach().float() * ca.norm_q.weight.detach().float(), device)
         self.n3w, self.n3b = _f32(blk.norm3.weight, device), _f32(blk.norm3.bias, device)
         self.eps = blk.norm1.eps
         self.w_f0, self.b_f0 = _bf16(blk.ffn[0].weight, device), _f32(blk.ffn[0].bias, device)
         self.w_f2, self.b_f2 = _bf16(blk.ffn[2].weight, device), _f32(blk.ffn[2].bias, device)
-        self.mod = _f32(blk.modulation.reshape(6, blk.dim), device)
         if getattr(blk, "enable_multitalk", False):
             a = blk.audio_cross_attn
             self.w_aq, self.b_aq = _bf16(a.q_linear.weight, device), _f32(a.q_linear.bias, device)
@@ -202,6 +203,15 @@ class ContextState:
         self.kv_img_all = torch.empty(n_layers, 257, 2 * width, device=device, dtype=torch.bfloat16) if n_layers and n_img else None
         self.kv_txt = [] if self.kv_txt_all is None else list(self.kv_txt_all.unbind(0))     # per layer bf16 [n_txt, 2d]  (k normalised | v)
         self.kv_img = [] if self.kv_img_all is None else list(self.kv_img_all.unbind(0))     # per layer bf16 [257, 2d]
+
+
+class TimeState:
+    """Timestep conditioning of one forward: t f32 [1,d], t_mod f32 [6,d] and `mods` f32 [6*layers + 2, d] = every block's
+    modulation table + t_mod (rows 6i..6i+5: shift/scale/gate of self-attention, shift/scale/gate of the FFN;
+    wan_video_dit.py:356-357) followed by the head's shift/scale rows (:402)."""
+
+    def __init__(self, t, t_mod, mods):
+        self.t, self.t_mod, self.mods = t, t_mod, mods
 
 
 class AudioState:
@@ -273,6 +283,7 @@ class WanDiTEngine:
         self.w_tp, self.b_tp = _bf16(model.time_projection[1].weight, self.device), _f32(model.time_projection[1].bias, self.device)
         self.w_head, self.b_head = _bf16(model.head.head.weight, self.device), _f32(model.head.head.bias, self.device)
         self.head_mod = _f32(model.head.modulation.reshape(2, d), self.device)
+        self.mod_table = _f32(torch.cat([b.modulation.reshape(6, d) for b in model.blocks], 0), self.device)   # [6*layers, d]
         self.eps = model.head.norm.eps
         if model.has_image_input:
             p = model.img_emb.proj
@@ -314,24 +325,40 @@ class WanDiTEngine:
         return self._rope[key]
 
     # ------------------------------------------------------------------ conditioning
-    def time_state(self, timestep):
-        """t f32 [1,d] and t_mod f32 [6,d] for a scalar timestep (svi_video.py:90-91)."""
+    def _gemm_split(self, a2, w, out, bias=None, residual=None):
+        """out(f32) = [a_hi | a_lo] @ w^T (+ bias) (+ residual) as two accumulating passes over the same weights: the A operand
+        enters with ~16 mantissa bits instead of bf16's 8.  Used for the GEMMs whose bf16 A operand dominated the parity
+        error at negligible cost (embedding MLPs, patch embedding, head; tools/rounding_study.py)."""
+        K = w.shape[1]
+        self.k.gemm(a2[:, :K], w, out, bias=bias, residual=residual)
+        self.k.gemm(a2[:, K:], w, out, residual=out)
+        return out
+
+    def time_state(self, timestep) -> TimeState:
+        """TimeState of a scalar timestep (svi_video.py:90-91): time MLP and time projection in split precision, then the
+        modulation rows of every block and of the head in one launch each.  Cached per timestep value (both CFG branches
+        and every clip of a video use the same 50 values)."""
         tv = float(timestep.reshape(-1)[0]) if isinstance(timestep, torch.Tensor) else float(timestep)
         hit = self._time_cache.get(tv)
         if hit is not None:
             return hit
-        d = self.dim
-        te = sinusoidal_embedding_1d(self.model.freq_dim, torch.tensor([tv], dtype=torch.float64))
-        te = te.to(torch.bfloat16).to(self.device)
-        th = torch.empty(1, d, device=self.device, dtype=torch.bfloat16)
-        t = torch.empty(1, d, device=self.device, dtype=torch.float32)
-        ts = torch.empty(1, d, device=self.device, dtype=torch.bfloat16)
-        t_mod = torch.empty(1, 6 * d, device=self.device, dtype=torch.float32)
-        self.k.gemm(te, self.w_t0, th, bias=self.b_t0, act=nv.ACT_SILU)
-        self.k.gemm(th, self.w_t2, t, bias=self.b_t2)
-        self.k.cast_f32_to_bf16(t, ts, act=nv.ACT_SILU)
-        self.k.gemm(ts, self.w_tp, t_mod, bias=self.b_tp)
-        out = (t, t_mod.view(6, d))
+        d, dev, nl = self.dim, self.device, len(self.blocks)
+        fd = self.model.freq_dim
+        te = sinusoidal_embedding_1d(fd, torch.tensor([tv], dtype=torch.float64)).to(torch.float32).to(dev)
+        te2 = torch.empty(1, 2 * fd, device=dev, dtype=torch.bfloat16)
+        th, t = (torch.empty(1, d, device=dev, dtype=torch.float32) for _ in range(2))
+        th2, ts2 = (torch.empty(1, 2 * d, device=dev, dtype=torch.bfloat16) for _ in range(2))
+        t_mod = torch.empty(1, 6 * d, device=dev, dtype=torch.float32)
+        mods = torch.empty(6 * nl + 2, d, device=dev, dtype=torch.float32)
+        self.k.split_f32_to_bf16x2(te, te2)
+        self._gemm_split(te2, self.w_t0, th, bias=self.b_t0)
+        self.k.split_f32_to_bf16x2(th, th2, act=nv.ACT_SILU)
+        self._gemm_split(th2, self.w_t2, t, bias=self.b_t2)
+        self.k.split_f32_to_bf16x2(t, ts2, act=nv.ACT_SILU)
+        self._gemm_split(ts2, self.w_tp, t_mod, bias=self.b_tp)
+        self.k.add_rows(self.mod_table, t_mod.view(6, d), mods[:6 * nl])
+        self.k.add_rows(self.head_mod, t, mods[6 * nl:])
+        out = TimeState(t, t_mod.view(6, d), mods)
         self._time_cache[tv] = out
         while len(self._time_cache) > 256:
             self._time_cache.popitem(last=False)
@@ -347,45 +374,60 @@ class WanDiTEngine:
             return hit[2]
         d, dev = self.dim, self.device
         ctx_in = context.reshape(-1, context.shape[-1])
-        n_txt = ctx_in.shape[0]
-        if ctx_in.dtype != torch.bfloat16:
-            src = ctx_in.to(device=dev, dtype=torch.float32).contiguous()
-            ctx_bf = torch.empty(src.shape, device=dev, dtype=torch.bfloat16)
-            self.k.cast_f32_to_bf16(src, ctx_bf)
-        else:
-            ctx_bf = ctx_in.to(dev).contiguous()
+        n_txt, td = ctx_in.shape
+        # text MLP (wan_video_dit.py:433-437) in split precision: f32 rows -> [hi | lo] bf16 pairs -> two-pass GEMMs
+        src = ctx_in.to(device=dev, dtype=torch.float32).contiguous()
+        c2 = torch.empty(n_txt, 2 * td, device=dev, dtype=torch.bfloat16)
+        self.k.split_f32_to_bf16x2(src, c2)
         n_img = 257 if self.model.has_image_input else 0
         emb = torch.empty(n_img + n_txt, d, device=dev, dtype=torch.bfloat16)
-        hid = torch.empty(n_txt, d, device=dev, dtype=torch.bfloat16)
-        self.k.gemm(ctx_bf, self.w_te0, hid, bias=self.b_te0, act=nv.ACT_GELU_TANH)
-        self.k.gemm(hid, self.w_te2, emb[n_img:], bias=self.b_te2)
+        hid = torch.empty(n_txt, d, device=dev, dtype=torch.float32)
+        hid2 = torch.empty(n_txt, 2 * d, device=dev, dtype=torch.bfloat16)
+        e32 = torch.empty(n_txt, d, device=dev, dtype=torch.float32)
+        self._gemm_split(c2, self.w_te0, hid, bias=self.b_te0)
+        self.k.split_f32_to_bf16x2(hid, hid2, act=nv.ACT_GELU_TANH)
+        self._gemm_split(hid2, self.w_te2, e32, bias=self.b_te2)
+        self.k.cast_f32_to_bf16(e32, emb[n_img:])
         if n_img:
             if clip_feature is None:
                 raise RuntimeError("has_image_input model needs clip_feature")
             cf = clip_feature.reshape(-1, clip_feature.shape[-1]).to(device=dev, dtype=torch.float32).contiguous()
             if cf.shape[0] != 257:
                 raise RuntimeError(f"clip_feature must have 257 tokens, got {cf.shape[0]}")
-            c0 = torch.empty(257, 1280, device=dev, dtype=torch.bfloat16)
-            c1 = torch.empty(257, 1280, device=dev, dtype=torch.bfloat16)
-            c2 = torch.empty(257, d, device=dev, dtype=torch.float32)
-            self.k.layernorm_modulate(cf, c0, self.ie_ln0[2], gamma=self.ie_ln0[0], beta=self.ie_ln0[1])
-            self.k.gemm(c0, self.ie_w1, c1, bias=self.ie_b1, act=nv.ACT_GELU_ERF)
-            self.k.gemm(c1, self.ie_w3, c2, bias=self.ie_b3)
-            self.k.layernorm_modulate(c2, emb[:257], self.ie_ln4[2], gamma=self.ie_ln4[0], beta=self.ie_ln4[1])
-        st = ContextState(n_img, n_txt, len(self.blocks), d, dev)
-        for li, bw in enumerate(self.blocks):
-            kv = st.kv_txt[li]
-            ss = torch.zeros(n_txt, 1, device=dev, dtype=torch.float32)
-            self.k.gemm(emb[n_img:], bw.w_ckv, kv, bias=bw.b_ckv, sumsq=ss, sumsq_group_cols=d)
-            self.k.rmsnorm_rope(kv[:, :d], ss, 0, bw.eps_qk, bw.cnk)
-            if n_img:
-                kvi = st.kv_img[li]
-                ssi = torch.zeros(257, 1, device=dev, dtype=torch.float32)
-                self.k.gemm(emb[:257], bw.w_ckv_img, kvi, bias=bw.b_ckv_img, sumsq=ssi, sumsq_group_cols=d)
-                self.k.rmsnorm_rope(kvi[:, :d], ssi, 0, bw.eps_qk, bw.cnk_img)
+            cw = cf.shape[1]
+            c0 = torch.empty(257, 2 * cw, device=dev, dtype=torch.bfloat16)
+            c1 = torch.empty(257, cw, device=dev, dtype=torch.float32)
+            c1s = torch.empty(257, 2 * cw, device=dev, dtype=torch.bfloat16)
+            c3 = torch.empty(257, d, device=dev, dtype=torch.float32)
+            self.k.layernorm_modulate_split(cf, c0, self.ie_ln0[2], gamma=self.ie_ln0[0], beta=self.ie_ln0[1])
+            self._gemm_split(c0, self.ie_w1, c1, bias=self.ie_b1)
+            self.k.split_f32_to_bf16x2(c1, c1s, act=nv.ACT_GELU_ERF)
+            self._gemm_split(c1s, self.ie_w3, c3, bias=self.ie_b3)
+            self.k.layernorm_modulate(c3, emb[:257], self.ie_ln4[2], gamma=self.ie_ln4[0], beta=self.ie_ln4[1])
+        st = self.project_context(emb, n_img)
         self._ctx_cache[key] = (weakref.ref(context), None if clip_feature is None else weakref.ref(clip_feature), st)
         while len(self._ctx_cache) > 8:
             self._ctx_cache.popitem(last=False)
+        return st
+
+    def project_context(self, emb, n_img=0) -> ContextState:
+        """Every layer's cross-attention K|V from EMBEDDED context rows (bf16 [n_img + n_txt, d]; image rows first):
+        K = RMSNorm(k) * (w_k * w_q) — see _BlockWeights — and V, both bf16 (wan_video_dit.py:273-274, 296-299)."""
+        d, dev = self.dim, self.device
+        n_txt = emb.shape[0] - n_img
+        st = ContextState(n_img, n_txt, len(self.blocks), d, dev)
+        ss = torch.empty(len(self.blocks), 2, max(n_txt, 257), device=dev, dtype=torch.float32)
+        self.k.zero_(ss)
+        for li, bw in enumerate(self.blocks):
+            kv = st.kv_txt[li]
+            sl = ss[li, 0, :n_txt].unsqueeze(1)
+            self.k.gemm(emb[n_img:], bw.w_ckv, kv, bias=bw.b_ckv, sumsq=sl, sumsq_group_cols=d)
+            self.k.rmsnorm_rope(kv[:, :d], sl, 0, bw.eps_qk, bw.cnk_q)       # K * rms * (w_k * w_q): see _BlockWeights
+            if n_img:
+                kvi = st.kv_img[li]
+                si = ss[li, 1, :257].unsqueeze(1)
+                self.k.gemm(emb[:257], bw.w_ckv_img, kvi, bias=bw.b_ckv_img, sumsq=si, sumsq_group_cols=d)
+                self.k.rmsnorm_rope(kvi[:, :d], si, 0, bw.eps_qk, bw.cnk_img_q)
         return st
 
     def audio_state(self, audio_embed_tuple) -> AudioState:
@@ -422,25 +464,33 @@ class WanDiTEngine:
         return self._buf("attn_ws", ((n + 3) // 4,), torch.float32)
 
     # ------------------------------------------------------------------ block stack
-    def run_block(self, i, x, t_mod, ctx: ContextState, cos, sin, sp=None, audio: Optional[AudioState] = None):
-        """x f32 [L,d] updated in place.  Reference DiTBlock.forward wan_video_dit.py:354-374."""
+    def _row_sums(self, L):
+        """f32 [layers, 3*L] accumulators of the GEMM epilogues' row sums of squares for one forward (per layer: q | k of
+        self-attention, q of cross-attention), zeroed by ONE memset node at the start of the forward."""
+        return self._buf("row_sums", (len(self.blocks), 3 * L), torch.float32)
+
+    def run_block(self, i, x, mods, ctx: ContextState, cos, sin, sp=None, audio: Optional[AudioState] = None, row_sums=None):
+        """x f32 [L,d] updated in place.  Reference DiTBlock.forward wan_video_dit.py:354-374.  `mods`: TimeState.mods (or
+        any f32 [>= 6*(i+1), d] table whose rows 6i..6i+5 are this block's shift/scale/gate rows); `row_sums`: this
+        forward's zeroed _row_sums buffer (None: a private one is zeroed here — single-block callers)."""
         bw = self.blocks[i]
         L, d, H = x.shape[0], self.dim, self.H
-        mod = self._buf("mod6", (6, d), torch.float32)
+        mod = mods[6 * i: 6 * i + 6]
         h = self._buf("h", (L, d), torch.bfloat16)
         qkv = self._buf("qkv", (L, 3 * d), torch.bfloat16)
         att = self._buf("att", (L, d), torch.bfloat16)
-        ss = self._buf("ss", (L, 2), torch.float32)
         ffn = self._buf("ffn", (L, bw.w_f0.shape[0]), torch.bfloat16)
-        self.k.add_rows(bw.mod, t_mod, mod)
+        if row_sums is None:
+            row_sums = self._row_sums(L)
+            self.k.zero_(row_sums[i])
+        rs = row_sums[i]
         # --- self attention
         self.k.layernorm_modulate(x, h, bw.eps, scale=mod[1], shift=mod[0])
         ev = self.attn_events
         if sp is None:
-            ss.zero_()
+            ss = rs[:2 * L].view(L, 2)
             self.k.gemm(h, bw.w_qkv, qkv, bias=bw.b_qkv, sumsq=ss, sumsq_group_cols=d)
-            self.k.rmsnorm_rope(qkv[:, :d], ss, 0, bw.eps_qk, bw.nq, cos, sin, 0)
-            self.k.rmsnorm_rope(qkv[:, d:2 * d], ss, 1, bw.eps_qk, bw.nk, cos, sin, 0)
+            self.k.qk_norm_rope(qkv[:, :2 * d], ss, bw.eps_qk, bw.nq, bw.nk, cos, sin, 0)
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
         else:
             # sequence parallel: q for the local rows; K|V written straight into this rank's rows of the full
@@ -455,10 +505,7 @@ class WanDiTEngine:
             else:
                 kvf = self._buf("kv_full", (L * sp.sp_size, 2 * d), torch.bfloat16)
                 kvl = kvf[sp.sp_rank * L:(sp.sp_rank + 1) * L]
-            ssq = self._buf("ssq", (L, 1), torch.float32)
-            ssk = self._buf("ssk", (L, 1), torch.float32)
-            ssq.zero_()
-            ssk.zero_()
+            ssq, ssk = rs[:L].view(L, 1), rs[L:2 * L].view(L, 1)
             self.k.gemm(h, bw.w_kv, kvl, bias=bw.b_kv, sumsq=ssk, sumsq_group_cols=d)
             self.k.rmsnorm_rope(kvl[:, :d], ssk, 0, bw.eps_qk, bw.nk, cos, sin, sp.sp_rank * L)
             if pe is not None:
@@ -481,18 +528,17 @@ class WanDiTEngine:
             e1.record()
             ev.append((e0, e1))
         self.k.gemm(att, bw.w_o, x, bias=bw.b_o, gate=mod[2], residual=x)
-        # --- cross attention
+        # --- cross attention: q stays un-normalised in memory; its RMS factor is applied inside the softmax and norm_q's
+        #     weight already sits in the context K (context_state)
         self.k.layernorm_modulate(x, h, bw.eps, gamma=bw.n3w, beta=bw.n3b)
         cq = qkv[:, :d]
-        ss1 = self._buf("ss1", (L, 1), torch.float32)
-        ss1.zero_()
+        ss1 = rs[2 * L:].view(L, 1)
         self.k.gemm(h, bw.w_cq, cq, bias=bw.b_cq, sumsq=ss1, sumsq_group_cols=d)
-        self.k.rmsnorm_rope(cq, ss1, 0, bw.eps_qk, bw.cnq)
         kv = ctx.kv_txt[i]
-        self.k.attention(cq, kv[:, :d], kv[:, d:], att, H)
+        self.k.attention_qscale(cq, kv[:, :d], kv[:, d:], att, H, ss1, d, bw.eps_qk)
         if ctx.n_img:
             kvi = ctx.kv_img[i]
-            self.k.attention(cq, kvi[:, :d], kvi[:, d:], att, H, accumulate=True)
+            self.k.attention_qscale(cq, kvi[:, :d], kvi[:, d:], att, H, ss1, d, bw.eps_qk, accumulate=True)
         self.k.gemm(att, bw.w_co, x, bias=bw.b_co, residual=x)
         # --- audio cross-attention (SVI-Talk, wan_video_dit.py:361-366): tokens of latent frame f attend to that frame's
         #     audio tokens (models/attention.py:318-371); 1/sqrt(head_dim) scale, no q/k norm
@@ -539,7 +585,7 @@ class WanDiTEngine:
             raise RuntimeError("svi_b200: channel count does not match patch_embedding")
         hh, ww = Hl // 2, Wl // 2
         L = f * hh * ww
-        t, t_mod = self.time_state(timestep)
+        ts = self.time_state(timestep)
         ctx = context if isinstance(context, ContextState) else self.context_state(context, clip_feature)
         cos, sin = self.rope(f, hh, ww)
         nh = self.w_head.shape[0]
@@ -552,38 +598,38 @@ class WanDiTEngine:
                 raise RuntimeError(f"svi_b200: {audio.n_frames} audio frames for {f} latent frames")
         if (self.use_graphs and sp is None and tea_cache is None and add_condition is None and audio is None
                 and self.attn_events is None and self.k.events is None and out.is_contiguous()):
-            return self._graph_forward(xs, ys, t, t_mod, ctx, cos, sin, out)
-        return self._run(xs, ys, t, t_mod, ctx, cos, sin, out, sp, tea_cache, add_condition, audio)
+            return self._graph_forward(xs, ys, ts, ctx, cos, sin, out)
+        return self._run(xs, ys, ts, ctx, cos, sin, out, sp, tea_cache, add_condition, audio)
 
     # ------------------------------------------------------------------ CUDA-graph replay (single GPU)
-    def _graph_forward(self, xs, ys, t, t_mod, ctx, cos, sin, out):
+    def _graph_forward(self, xs, ys, ts, ctx, cos, sin, out):
         """The whole forward is ~460 launches of fixed shape: after one eager call per input geometry it is captured into a
         CUDA graph that reads fixed copies of (latents, y, t, t_mod, cross-attention K|V) and writes a fixed output, so a
         step costs a handful of small copies + one replay on the host instead of ~15 ms of Python per forward
-        (`host_enqueue_ms_per_step` in bench.py).  Sequence-parallel, TeaCache and timing modes stay eager."""
+        (`host_enqueue_ms_per_step` in bench.py).  TeaCache and timing modes stay eager; sequence-parallel ranks have their
+        own capture (`_graph_forward_sp`)."""
         key = (tuple(xs.shape), None if ys is None else tuple(ys.shape), ctx.n_txt, ctx.n_img)
         ent = self._graphs.get(key)
         if ent is None:                       # first call of this geometry: eager (allocates every work buffer)
             self._graphs[key] = {"graph": None}
-            return self._run(xs, ys, t, t_mod, ctx, cos, sin, out, None, None, None, None)
+            return self._run(xs, ys, ts, ctx, cos, sin, out, None, None, None, None)
         if ent["graph"] is None:
             st = ContextState(ctx.n_img, ctx.n_txt, len(self.blocks), self.dim, self.device)
-            ent.update(xs=torch.empty_like(xs), ys=None if ys is None else torch.empty_like(ys), t=torch.empty_like(t),
-                       t_mod=torch.empty_like(t_mod), ctx=st, out=torch.empty_like(out))
+            ent.update(xs=torch.empty_like(xs), ys=None if ys is None else torch.empty_like(ys),
+                       ts=TimeState(None, None, torch.empty_like(ts.mods)), ctx=st, out=torch.empty_like(out))
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             n0 = self.k.launches
             # thread_local: other threads (NCCL watchdog, the bench's clock sampler) may keep calling the CUDA runtime
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._run(ent["xs"], ent["ys"], ent["t"], ent["t_mod"], st, cos, sin, ent["out"], None, None, None, None)
+                self._run(ent["xs"], ent["ys"], ent["ts"], st, cos, sin, ent["out"], None, None, None, None)
             ent["launches"] = self.k.launches - n0
             self.k.launches = n0               # recorded, not executed
             ent["graph"] = g
         ent["xs"].copy_(xs)
         if ys is not None:
             ent["ys"].copy_(ys)
-        ent["t"].copy_(t)
-        ent["t_mod"].copy_(t_mod)
+        ent["ts"].mods.copy_(ts.mods)
         ent["ctx"].kv_txt_all.copy_(ctx.kv_txt_all)
         if ctx.n_img:
             ent["ctx"].kv_img_all.copy_(ctx.kv_img_all)
@@ -592,16 +638,19 @@ class WanDiTEngine:
         out.copy_(ent["out"])
         return out
 
-    def _run(self, xs, ys, t, t_mod, ctx, cos, sin, out, sp, tea_cache, add_condition, audio=None):
+    def _run(self, xs, ys, ts, ctx, cos, sin, out, sp, tea_cache, add_condition, audio=None):
         """Device work of one forward on prepared inputs (everything here is stream-ordered and allocation-free after the
         first call of a geometry, so it can be captured)."""
         dev, d = self.device, self.dim
         C0, f, Hl, Wl = xs.shape
         hh, ww = Hl // 2, Wl // 2
         L = f * hh * ww
-        # patchify: im2col gather + GEMM (Conv3d k=s=(1,2,2), wan_video_dit.py:473-477)
-        tok = self._buf("tok", (L, self.kpatch), torch.bfloat16)
-        self.k.patchify_gather(xs, ys, tok)
+        # patchify: im2col gather + GEMM (Conv3d k=s=(1,2,2), wan_video_dit.py:473-477); the latents enter as [hi | lo] bf16
+        # pairs (two accumulating GEMM passes over K = 4*C columns each): a plain bf16 cast of the latents alone put
+        # 5e-4 of the output std of error on every velocity prediction (tools/rounding_study.py)
+        kp = self.kpatch
+        tok = self._buf("tok", (L, 2 * kp), torch.bfloat16)
+        self.k.patchify_gather(xs, ys, tok, split=True)
         if sp is None:
             Ll, tok_l = L, tok
         else:
@@ -609,30 +658,30 @@ class WanDiTEngine:
             Ll = sp.local_rows(L)
             tok_l = tok[sp.row_offset: sp.row_offset + Ll]
         xr = self._buf("x", (Ll, d), torch.float32)
-        if add_condition is None:
-            self.k.gemm(tok_l, self.w_patch, xr, bias=self.b_patch)
-        else:
+        cond_l = None
+        if add_condition is not None:
             if tuple(add_condition.shape) != (1, L, d):
                 raise RuntimeError(f"svi_b200: add_condition must be [1, {L}, {d}], got {tuple(add_condition.shape)}")
             cond = add_condition[0].to(device=dev, dtype=torch.float32).contiguous()
             cond_l = cond if sp is None else cond[sp.row_offset: sp.row_offset + Ll]
-            self.k.gemm(tok_l, self.w_patch, xr, bias=self.b_patch, residual=cond_l)     # x = add_condition + patchify(x)
-        if tea_cache is not None and tea_cache.check(self.model, xr, t_mod):
+        self._gemm_split(tok_l, self.w_patch, xr, bias=self.b_patch, residual=cond_l)     # x = [add_condition +] patchify(x)
+        nl = len(self.blocks)
+        if tea_cache is not None and tea_cache.check(self.model, xr, ts.t_mod):
             tea_cache.update(xr)                      # skipped step: tokens + residual of the last computed step
         else:
-            for i in range(len(self.blocks)):
-                self.run_block(i, xr, t_mod, ctx, cos, sin, sp, audio)
+            row_sums = self._row_sums(Ll)
+            self.k.zero_(row_sums)
+            for i in range(nl):
+                self.run_block(i, xr, ts.mods, ctx, cos, sin, sp, audio, row_sums)
             if tea_cache is not None:
                 tea_cache.store(xr)
-        # head (wan_video_dit.py:401-404) + unpatchify (:479-484)
-        mod2 = self._buf("mod2", (2, d), torch.float32)
-        self.k.add_rows(self.head_mod, t, mod2)
-        h = self._buf("h", (Ll, d), torch.bfloat16)
-        self.k.layernorm_modulate(xr, h, self.eps, scale=mod2[1], shift=mod2[0])
+        # head (wan_video_dit.py:401-404) + unpatchify (:479-484); the normalised tokens enter the head GEMM as [hi | lo]
+        h2 = self._buf("h_split", (Ll, 2 * d), torch.bfloat16)
+        self.k.layernorm_modulate_split(xr, h2, self.eps, scale=ts.mods[6 * nl + 1], shift=ts.mods[6 * nl])
         nh = self.w_head.shape[0]
         ho = self._buf("head_out", (L, nh), torch.float32)
         ho_l = ho if sp is None else ho[sp.row_offset: sp.row_offset + Ll]
-        self.k.gemm(h, self.w_head, ho_l, bias=self.b_head)
+        self._gemm_split(h2, self.w_head, ho_l, bias=self.b_head)
         if sp is not None:
             sp.all_gather_rows(ho)
         self.k.unpatchify(ho, out[0])
@@ -669,14 +718,30 @@ class WanModel(nn.Module):
             self.audio_proj = AudioProjModel(seq_len=5, seq_len_vf=8, intermediate_dim=512, output_dim=768, context_tokens=32,
                                              norm_output_audio=True)
         self._engine: Optional[WanDiTEngine] = None
+        self._sig_params = None
 
     # -- engine management -------------------------------------------------------------------
     def _param_signature(self):
-        """Cheap staleness stamp: parameter storage pointers + in-place version counters."""
+        """Staleness stamp of the kernel-ready weight copies: storage pointer + in-place version counter of a fixed SAMPLE of
+        parameters (first / last / every 97th).  Whole-model events — .to() / .cuda() / dtype casts (`_apply`),
+        `load_state_dict`, LoRA merges (`invalidate_engine`) — drop the engine explicitly, so the per-call check only has to
+        catch stray in-place edits and stays O(1) instead of a Python loop over ~1k tensors per forward."""
+        ps = self._sig_params
+        if ps is None:
+            allp = list(self.parameters())
+            ps = self._sig_params = allp[::97] + allp[-1:]
         s = 0
-        for p in self.parameters():
+        for p in ps:
             s = (s * 1000003 + p.data_ptr() + 7919 * p._version) % (1 << 61)
         return s
+
+    def _apply(self, fn, *a, **k):
+        self._engine, self._sig_params = None, None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine, self._sig_params = None, None
+        return super().load_state_dict(*a, **k)
 
     def engine(self, device=None) -> WanDiTEngine:
         if device is None:
@@ -693,7 +758,7 @@ class WanModel(nn.Module):
         return eng
 
     def invalidate_engine(self):
-        self._engine = None
+        self._engine, self._sig_params = None, None
 
     # -- reference surface ---------------------------------------------------------------------
     def patchify(self, x: torch.Tensor):

@@ -523,18 +523,28 @@ class WanVideoVAE(nn.Module):
             self._engine = e
         return e
 
+    _tiled_warned = False
+
+    @classmethod
+    def _note_untiled(cls, what):
+        """`tiled=True` (the pipelines' default argument) is a DOCUMENTED deviation: the reference's tiling
+        (wan_video_vae.py:643-744) is a memory workaround whose blend ramps change the result against its own untiled path;
+        with 180 GB of HBM the untiled computation fits and is what runs.  Said once per process."""
+        if not cls._tiled_warned:
+            cls._tiled_warned = True
+            import warnings
+            warnings.warn(f"svi_b200: WanVideoVAE.{what}(tiled=True) runs UNTILED (tile_size / tile_stride ignored): results "
+                          f"equal the reference's tiled=False path, not its blended tiles", stacklevel=3)
+
     def encode(self, videos, device, tiled=False, tile_size=(34, 34), tile_stride=(18, 16)):
-        # tiled=True (the pipelines' default for video-to-video input): the reference's tiling (:643-744) is a memory
-        # workaround whose blend ramps change the latents; with 180 GB of HBM the untiled encode fits and is used, exactly
-        # as decode() does
+        if tiled:
+            self._note_untiled("encode")
         eng = self.engine(device)
         return torch.stack([eng.encode(v) for v in videos])
 
     def decode(self, hidden_states, device, tiled=False, tile_size=(34, 34), tile_stride=(18, 16)):
         if tiled:
-            # The reference's tiling (wan_video_vae.py:643-744) is a memory workaround that changes pixels; with
-            # 180 GB of HBM the untiled decode fits, so `tiled=True` (test_svi.py default False) runs untiled.
-            pass
+            self._note_untiled("decode")
         eng = self.engine(device)
         return torch.stack([eng.decode(h) for h in hidden_states])
 

@@ -115,6 +115,8 @@ def model_fn_wan_video(dit: WanModel, x: torch.Tensor, timestep: torch.Tensor, c
 
 
 class SVIVideoPipeline(BasePipeline):
+    OTHER_RANK = object()      # stands for the ContextState of a CFG branch that another rank group computes (denoise_step)
+
     def __init__(self, device="cuda", torch_dtype=torch.float16, tokenizer_path=None, is_test=False, num_train_timesteps=1000):
         super().__init__(device=device, torch_dtype=torch_dtype)
         self.scheduler = FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True, num_train_timesteps=num_train_timesteps)
@@ -132,10 +134,12 @@ class SVIVideoPipeline(BasePipeline):
     # ------------------------------------------------------------------ construction
     def enable_vram_management(self, num_persistent_param_in_dit=None):
         """Reference svi_video.py:156-241 wraps every Linear for CPU offload under a 6e9-parameter budget.  On a
-        180 GB B200 the whole 14B model (32 GB bf16) is resident: this is the all-resident policy."""
-        for name in ("dit", "vae"):
-            m = getattr(self, name)
-            if m is not None:
+        180 GB B200 the whole 14B model (32 GB bf16) plus umT5-XXL, CLIP and the VAE are resident: the all-resident
+        policy.  The reference harness builds its ModelManager on the CPU (test_svi.py:316-318), so every model the
+        pipeline holds is moved here (and in fetch_models): the engines exist for CUDA devices only."""
+        for name in ("dit", "vae", "text_encoder", "image_encoder"):
+            m = getattr(self, name, None)
+            if isinstance(m, torch.nn.Module):
                 m.to(self.device)
                 m.vram_management_enabled = False
 
@@ -153,8 +157,10 @@ class SVIVideoPipeline(BasePipeline):
             if os.path.isdir(tok_dir):
                 self.prompter.fetch_tokenizer(tok_dir)
         self.image_encoder = model_manager.fetch_model("wan_video_image_encoder")
-        if self.dit is not None:
-            self.dit.to(self.device).eval()
+        for name in ("dit", "vae", "text_encoder", "image_encoder"):       # a CPU-resident ModelManager is the reference flow
+            m = getattr(self, name, None)
+            if isinstance(m, torch.nn.Module) and torch.device(self.device).type == "cuda":
+                m.to(self.device).eval()
 
     @staticmethod
     def from_model_manager(model_manager, torch_dtype=None, device=None, use_usp=False, is_test=False, num_train_timesteps=1000):
@@ -162,11 +168,18 @@ class SVIVideoPipeline(BasePipeline):
         torch_dtype = model_manager.torch_dtype if torch_dtype is None else torch_dtype
         pipe = SVIVideoPipeline(device=device, torch_dtype=torch_dtype, is_test=is_test, num_train_timesteps=num_train_timesteps)
         pipe.fetch_models(model_manager)
-        if use_usp:   # reference :265-273 patches in xfuser USP; here: native token-axis sequence parallelism
+        if use_usp:   # reference :265-273 patches in xfuser USP; here: the native CFG-parallel x sequence-parallel plan
             from ..distributed.sequence_parallel import get_sp_group
             pipe.sp_size = get_sp_group().world
             pipe.use_unified_sequence_parallel = True
         return pipe
+
+    def sp_group(self):
+        """The multi-GPU plan of this pipeline (None on one GPU)."""
+        if not self.use_unified_sequence_parallel:
+            return None
+        from ..distributed.sequence_parallel import get_sp_group
+        return get_sp_group()
 
     def denoising_model(self):
         return self.dit
@@ -234,6 +247,22 @@ class SVIVideoPipeline(BasePipeline):
                                tile_size=tile_size, tile_stride=tile_stride)
 
     # ------------------------------------------------------------------ denoising
+    def denoise_step(self, eng, lat, t, sigma, sigma_next, cp, cn, v_c, v_u, cfg_scale, y=None, sp=None, tea=(None, None),
+                     add_condition=(None, None)):
+        """ONE flow-matching step of the hot loop (reference :404-420: two forwards, CFG combine, scheduler.step) on the
+        device-resident f32 latents `lat` (updated in place).  cp / cn: ContextState of the conditional / unconditional
+        prompt (cn None: no guidance).  sp: the multi-GPU plan — with two CFG groups every rank runs ONE branch on its
+        token rows and the branches' velocity fields are joined once per step (SequenceParallelGroup.cfg_parallel_step)."""
+        if sp is not None and cn is not None:
+            return sp.cfg_parallel_step(eng, lat, t, cp, cn, v_c, v_u, cfg_scale, sigma, sigma_next, y=y, tea=tea,
+                                        add_condition=add_condition)
+        inner = sp if sp is not None and sp.sp_size > 1 else None
+        eng.forward(lat, t, cp, y=y, sp=inner, out=v_c, tea_cache=tea[0], add_condition=add_condition[0])
+        if cn is not None:
+            eng.forward(lat, t, cn, y=y, sp=inner, out=v_u, tea_cache=tea[1], add_condition=add_condition[1])
+        eng.k.cfg_euler_step(lat, v_c, v_u if cn is not None else None, cfg_scale, sigma, sigma_next)
+        return lat
+
     def denoise_latents(self, latents, context_posi, context_nega, clip_feature=None, y=None, cfg_scale=5.0,
                         progress_bar_cmd=lambda x: x, sp=None, tea_cache_posi=None, tea_cache_nega=None,
                         add_condition_posi=None, add_condition_nega=None):
@@ -245,30 +274,24 @@ class SVIVideoPipeline(BasePipeline):
             lat = lat.to(torch.float32).contiguous()
         if y is not None:
             y = y.to(device=self.device, dtype=torch.float32).contiguous()
-        cp = eng.context_state(context_posi, clip_feature)
         use_cfg = cfg_scale != 1.0
-        cn = eng.context_state(context_nega, clip_feature) if use_cfg else None
+        both = sp is None or not use_cfg          # a CFG-parallel rank projects only its own branch's prompt
+        cp = eng.context_state(context_posi, clip_feature) if both or sp.owns_branch(0) else None
+        cn = (eng.context_state(context_nega, clip_feature) if both or sp.owns_branch(1) else self.OTHER_RANK) if use_cfg else None
         v_c = torch.empty_like(lat)
         v_u = torch.empty_like(lat) if use_cfg else None
         sig = self.scheduler.sigmas
         ts = self.scheduler.timesteps
         n = len(ts)
         for i in progress_bar_cmd(range(n)):
-            t = float(ts[i])
-            eng.forward(lat, t, cp, y=y, sp=sp, out=v_c, tea_cache=tea_cache_posi, add_condition=add_condition_posi)
-            if use_cfg:
-                eng.forward(lat, t, cn, y=y, sp=sp, out=v_u, tea_cache=tea_cache_nega, add_condition=add_condition_nega)
-            sigma = float(sig[i])
             nxt = float(sig[i + 1]) if i + 1 < n else 0.0
-            eng.k.cfg_euler_step(lat, v_c, v_u, cfg_scale, sigma, nxt)
+            self.denoise_step(eng, lat, float(ts[i]), float(sig[i]), nxt, cp, cn, v_c, v_u, cfg_scale, y=y, sp=sp,
+                              tea=(tea_cache_posi, tea_cache_nega), add_condition=(add_condition_posi, add_condition_nega))
         return lat
 
     def _sample_with_regular_video(self, latents, prompt_emb_posi, prompt_emb_nega, image_emb, extra_input, tea_cache_posi,
                                    tea_cache_nega, usp_kwargs, use_controlnet, cfg_scale, progress_bar_cmd):
-        sp = None
-        if usp_kwargs.get("use_unified_sequence_parallel"):
-            from ..distributed.sequence_parallel import get_sp_group
-            sp = get_sp_group()
+        sp = self.sp_group() if usp_kwargs.get("use_unified_sequence_parallel") else None
         scale = cfg_scale["text"] if isinstance(cfg_scale, dict) else cfg_scale
         bar = (lambda r: progress_bar_cmd(r)) if progress_bar_cmd is not None else (lambda r: r)
         return self.denoise_latents(latents, prompt_emb_posi["context"], prompt_emb_nega["context"],

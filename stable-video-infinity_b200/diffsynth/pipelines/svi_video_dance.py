@@ -88,7 +88,7 @@ class SVIDanceVideoPipeline(SVIVideoPipeline):
         scale = cfg_scale["text"] if isinstance(cfg_scale, dict) else cfg_scale
         bar = (lambda r: progress_bar_cmd(r)) if progress_bar_cmd is not None else (lambda r: r)
         latents = self.denoise_latents(latents, pos["context"], neg["context"], image_emb.get("clip_feature"),
-                                       image_emb.get("y"), scale, bar, None, mk(), mk(),
+                                       image_emb.get("y"), scale, bar, self.sp_group(), mk(), mk(),
                                        add_condition_posi=condition, add_condition_nega=condition if cond_wo_pose else None)
         frames = self.decode_video(latents, **tiler_kwargs)
         return self.tensor2video(frames[0])

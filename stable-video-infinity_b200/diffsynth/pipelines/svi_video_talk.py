@@ -79,11 +79,10 @@ class SVITalkVideoPipeline(SVIVideoPipeline):
                              cfg_scale, progress_bar_cmd=lambda x: x, tea_cache_posi=None, tea_cache_nega=None, condition=None):
         """reference _sample_with_multitalk :448-466 (three forwards per step unless both scales are 1)."""
         eng = self.dit.engine(self.device)
-        sp = None
-        if self.use_unified_sequence_parallel:
-            from ..distributed.sequence_parallel import get_sp_group
-            sp = get_sp_group()
-            sp = sp if sp.sp_size > 1 else None
+        # three-way guidance: the forwards of one step run one after the other on every rank, each split over the token axis
+        # of the rank's sequence-parallel group (with two CFG groups both groups compute the same step)
+        sp = self.sp_group()
+        sp = sp if sp is not None and sp.sp_size > 1 else None
         lat = latents if latents.dtype == torch.float32 and latents.is_contiguous() else latents.to(torch.float32).contiguous()
         if y is not None:
             y = y.to(device=self.device, dtype=torch.float32).contiguous()

@@ -65,6 +65,7 @@ class WanVideoPipeline(SVIVideoPipeline):
         mk = lambda: (TeaCache(num_inference_steps, rel_l1_thresh=tea_cache_l1_thresh, model_id=tea_cache_model_id)
                       if tea_cache_l1_thresh is not None else None)     # reference wan_video.py:261-262
         latents = self.denoise_latents(latents, pos["context"], neg["context"], image_emb.get("clip_feature"),
-                                       image_emb.get("y"), cfg_scale, bar, tea_cache_posi=mk(), tea_cache_nega=mk())
+                                       image_emb.get("y"), cfg_scale, bar, self.sp_group(), tea_cache_posi=mk(),
+                                       tea_cache_nega=mk())
         frames = self.decode_video(latents, **tiler_kwargs)
         return self.tensor2video(frames[0])

@@ -59,6 +59,45 @@ def attention_workspace_bytes(Lq, Lk, num_heads):
     return 0
 
 
+def attention_qscale(q, k, v, out, num_heads, q_sumsq, q_dim, q_eps, scale=None, accumulate=False, workspace=None):
+    hd = q.shape[1] // num_heads
+    scale = hd ** -0.5 if scale is None else scale
+    rs = torch.rsqrt(q_sumsq[:, 0] / q_dim + q_eps).unsqueeze(1)
+    return attention((q.float() * rs), k, v, out, num_heads, scale, accumulate)     # the factor rides in fp32, q stays bf16
+
+
+def _split(v, out):
+    K = v.shape[1]
+    hi = v.to(torch.bfloat16)
+    out[:, :K] = hi
+    out[:, K:] = (v - hi.float()).to(torch.bfloat16)
+    return out
+
+
+def split_f32_to_bf16x2(src, dst, act=0):
+    return _split(_act(src.float(), act), dst)
+
+
+def layernorm_modulate_split(x, out, eps, gamma=None, beta=None, scale=None, shift=None):
+    y = F.layer_norm(x, (x.shape[1],), gamma, beta, eps)
+    if scale is not None:
+        y = y * (1 + scale)
+    if shift is not None:
+        y = y + shift
+    return _split(y, out)
+
+
+def qk_norm_rope(qk, sumsq, eps, wq, wk, rope_cos, rope_sin, row_offset=0):
+    D = qk.shape[1] // 2
+    rmsnorm_rope(qk[:, :D], sumsq, 0, eps, wq, rope_cos, rope_sin, row_offset)
+    rmsnorm_rope(qk[:, D:], sumsq, 1, eps, wk, rope_cos, rope_sin, row_offset)
+    return qk
+
+
+def zero_(t):
+    return t.zero_()
+
+
 def layernorm_modulate(x, out, eps, gamma=None, beta=None, scale=None, shift=None):
     y = F.layer_norm(x, (x.shape[1],), gamma, beta, eps)
     if scale is not None:
@@ -83,12 +122,16 @@ def rmsnorm_rope(t, sumsq, sumsq_col, eps, weight, rope_cos=None, rope_sin=None,
     return t
 
 
-def patchify_gather(x, y, tokens):
+def patchify_gather(x, y, tokens, split=False):
     src = x if y is None else torch.cat([x, y], dim=0)
     C, Fr, H, W = src.shape
     p = src.reshape(C, Fr, H // 2, 2, W // 2, 2).permute(1, 2, 4, 0, 3, 5).reshape(Fr * (H // 2) * (W // 2), C * 4)
     tokens.zero_()
-    tokens[:, :C * 4] = p.to(tokens.dtype)
+    hi = p.to(tokens.dtype)
+    tokens[:, :C * 4] = hi
+    if split:
+        kp = tokens.shape[1] // 2
+        tokens[:, kp:kp + C * 4] = (p - hi.float()).to(tokens.dtype)
     return tokens
 
 
@@ -116,7 +159,7 @@ def cast_bf16_to_f32(src, dst):
 
 
 def add_rows(table, t, out):
-    out.copy_(table + t)
+    out.copy_(table + t.repeat(table.shape[0] // t.shape[0], 1))
     return out
 
 
@@ -125,8 +168,9 @@ def axpby(a, alpha, b, beta, out):
     return out
 
 
-_NAMES = ("gemm", "attention", "attention_workspace_bytes", "layernorm_modulate", "rmsnorm_rope", "patchify_gather",
-          "unpatchify", "cfg_euler_step", "cast_f32_to_bf16", "cast_bf16_to_f32", "add_rows", "axpby")
+_NAMES = ("gemm", "attention", "attention_workspace_bytes", "attention_qscale", "layernorm_modulate", "layernorm_modulate_split",
+          "rmsnorm_rope", "qk_norm_rope", "patchify_gather", "unpatchify", "cfg_euler_step", "cast_f32_to_bf16",
+          "cast_bf16_to_f32", "split_f32_to_bf16x2", "zero_", "add_rows", "axpby")
 
 
 def install(monkeypatch=None):

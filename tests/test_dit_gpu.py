@@ -1,9 +1,15 @@
 """GPU parity: the native DiT (C-ABI kernels) against the CPU oracle on identical seeded weights / inputs.
 
-Tolerance (BASELINE.json north_star): rtol=1e-2 / atol=1e-3.  A 30-block bf16-operand model cannot satisfy a
-literal allclose (the reference's own bf16 path reaches 44 % of elements, SURVEY.md §7 hard part 1), so the
-stacked-model tests assert the fraction of elements inside the tolerance and the max / mean error against the
-survey's measured bars, while single ops/blocks are asserted strictly in test_kernels_gpu.py.
+Tolerance (BASELINE.json north_star): rtol=1e-2 / atol=1e-3, counted per element.  A 30-block bf16-operand model cannot
+satisfy a literal allclose (the reference's own bf16 path reaches 44 % of elements, SURVEY.md §7 hard part 1), so the
+stacked-model tests assert the fraction of elements inside the tolerance and the max / mean error.  Where the bars come
+from (tools/rounding_study.py, a CPU emulation of every bf16 rounding point of the native path on the oracle):
+  * the noise floor is set by the bf16 A operand of the BLOCK GEMMs (97 % inside at cfg-1 with these weights if nothing
+    else is rounded); q/k/v/P storage formats cost < 0.2 points; the small GEMMs around the block stack (embedding MLPs,
+    patch embedding, head) cost 6 points when fed plain bf16 and are therefore fed two-term bf16 operands;
+  * tools.synth draws matrices from N(0, 1/fan_in): a sqrt(3) larger weight std than the reference's constructors
+    (nn.Linear default init), on which SURVEY.md measured its 97.5 % bar.  Both initialisations are asserted below.
+Single ops / one block are asserted strictly (>= 99.5 % inside) here and in test_kernels_gpu.py.
 """
 import pytest
 import torch
@@ -46,9 +52,9 @@ def test_tiny_dit_matches_oracle(cfg, f, h, w, ctx_len, seed):
             y=None if "y" not in inp else inp["y"].cuda()).float().cpu()
     inside, mx, rel = _stats(out, ref)
     print(f"tiny dit: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
-    # bf16 operands put ~2^-9 relative noise on every GEMM input: mean |err| ~ 0.2 % of the output std; with an
-    # output std ~1.1 the atol=1e-3 leg of the tolerance is tighter than that for small elements
-    assert inside > 0.80 and mx < 0.03 and rel < 4e-3
+    # two blocks of bf16-operand GEMMs: mean |err| ~ 0.05-0.1 % of the output std (round 1, plain bf16 embeddings /
+    # patch / head operands: 0.86-0.90 inside, 0.22 %)
+    assert inside > 0.95 and mx < 0.012 and rel < 1.5e-3
 
 
 def test_golden_fixture_tiny_t2v():
@@ -63,7 +69,8 @@ def test_golden_fixture_tiny_t2v():
     m = _build(cfg, sd)
     out = m(inp["x"].cuda(), torch.from_numpy(g["timestep"]), inp["context"].cuda()).float().cpu()
     inside, mx, rel = _stats(out, torch.from_numpy(g["out"]))
-    assert inside > 0.80 and mx < 0.03 and rel < 4e-3
+    print(f"golden tiny t2v: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
+    assert inside > 0.95 and mx < 0.012 and rel < 1.5e-3
 
 
 def test_model_fn_and_cfg_euler_step_match_oracle():
@@ -127,7 +134,7 @@ def test_add_condition_is_added_to_the_patch_embedding():
     base = O.dit_forward(sd, cfg, a["x"], ts, a["context"])
     inside, mx, rel = _stats(out, ref)
     print(f"add_condition: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
-    assert inside > 0.80 and rel < 4e-3 and (ref - base).abs().max() > 1e-2
+    assert inside > 0.95 and rel < 1.5e-3 and (ref - base).abs().max() > 1e-2
 
 
 def test_teacache_denoise_matches_oracle():
@@ -164,11 +171,15 @@ def test_teacache_denoise_matches_oracle():
 
 
 @pytest.mark.slow
-def test_cfg1_1p3b_one_step_matches_oracle():
-    """BASELINE config 1: Wan2.1-T2V-1.3B random-init, 1 denoise step, 17x320x512 (latent [1,16,5,40,64])."""
+@pytest.mark.parametrize("init,min_inside,max_err,max_rel", [("normal", 0.94, 0.012, 1.3e-3), ("torch_default", 0.98, 0.006, 7e-4)])
+def test_cfg1_1p3b_one_step_matches_oracle(init, min_inside, max_err, max_rel):
+    """BASELINE config 1: Wan2.1-T2V-1.3B random-init, 1 denoise step, 17x320x512 (latent [1,16,5,40,64]).
+    init="torch_default" is the reference constructors' own initialisation (the survey's 97.5 % / 0.005 bar);
+    "normal" is tools.synth's wider N(0, 1/fan_in).  The CPU emulation of bf16 block-GEMM operands alone
+    (tools/rounding_study.py `blk`) gives 0.963 / 0.0085 / 1.0e-3 and better than 0.987 / 0.0049 / 7.2e-4."""
     from oracle import wan_dit_oracle as O
     cfg = synth.CFG_T2V_1_3B
-    sd = _sd(cfg, 0)
+    sd = {k: v.to(torch.bfloat16).float() for k, v in synth.make_dit_state_dict(cfg, seed=0, init=init).items()}
     inp = synth.make_dit_inputs(cfg, 5, 40, 64, seed=0, ctx_len=512)
     ts = torch.tensor([1000.0])
     torch.set_num_threads(max(1, torch.get_num_threads()))
@@ -179,10 +190,37 @@ def test_cfg1_1p3b_one_step_matches_oracle():
     v = m(inp["x"].cuda(), ts, inp["context"].cuda()).float()
     out = (inp["x"].cuda() - v).cpu()
     inside, mx, rel = _stats(out, ref)
-    print(f"cfg-1 1.3B: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
-    # bars from SURVEY.md §7: emulated bf16-operand/fp32-residual design = 97.5 % inside, max 0.005;
-    # the reference's own bf16 path = 44 % inside, max 0.042
-    assert inside > 0.85 and mx < 0.042 and rel < 6e-3
+    print(f"cfg-1 1.3B init={init}: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
+    assert inside > min_inside and mx < max_err and rel < max_rel
+
+
+@pytest.mark.slow
+def test_block_at_bench_shape_matches_oracle():
+    """ONE DiT block at the benchmark's shape (BASELINE configs[1]: L = 21*30*52 = 32760 tokens, d = 1536, 12 heads,
+    512 context rows) against oracle.dit_block: the ragged last tile (32760 = 255*128 + 120), the sliced last wave of the
+    attention launch plan + its merge kernel, and the full-size GEMM tilings are all live.  Per-block bar
+    (BASELINE.md section 2): >= 99.6 % of elements inside rtol 1e-2 / atol 1e-3."""
+    from oracle import wan_dit_oracle as O
+    cfg = dict(synth.CFG_T2V_1_3B, num_layers=1)
+    f, h, w = 21, 30, 52
+    L, d = f * h * w, cfg["dim"]
+    sd = _sd(cfg, 0)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, L, d, generator=g)
+    ctx = torch.randn(1, 512, d, generator=g).to(torch.bfloat16).float()      # embedded context rows (a GEMM A operand)
+    t_mod = torch.randn(1, 6, d, generator=g) * 0.1
+    ref = O.dit_block(sd, 0, x, ctx, t_mod, O.rope_angles_3d(128, f, h, w), cfg)[0]
+    m = _build(cfg, sd)
+    eng = m.engine("cuda")
+    st = eng.project_context(ctx[0].to("cuda", torch.bfloat16))
+    mods = (sd["blocks.0.modulation"].reshape(6, d) + t_mod[0]).cuda().contiguous()
+    cos, sin = eng.rope(f, h, w)
+    xg = x[0].cuda().contiguous()
+    eng.run_block(0, xg, mods, st, cos, sin)
+    torch.cuda.synchronize()
+    inside, mx, rel = _stats(xg.cpu(), ref)
+    print(f"block @ L={L}: inside={inside:.5f} max={mx:.4e} mean/std={rel:.4e}")
+    assert inside > 0.995 and mx < 0.02 and rel < 6e-4
 
 
 @pytest.mark.slow
@@ -200,4 +238,4 @@ def test_14b_width_single_layer_matches_oracle():
     out = m(inp["x"].cuda(), ts, inp["context"].cuda(), clip_feature=inp["clip_feature"].cuda(), y=inp["y"].cuda()).float().cpu()
     inside, mx, rel = _stats(out, ref)
     print(f"14B-width 1 layer: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
-    assert inside > 0.80 and mx < 0.03 and rel < 4e-3
+    assert inside > 0.95 and mx < 0.012 and rel < 1.5e-3

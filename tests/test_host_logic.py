@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/svi_b200.h but not exported"
         assert name in nv.SIGNATURES, f"{name} has no ctypes signature in diffsynth/_native.py"
     assert sorted(nv.SIGNATURES) == declared
-    assert lib.svi_abi_version() == 2
+    assert lib.svi_abi_version() == 3
 
 
 def test_header_is_plain_c():

@@ -42,14 +42,19 @@ class TokenPrompter:
         return self.prompter.encode_ids(ids, mask, device="cuda").to(torch.float32)
 
 
-def main():
+def main_from_bench(bargs):
+    """bench.py --workload cfg4: the chained-clip loop (BASELINE configs[3]) with bench's --clips."""
+    return main(["--clips", str(bargs.clips)])
+
+
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--clips", type=int, default=2)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--motion-frames", type=int, default=5)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=832)
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     from diffsynth import ModelManager, SVIVideoPipeline
     from diffsynth.models.wan_video_dit import WanModel, precompute_freqs_cis_3d
     from diffsynth.models.wan_video_image_encoder import WanImageEncoder

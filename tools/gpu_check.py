@@ -18,15 +18,21 @@ dev = "cuda"
 RESULTS = []   # (name, ok) of every report() call — tests/test_kernels_gpu.py asserts on it
 
 
-def report(name, got, ref, tol):
+def report(name, got, ref, tol, min_inside=None):
+    """Max-norm criterion (err <= tol * max|ref|) and, when min_inside is given, the elementwise criterion of the north
+    star as well: the fraction of elements with err <= 1e-3 * rms(ref) + 1e-2 * |ref| must reach min_inside (atol is taken
+    relative to the reference's rms so that the bar means the same for unit-scale and for 1/sqrt(L)-scale outputs)."""
     got = got.float()
     ref = ref.float()
     err = (got - ref).abs()
     mx = err.max().item()
     scale = ref.abs().max().item()
     bad = (err > tol * max(scale, 1e-6)).float().mean().item()
-    ok = math.isfinite(mx) and mx <= tol * max(scale, 1e-6)
-    print(f"[{'OK ' if ok else 'BAD'}] {name}: max_err={mx:.4e} ref_max={scale:.4e} frac_bad={bad:.4f}", flush=True)
+    rms = ref.pow(2).mean().sqrt().item()
+    inside = (err <= 1e-3 * rms + 1e-2 * ref.abs()).float().mean().item()
+    ok = math.isfinite(mx) and mx <= tol * max(scale, 1e-6) and (min_inside is None or inside >= min_inside)
+    print(f"[{'OK ' if ok else 'BAD'}] {name}: max_err={mx:.4e} ref_max={scale:.4e} frac_bad={bad:.4f} "
+          f"inside(rtol 1e-2, atol 1e-3 rms)={inside:.4f}", flush=True)
     RESULTS.append((name, ok))
     if not ok:
         # locate the error pattern to help debugging descriptor/layout mistakes
@@ -126,6 +132,116 @@ def sec_attn():
             nv.attention(q, k, v, out, H, scale, workspace=ws)
             torch.cuda.synchronize()
             report(f"attn Lq={Lq} Lk={Lk} H={H} amp={amp} workspace={'yes' if ws is not None else 'no'}", out, ref, 2e-2)
+
+
+def attn_ref_chunked(q, k, v, H, scale, chunk=4096):
+    """fp32 reference on the GPU, query rows in chunks (a [chunk, Lk] score matrix per head at a time)."""
+    Lq, Lk = q.shape[0], k.shape[0]
+    out = torch.empty(Lq, H * 128, device=q.device, dtype=torch.float32)
+    for h in range(H):
+        kh = k[:, h * 128:(h + 1) * 128].float()
+        vh = v[:, h * 128:(h + 1) * 128].float()
+        for r0 in range(0, Lq, chunk):
+            sc = (q[r0:r0 + chunk, h * 128:(h + 1) * 128].float() @ kh.t()) * scale
+            out[r0:r0 + chunk, h * 128:(h + 1) * 128] = torch.softmax(sc, dim=-1) @ vh
+    return out
+
+
+def sec_attn_bench():
+    """Self-attention at the BENCHMARK shape (L = 32760 = 255*128 + 120, 12 heads): 1536 (head, Q-pair) units on 148 SMs =
+    10 whole waves + a sliced last wave merged by attn_merge_kernel, ragged last K/V and Q tiles.  amp 3 makes the softmax
+    peaked (score std 9), so the outputs are O(1) and the elementwise tolerance bites."""
+    g = torch.Generator(device="cpu").manual_seed(12)
+    scale = 128 ** -0.5
+    L, H = 32760, 12
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for amp in (1.0, 3.0):
+            q = (torch.randn(L, H * 128, generator=g) * amp).to(dev, torch.bfloat16)
+            k = (torch.randn(L, H * 128, generator=g) * amp).to(dev, torch.bfloat16)
+            v = torch.randn(L, H * 128, generator=g).to(dev, torch.bfloat16)
+            ref = attn_ref_chunked(q, k, v, H, scale)
+            for ws in (torch.empty(nv.attention_workspace_bytes(L, L, H) // 4 + 1, device=dev), None):
+                out = torch.full((L, H * 128), float("nan"), device=dev, dtype=torch.bfloat16)
+                nv.attention(q, k, v, out, H, scale, workspace=ws)
+                torch.cuda.synchronize()
+                report(f"attn bench shape L={L} H={H} amp={amp} workspace={'yes' if ws is not None else 'no'}", out, ref, 2e-2,
+                       min_inside=0.99)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def sec_abi3():
+    """Entry points added with ABI 3: split-precision staging, q|k norm in one launch, attention with a per-row Q scale."""
+    g = torch.Generator(device="cpu").manual_seed(13)
+    # two-term bf16 split: hi + lo reproduces the f32 value to ~2^-17
+    for (M, K, act, fn) in [(5, 256, nv.ACT_NONE, lambda t: t), (300, 1536, nv.ACT_SILU, torch.nn.functional.silu),
+                            (257, 1280, nv.ACT_GELU_ERF, torch.nn.functional.gelu),
+                            (512, 96, nv.ACT_GELU_TANH, lambda t: torch.nn.functional.gelu(t, approximate="tanh"))]:
+        x = (torch.randn(M, K, generator=g) * 3).to(dev)
+        d2 = torch.full((M, 2 * K), float("nan"), device=dev, dtype=torch.bfloat16)
+        nv.split_f32_to_bf16x2(x, d2, act=act)
+        report(f"split_f32_to_bf16x2 M={M} K={K} act={act}", d2[:, :K].float() + d2[:, K:].float(), fn(x), 2e-5)
+        report(f"split hi part is the bf16 rounding act={act}", d2[:, :K], fn(x).to(torch.bfloat16), 4e-3)
+    # LayerNorm + modulate, split output
+    for (M, D) in [(77, 1536), (9, 5120), (33, 256)]:
+        x = (torch.randn(M, D, generator=g) * 2 + 0.3).to(dev)
+        sc, sh = torch.randn(D, generator=g).to(dev) * 0.1, torch.randn(D, generator=g).to(dev) * 0.1
+        o2 = torch.full((M, 2 * D), float("nan"), device=dev, dtype=torch.bfloat16)
+        nv.layernorm_modulate_split(x, o2, 1e-6, scale=sc, shift=sh)
+        ref = torch.nn.functional.layer_norm(x, (D,), eps=1e-6) * (1 + sc) + sh
+        report(f"layernorm_modulate_split M={M} D={D}", o2[:, :D].float() + o2[:, D:].float(), ref, 2e-5)
+    # patchify, split output
+    C0, C1, F, Hh, Ww = 16, 20, 3, 8, 12
+    x = torch.randn(C0, F, Hh, Ww, generator=g).to(dev)
+    y = torch.randn(C1, F, Hh, Ww, generator=g).to(dev)
+    L = F * (Hh // 2) * (Ww // 2)
+    kp = 4 * (C0 + C1)
+    tok = torch.full((L, 2 * kp), float("nan"), device=dev, dtype=torch.bfloat16)
+    nv.patchify_gather(x, y, tok, split=True)
+    xy = torch.cat([x, y], 0)
+    ref = xy.view(C0 + C1, F, Hh // 2, 2, Ww // 2, 2).permute(1, 2, 4, 0, 3, 5).reshape(L, kp)
+    report("patchify_gather split", tok[:, :kp].float() + tok[:, kp:].float(), ref, 2e-5)
+    # q | k norm + rope in one launch == two single launches
+    M, H = 333, 3
+    D = H * 128
+    t = torch.randn(M, 3 * D, generator=g).to(dev, torch.bfloat16)
+    tf = t.float()
+    ss = torch.stack([(tf[:, :D] ** 2).sum(1), (tf[:, D:2 * D] ** 2).sum(1)], 1).contiguous()
+    wq = (torch.randn(D, generator=g) * 0.2 + 1).to(dev)
+    wk = (torch.randn(D, generator=g) * 0.2 + 1).to(dev)
+    ang = torch.rand(M + 7, 64, generator=g, dtype=torch.float64) * 6.28
+    cos, sin = ang.cos().float().to(dev), ang.sin().float().to(dev)
+    a, b = t.clone(), t.clone()
+    nv.qk_norm_rope(a[:, :2 * D], ss, 1e-6, wq, wk, cos, sin, row_offset=7)
+    nv.rmsnorm_rope(b[:, :D], ss, 0, 1e-6, wq, cos, sin, row_offset=7)
+    nv.rmsnorm_rope(b[:, D:2 * D], ss, 1, 1e-6, wk, cos, sin, row_offset=7)
+    report("qk_norm_rope == rmsnorm_rope(q), rmsnorm_rope(k)", a, b, 1e-6)
+    # attention with the Q RMS factor in the softmax scale == attention on the normalised q
+    scale = 128 ** -0.5
+    for (Lq, Lk, Hh_) in [(700, 512, 2), (3200, 257, 12), (130, 77, 1)]:
+        Dq = Hh_ * 128
+        q = (torch.randn(Lq, Dq, generator=g) * 2.5).to(dev, torch.bfloat16)
+        k = torch.randn(Lk, Dq, generator=g).to(dev, torch.bfloat16)
+        v = torch.randn(Lk, Dq, generator=g).to(dev, torch.bfloat16)
+        ssq = (q.float() ** 2).sum(1, keepdim=True).contiguous()
+        qn = q.float() * torch.rsqrt(ssq / Dq + 1e-6)
+        out = torch.full((Lq, Dq), float("nan"), device=dev, dtype=torch.bfloat16)
+        nv.attention_qscale(q, k, v, out, Hh_, ssq, Dq, 1e-6, scale)
+        ref = attn_ref(qn, k, v, Hh_, scale)
+        report(f"attention_qscale Lq={Lq} Lk={Lk} H={Hh_}", out, ref, 2e-2, min_inside=0.99)
+        nv.attention_qscale(q, k, v, out, Hh_, ssq, Dq, 1e-6, scale, accumulate=True)
+        report(f"attention_qscale accumulate Lq={Lq} Lk={Lk} H={Hh_}", out, ref.bfloat16().float() + ref, 3e-2)
+    # periodic add_rows + zero_
+    tb = torch.randn(12, 256, generator=g).to(dev)
+    tt = torch.randn(6, 256, generator=g).to(dev)
+    oo = torch.empty_like(tb)
+    nv.add_rows(tb, tt, oo)
+    report("add_rows periodic", oo, tb + tt.repeat(2, 1), 1e-6)
+    z = torch.randn(1000, 3, generator=g).to(dev)
+    nv.zero_(z)
+    report("zero_", z + 1, torch.ones_like(z), 1e-7)
 
 
 def sec_attn_cross():

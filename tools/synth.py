@@ -77,14 +77,24 @@ def dit_param_shapes(cfg):
     return sh
 
 
-def make_dit_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
-    """Seeded random-init state dict.  Matrices ~ N(0, 1/fan_in), norm weights ~ 1 + 0.1 N, biases ~ 0.02 N,
-    modulation ~ N(0,1)/sqrt(dim) (as wan_video_dit.py:336,399).  Per-tensor generators keyed by name order so
-    that a subset (e.g. fewer layers) is reproducible."""
+def make_dit_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32, init="normal"):
+    """Seeded random-init state dict.  init="normal": matrices ~ N(0, 1/fan_in), norm weights ~ 1 + 0.1 N, biases ~ 0.02 N,
+    modulation ~ N(0,1)/sqrt(dim) (as wan_video_dit.py:336,399).  init="torch_default": the distribution the reference's
+    constructors produce (nn.Linear / nn.Conv3d: weights and biases ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)); norm weights 1,
+    norm biases 0) — a sqrt(3) smaller weight std, i.e. the random-init model SURVEY.md section 7 measured its parity bars on.
+    Per-tensor generators keyed by name order so that a subset (e.g. fewer layers) is reproducible."""
     sd = {}
-    for idx, (name, shape) in enumerate(dit_param_shapes(cfg).items()):
+    shapes = dit_param_shapes(cfg)
+    for idx, (name, shape) in enumerate(shapes.items()):
         g = torch.Generator(device="cpu").manual_seed(seed * 1000003 + idx)
-        if name.endswith("modulation"):
+        if init == "torch_default" and not name.endswith("modulation"):
+            if "norm" in name or name.startswith("img_emb.proj.0") or name.startswith("img_emb.proj.4"):
+                t = torch.ones(shape) if name.endswith(".weight") else torch.zeros(shape)
+            else:
+                wshape = shape if name.endswith(".weight") else shapes[name[:-5] + ".weight"]
+                bound = 1.0 / math.sqrt(math.prod(wshape[1:]))
+                t = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        elif name.endswith("modulation"):
             t = torch.randn(shape, generator=g) / cfg["dim"] ** 0.5
         elif "norm" in name and name.endswith(".weight") or name in ("img_emb.proj.0.weight", "img_emb.proj.4.weight"):
             t = 1.0 + 0.1 * torch.randn(shape, generator=g)

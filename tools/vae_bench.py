@@ -51,5 +51,56 @@ def main():
     print(json.dumps({"workload": f"vae {T}f x {H}x{W}", "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, **res}))
 
 
+def sweep_from_bench(args):
+    """bench.py --workload cfg5 (BASELINE configs[4]): VAE encode / decode at 17..161 frames x 720 x 1280 on one GPU.  Per point:
+    CUDA-event time (1 warm-up + 1 timed call through WanVideoVAE.encode / .decode, the public API), algorithmic TFLOP/s
+    (BASELINE.md section 3 formulas) against the measured bf16 peak and minimal-traffic GB/s (conv in + out, bf16: SURVEY
+    section 8d) against the measured HBM peak.  One JSON line; `value` = decoded pixel frames per second at 81 frames."""
+    from diffsynth.models.wan_video_vae import WanVideoVAE
+    from tools import flops
+    peaks = {}
+    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pp):
+        peaks = json.load(open(pp))
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    bw_peak = peaks.get("hbm_gbs", peaks.get("hbm_gbps", 6650.0))
+    vae = WanVideoVAE().eval()
+    vae.load_state_dict(synth_vae.make_vae_state_dict(seed=0))
+    vae.to("cuda")
+    H, W = 720, 1280
+    h, w = H // 8, W // 8
+    pts = []
+    frames_list = [int(v) for v in os.environ.get("SVI_VAE_SWEEP", "17,33,49,81,113,161").split(",")]
+    for T in frames_list:
+        tl = (T - 1) // 4 + 1
+        g = torch.Generator().manual_seed(T)
+        z = torch.randn(1, 16, tl, h, w, generator=g).cuda()
+        video = (torch.rand(3, T, H, W, generator=g) * 2 - 1).cuda()
+        row = {"frames": T, "latent_frames": tl}
+        for name, fn, fl in (("decode", lambda: vae.decode(z, device="cuda"), flops.vae_decode_flops(tl, h, w)),
+                             ("encode", lambda: vae.encode([video], device="cuda"), flops.vae_encode_flops(tl, H, W))):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            row[name] = {"ms": ms, "tflops": fl / ms / 1e9, "frac_of_bf16_peak": fl / ms / 1e9 / tf_peak, "frames_per_s": T / ms * 1e3}
+            if name == "decode":
+                nb = flops.vae_min_bytes(tl, h, w)
+                row[name].update(min_traffic_gbs=nb / ms / 1e6, frac_of_hbm_peak=nb / ms / 1e6 / bw_peak)
+        pts.append(row)
+        del z, video
+        torch.cuda.empty_cache()
+    ref = next((p for p in pts if p["frames"] == 81), pts[-1])
+    print(json.dumps({"metric": "VAE decoded pixel frames/sec (720p)", "value": ref["decode"]["frames_per_s"], "unit": "frames/s",
+                      "n_gpus": 1, "higher_is_better": True, "dtype": "bf16 conv operands, fp32 activations", "data": "synthetic",
+                      "config": {"workload": "cfg5", "description": "3D-VAE encode/decode sweep 17..161 frames x 720x1280 (BASELINE configs[4])"},
+                      "peaks": {"bf16_tflops_sustained": tf_peak, "hbm_gbs": bw_peak}, "points": pts,
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+
+
 if __name__ == "__main__":
     main()
