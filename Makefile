@@ -30,6 +30,16 @@ fastmath:
 	@mkdir -p $(PKG)/lib build
 	$(NVCC) $(NVFLAGS) --use_fast_math -shared -o $(FM_LIB) $(SRCS) -cudart shared
 
+# attention A/B builds (measurement only, selected with SVI_B200_LIB): share of exponentials on the FMA-pipe polynomial
+attn_variants:
+	@mkdir -p $(PKG)/lib build
+	for q in 0 2 4 6; do $(NVCC) $(NVFLAGS) -DSVI_ATTN_POLY16=$$q -shared -o $(PKG)/lib/libsvi_b200_attn_poly$$q.so $(SRCS) -cudart shared || exit 1; done
+
+# the library with the ROUND-1 attention kernel (320 threads, 168 registers, 6/16 polynomial share) for same-box A/B runs
+attn_r1:
+	@mkdir -p $(PKG)/lib build
+	$(NVCC) $(NVFLAGS) -shared -o $(PKG)/lib/libsvi_b200_attn_r1.so $(filter-out $(CSRC)/attn_tcgen05.cu,$(SRCS)) $(CSRC)/experimental/attn_r1_tcgen05.cu -cudart shared
+
 clean:
 	rm -rf build $(LIB) $(EXP_LIB)
-.PHONY: all clean exp fastmath
+.PHONY: all clean exp fastmath attn_variants attn_r1

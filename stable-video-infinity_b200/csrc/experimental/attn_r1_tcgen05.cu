@@ -2,19 +2,10 @@
 //
 // One CTA owns TWO 128-row Q tiles of one head and streams K/V tiles of 128 rows past them:
 //
-//   warps 0-3  : softmax warpgroup for Q tile 0 (thread = row; TMEM lane quadrant = warp % 4)   224 registers
-//   warps 4-7  : softmax warpgroup for Q tile 1                                                 224 registers
-//   warp  8    : TMA producer (Q once, then K_j / V_j into 2-stage rings, 128B-swizzled boxes)   56 registers
-//   warp  9    : tcgen05.mma issuer + TMEM owner                                                 56 registers
-//   warps 10-11: idle (they complete the third warpgroup: setmaxnreg is a warpgroup-wide instruction)
-//
-// What bounds it (ncu source view of the round-1 kernel, profiles/r02_attn_analysis.md): the softmax warps are bound by
-// ISSUE CYCLES on their SM sub-partition, not by latency — FFMA2 / FADD2 / FMNMX3 / IMAD each hold the issue port for two
-// cycles, and one sub-partition serves one warp of each softmax warpgroup.  Per 128x128 tile and warp the round-1 code
-// needed ~1125 issue cycles (x2 warps = 2250 per K/V step against 2048 tensor-pipe cycles).  This version: setmaxnreg
-// gives the softmax threads 224 registers (no spills, no register-shuffling IMAD.MOVs: 98 -> 29 IMADs), and the share of
-// exponentials computed by the FMA-pipe polynomial is 3 of 16 pairs instead of 6 (each polynomial pair costs 18 issue
-// cycles to save 16 XU cycles): ~825 issue cycles and ~830 XU cycles per tile and warp, both below the tensor time.
+//   warps 0-3 : softmax warpgroup for Q tile 0 (thread = row; TMEM lane quadrant = warp % 4)
+//   warps 4-7 : softmax warpgroup for Q tile 1
+//   warp  8   : TMA producer (Q once, then K_j / V_j into 2-stage rings, 128B-swizzled boxes)
+//   warp  9   : tcgen05.mma issuer + TMEM owner
 //
 // TMEM (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,384) | O1 [384,512); P_i (bf16, 64 columns)
 // aliases the front of S_i and is consumed straight from TMEM by the P*V MMA (A operand in TMEM).
@@ -27,8 +18,8 @@
 // over all SMs; sliced units leave (unnormalised O, row max, row sum) in a workspace and attn_merge_kernel combines
 // them.  Without a workspace every unit runs whole.
 // Replaces flash_attention(), reference wan_video_dit.py:116-147.
-#include "common.cuh"
-#include "../../include/svi_b200.h"
+#include "../common.cuh"
+#include "../../../include/svi_b200.h"
 
 namespace svi {
 namespace attn {
@@ -39,20 +30,7 @@ constexpr int HD = 128;
 constexpr int KV_STAGES = 2;
 constexpr int HALF_BYTES = 128 * 64 * 2;   // one 128-row x 64-col swizzled box (16 KB)
 constexpr int TILE_BYTES = 2 * HALF_BYTES;  // 128 x 128 bf16 (32 KB)
-constexpr int NUM_THREADS = 384;   // 12 warps = 3 warpgroups: setmaxnreg is a warpgroup-wide instruction
-#ifndef SVI_ATTN_POLY16
-#define SVI_ATTN_POLY16 3            // exponentials on the FMA pipes: this many of every 16 element pairs
-#endif
-#ifndef SVI_ATTN_OTHER_REGS
-#define SVI_ATTN_OTHER_REGS 56
-#endif
-#ifndef SVI_ATTN_SOFTMAX_REGS
-#define SVI_ATTN_SOFTMAX_REGS 224
-#endif
-// setmaxnreg only redistributes the registers the CTA was launched with (384 threads x 168): a larger request than the
-// pool holds blocks forever
-static_assert(2 * SVI_ATTN_SOFTMAX_REGS + SVI_ATTN_OTHER_REGS <= 3 * 168, "register split exceeds the CTA's allocation");
-static_assert(SVI_ATTN_SOFTMAX_REGS % 8 == 0 && SVI_ATTN_OTHER_REGS % 8 == 0, "setmaxnreg takes multiples of 8");
+constexpr int NUM_THREADS = 320;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
@@ -130,269 +108,277 @@ __device__ __forceinline__ void wait_kv_chunk(const uint32_t* flags, int chunk, 
   asm volatile("fence.proxy.async.global;" ::: "memory");   // later TMA (async proxy) reads see the pushed rows
 }
 
-// Register budget: the kernel starts with 65536 / 384 = 168 registers per thread; once the roles are fixed the TMA / MMA /
-// idle warpgroup drops to SVI_ATTN_OTHER_REGS and the two softmax warpgroups grow to SVI_ATTN_SOFTMAX_REGS
-// (256*224 + 128*56 = 64512 = the launch allocation: setmaxnreg can only redistribute what the CTA already owns).
-__device__ __forceinline__ void setmaxnreg_inc() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SVI_ATTN_SOFTMAX_REGS));
-}
-__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SVI_ATTN_OTHER_REGS)); }
+// 10 warps over 4 SM sub-partitions put 3 warps on one 16K-register partition: 168 registers/thread is the ceiling
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_q = smem;                               // [2][TILE_BYTES]
+  uint8_t* smem_k = smem + 2 * TILE_BYTES;              // [KV_STAGES][TILE_BYTES]
+  uint8_t* smem_v = smem_k + KV_STAGES * TILE_BYTES;    // [KV_STAGES][TILE_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + KV_STAGES * TILE_BYTES);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* k_full = bars + 2;     // [2]
+  uint64_t* k_empty = bars + 4;    // [2]
+  uint64_t* v_full = bars + 6;     // [2]
+  uint64_t* v_empty = bars + 8;    // [2]
+  uint64_t* s_full = bars + 10;    // [2]  MMA -> softmax_i : S_i(j) ready (and PV_i(j-1) retired)
+  uint64_t* p_ready = bars + 12;   // [2][2] softmax_i -> MMA : half h (64 keys) of P_i(j) in TMEM, O_i rescaled; the P*V of
+                                   //        the first half overlaps the exponentials of the second half
+  uint64_t* o_full = bars + 16;    // [2]  MMA -> softmax_i : O_i final
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
 
-// ---- shared-memory map (32-bit shared addresses throughout: the role code keeps no 64-bit generic pointers alive) ----
-constexpr uint32_t OFF_Q = 0;                                   // [2][TILE_BYTES]
-constexpr uint32_t OFF_K = 2 * TILE_BYTES;                      // [KV_STAGES][TILE_BYTES]
-constexpr uint32_t OFF_V = OFF_K + KV_STAGES * TILE_BYTES;      // [KV_STAGES][TILE_BYTES]
-constexpr uint32_t OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
-enum : uint32_t {
-  Q_FULL = 0,    // [2]
-  K_FULL = 2,    // [2]
-  K_EMPTY = 4,   // [2]
-  V_FULL = 6,    // [2]
-  V_EMPTY = 8,   // [2]
-  S_FULL = 10,   // [2]  MMA -> softmax_i : S_i(j) ready (and PV_i(j-1) retired)
-  P_READY = 12,  // [2][2] softmax_i -> MMA : half h (64 keys) of P_i(j) in TMEM, O_i rescaled; the P*V of the first
-                 //        half overlaps the exponentials of the second half
-  O_FULL = 16,   // [2]  MMA -> softmax_i : O_i final
-  NUM_BARS = 18
-};
-
-struct Unit {      // what this CTA computes (decoded per role: nothing of it stays live across the role dispatch)
-  int head, q_row0, j_begin, n_kv, n_kv_total, slice_slot;
-};
-__device__ __forceinline__ Unit decode_unit(const Params& p) {
-  Unit u;
-  u.n_kv_total = (p.Lk + BKV - 1) / BKV;
-  int unit = blockIdx.x;
-  u.j_begin = 0;
-  u.n_kv = u.n_kv_total;                            // K/V tiles THIS CTA streams, starting at j_begin
-  u.slice_slot = (int)blockIdx.x - p.n_full;        // >= 0: this CTA computes one slice of a unit
-  if (u.slice_slot >= 0) {
-    unit = p.n_full + u.slice_slot / p.split;
-    const int sl = u.slice_slot % p.split;
-    u.j_begin = (int)((long long)u.n_kv_total * sl / p.split);
-    u.n_kv = (int)((long long)u.n_kv_total * (sl + 1) / p.split) - u.j_begin;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_kv_total = (p.Lk + BKV - 1) / BKV;
+  int unit = blockIdx.x, j_begin = 0, n_kv = n_kv_total;   // n_kv: K/V tiles THIS CTA streams, starting at j_begin
+  const int slice_slot = (int)blockIdx.x - p.n_full;        // >= 0: this CTA computes one slice of a unit
+  if (slice_slot >= 0) {
+    unit = p.n_full + slice_slot / p.split;
+    const int sl = slice_slot % p.split;
+    j_begin = (int)((long long)n_kv_total * sl / p.split);
+    n_kv = (int)((long long)n_kv_total * (sl + 1) / p.split) - j_begin;
   }
-  u.head = unit / p.n_qpairs;
-  u.q_row0 = (unit % p.n_qpairs) * (2 * BQ);
-  return u;
-}
+  const int head = unit / p.n_qpairs;
+  const int q_row0 = (unit % p.n_qpairs) * (2 * BQ);
 
-// ------------------------------------ TMA producer (one lane) ------------------------------------
-__device__ __forceinline__ void tma_role(const CUtensorMap* tmap_q, const CUtensorMap* tmap_k, const CUtensorMap* tmap_v,
-                                         const Params& p, uint32_t sbase) {
-  const Unit u = decode_unit(p);
-  const uint32_t bars = sbase + OFF_BAR;
-  const int col0 = u.head * HD;
-  auto load_tile = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int row) {
-    mbar_expect_tx_a(bar, TILE_BYTES);
-    tma_load_2d_a(dst, m, bar, col0, row);
-    tma_load_2d_a(dst + HALF_BYTES, m, bar, col0 + 64, row);
-  };
-  load_tile(sbase + OFF_Q, tmap_q, bars + 8 * Q_FULL, u.q_row0);
-  int landed = p.kv_self_chunk;   // most recent remote chunk known to be present (chunks are visited in runs)
-  for (int j = 0; j < u.n_kv; ++j) {
-    const int s = j % KV_STAGES;
-    const uint32_t ph = (j / KV_STAGES) & 1;
-    const int row = kv_tile_at(u.j_begin + j, p.kv_first_tile, u.n_kv_total) * BKV;
-    if (p.kv_flags) {
-      const int c0 = row / p.kv_chunk_rows;
-      const int c1 = (min(row + BKV, p.Lk) - 1) / p.kv_chunk_rows;
-      for (int c = c0; c <= c1; ++c) {
-        if (c == p.kv_self_chunk || c == landed) continue;
-        wait_kv_chunk(p.kv_flags, c, p.kv_epoch);
-        landed = c;
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&q_full[i], 1);
+        mbar_init(&k_full[i], 1);
+        mbar_init(&k_empty[i], 1);
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_ready[i * 2 + 0], 4);  // one arrive per softmax warp
+        mbar_init(&p_ready[i * 2 + 1], 4);
+        mbar_init(&o_full[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 8) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (lane == 0) {
+      const int col0 = head * HD;
+      auto load_tile = [&](uint8_t* dst, const CUtensorMap* m, uint64_t* bar, int row) {
+        mbar_expect_tx(bar, TILE_BYTES);
+        tma_load_2d(dst, m, bar, col0, row);
+        tma_load_2d(dst + HALF_BYTES, m, bar, col0 + 64, row);
+      };
+      load_tile(smem_q, &tmap_q, &q_full[0], q_row0);
+      int landed = p.kv_self_chunk;   // most recent remote chunk known to be present (chunks are visited in runs)
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        const int row = kv_tile_at(j_begin + j, p.kv_first_tile, n_kv_total) * BKV;
+        if (p.kv_flags) {
+          const int c0 = row / p.kv_chunk_rows;
+          const int c1 = (min(row + BKV, p.Lk) - 1) / p.kv_chunk_rows;
+          for (int c = c0; c <= c1; ++c) {
+            if (c == p.kv_self_chunk || c == landed) continue;
+            wait_kv_chunk(p.kv_flags, c, p.kv_epoch);
+            landed = c;
+          }
+        }
+        mbar_wait(&k_empty[s], ph ^ 1);
+        load_tile(smem_k + s * TILE_BYTES, &tmap_k, &k_full[s], row);
+        if (j == 0) load_tile(smem_q + TILE_BYTES, &tmap_q, &q_full[1], q_row0 + BQ);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        load_tile(smem_v + s * TILE_BYTES, &tmap_v, &v_full[s], row);
       }
     }
-    mbar_wait_a(bars + 8 * (K_EMPTY + s), ph ^ 1);
-    load_tile(sbase + OFF_K + s * TILE_BYTES, tmap_k, bars + 8 * (K_FULL + s), row);
-    if (j == 0) load_tile(sbase + OFF_Q + TILE_BYTES, tmap_q, bars + 8 * (Q_FULL + 1), u.q_row0 + BQ);
-    mbar_wait_a(bars + 8 * (V_EMPTY + s), ph ^ 1);
-    load_tile(sbase + OFF_V + s * TILE_BYTES, tmap_v, bars + 8 * (V_FULL + s), row);
-  }
-}
+  } else if (warp == 9) {
+    // ------------------------------------ MMA issuer --------------------------------------
+    constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major (d contiguous)
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);   // P K-major (TMEM), V MN-major
+    constexpr uint32_t hi_kmaj = smem_desc_hi(1024, 2);            // SBO 1024 B (8 rows x 128 B), 128B swizzle
+    const uint32_t lead = (lane == 0) ? 1u : 0u;
+    const uint32_t q_lo = smem_desc_lo(smem_u32(smem_q), 16);
+    const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
+    const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), HALF_BYTES);  // MN-major: LBO = distance of the 64-col atoms
+    // whole warp executes (uniform operands -> uniform registers); `lead` predicates the single issuing lane
+    auto issue_qk = [&](int i, int ks) {   // 8 K-steps = 2 swizzle boxes x 4 (batched issue)
+      const uint32_t a0 = q_lo + ((i * TILE_BYTES) >> 4), b0 = k_lo + ((ks * TILE_BYTES) >> 4);
+      tc_mma_ss_k4(tmem_base + i * 128, a0, hi_kmaj, b0, hi_kmaj, idesc_qk, 0);
+      tc_mma_ss_k4(tmem_base + i * 128, a0 + (HALF_BYTES >> 4), hi_kmaj, b0 + (HALF_BYTES >> 4), hi_kmaj, idesc_qk, 1);
+    };
+    auto issue_pv_half = [&](int i, int vs, int h, uint32_t accumulate) {   // 4 K-steps = 64 K/V rows of half h
+      tc_mma_ts_k4(tmem_base + 256 + i * 128, tmem_base + i * 128 + h * 32, v_lo + ((vs * TILE_BYTES + h * 4 * 2048) >> 4),
+                   hi_kmaj, idesc_pv, accumulate);
+    };
 
-// ------------------------------------ MMA issuer (whole warp, uniform issue) ----------------------
-__device__ __forceinline__ void mma_role(const Params& p, uint32_t sbase, uint32_t tmem_base) {
-  const Unit u = decode_unit(p);
-  const int n_kv = u.n_kv;
-  const uint32_t bars = sbase + OFF_BAR;
-  constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major (d contiguous)
-  constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);   // P K-major (TMEM), V MN-major
-  constexpr uint32_t hi_kmaj = smem_desc_hi(1024, 2);            // SBO 1024 B (8 rows x 128 B), 128B swizzle
-  const uint32_t q_lo = smem_desc_lo(sbase + OFF_Q, 16);
-  const uint32_t k_lo = smem_desc_lo(sbase + OFF_K, 16);
-  const uint32_t v_lo = smem_desc_lo(sbase + OFF_V, HALF_BYTES);  // MN-major: LBO = distance of the 64-col atoms
-  // whole warp executes (uniform operands -> uniform registers); elect.sync inside the wrappers picks the issuing lane
-  auto issue_qk = [&](int i, int ks) {   // 8 K-steps = 2 swizzle boxes x 4 (batched issue)
-    const uint32_t a0 = q_lo + ((i * TILE_BYTES) >> 4), b0 = k_lo + ((ks * TILE_BYTES) >> 4);
-    tc_mma_ss_k4(tmem_base + i * 128, a0, hi_kmaj, b0, hi_kmaj, idesc_qk, 0);
-    tc_mma_ss_k4(tmem_base + i * 128, a0 + (HALF_BYTES >> 4), hi_kmaj, b0 + (HALF_BYTES >> 4), hi_kmaj, idesc_qk, 1);
-  };
-  auto issue_pv_half = [&](int i, int vs, int h, uint32_t accumulate) {   // 4 K-steps = 64 K/V rows of half h
-    tc_mma_ts_k4(tmem_base + 256 + i * 128, tmem_base + i * 128 + h * 32, v_lo + ((vs * TILE_BYTES + h * 4 * 2048) >> 4),
-                 hi_kmaj, idesc_pv, accumulate);
-  };
-
-  // prologue: S_i(0) = Q_i K_0^T
-  mbar_wait_a(bars + 8 * K_FULL, 0);
-  for (int i = 0; i < 2; ++i) {
-    mbar_wait_a(bars + 8 * (Q_FULL + i), 0);
-    tc_fence_after();
-    issue_qk(i, 0);
-    tc_commit_a(bars + 8 * (S_FULL + i));
-  }
-  tc_commit_a(bars + 8 * K_EMPTY);
-
-  for (int j = 0; j < n_kv; ++j) {
-    const int vs = j % KV_STAGES;
-    const int ks = (j + 1) % KV_STAGES;
-    const bool has_next = (j + 1) < n_kv;
-    mbar_wait_a(bars + 8 * (V_FULL + vs), (j / KV_STAGES) & 1);
-#pragma unroll
+    // prologue: S_i(0) = Q_i K_0^T
+    mbar_wait(&k_full[0], 0);
     for (int i = 0; i < 2; ++i) {
-      mbar_wait_a(bars + 8 * (P_READY + i * 2 + 0), j & 1);
+      mbar_wait(&q_full[i], 0);
       tc_fence_after();
-      issue_pv_half(i, vs, 0, j > 0);
-      if (has_next && i == 0) mbar_wait_a(bars + 8 * (K_FULL + ks), ((j + 1) / KV_STAGES) & 1);
-      mbar_wait_a(bars + 8 * (P_READY + i * 2 + 1), j & 1);
+      issue_qk(i, 0);
+      tc_commit_p(lead, &s_full[i]);
+    }
+    tc_commit_p(lead, &k_empty[0]);
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int vs = j % KV_STAGES;
+      const int ks = (j + 1) % KV_STAGES;
+      const bool has_next = (j + 1) < n_kv;
+      mbar_wait(&v_full[vs], (j / KV_STAGES) & 1);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        mbar_wait(&p_ready[i * 2 + 0], j & 1);
+        tc_fence_after();
+        issue_pv_half(i, vs, 0, j > 0);
+        if (has_next && i == 0) mbar_wait(&k_full[ks], ((j + 1) / KV_STAGES) & 1);
+        mbar_wait(&p_ready[i * 2 + 1], j & 1);
+        tc_fence_after();
+        issue_pv_half(i, vs, 1, 1);
+        if (has_next) {
+          issue_qk(i, ks);
+          tc_commit_p(lead, &s_full[i]);
+        } else {
+          tc_commit_p(lead, &o_full[i]);
+        }
+      }
+      tc_commit_p(lead, &v_empty[vs]);
+      if (has_next) tc_commit_p(lead, &k_empty[ks]);
+    }
+  } else {
+    // ------------------------------------ softmax warpgroups ------------------------------
+    const int i = warp >> 2;    // which Q tile
+    const int quad = warp & 3;  // TMEM lane quadrant
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + i * 128 + lane_sel;
+    const uint32_t tO = tmem_base + 256 + i * 128 + lane_sel;
+    float c = p.scale_log2;
+    if (p.q_sumsq) {          // this thread's Q row carries its RMSNorm factor in the softmax scale
+      const int qrow = min(q_row0 + i * BQ + quad * 32 + lane, p.Lq - 1);
+      c *= rsqrtf(__ldg(p.q_sumsq + (long long)qrow * p.q_ss_ld) * p.q_inv_d + p.q_eps);
+    }
+    float m_cur = -INFINITY;  // running row max (scaled, log2 domain); reference point of P and O
+    float l = 0.f;            // running row sum of P
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
-      issue_pv_half(i, vs, 1, 1);
-      if (has_next) {
-        issue_qk(i, ks);
-        tc_commit_a(bars + 8 * (S_FULL + i));
-      } else {
-        tc_commit_a(bars + 8 * (O_FULL + i));
+      const int limit = p.Lk - kv_tile_at(j_begin + j, p.kv_first_tile, n_kv_total) * BKV;  // valid key columns (>=128: all)
+      // single pass: the whole 128-wide S row of this thread lives in registers (4 TMEM loads in flight, one wait)
+      uint32_t sr[4][32];
+      tmem_ld32(tS + 0, sr[0]);
+      tmem_ld32(tS + 32, sr[1]);
+      tmem_ld32(tS + 64, sr[2]);
+      tmem_ld32(tS + 96, sr[3]);
+      tmem_ld_wait();
+      if (limit < BKV) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (cc * 32 + e >= limit) sr[cc][e] = 0xff800000u;  // -inf: masked key column
+      }
+      // row max: 8 independent chains (the 128-long serial fmax chain was the critical path)
+      float m8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) m8[u] = fmaxf(__uint_as_float(sr[0][u]), __uint_as_float(sr[0][u + 8]));
+#pragma unroll
+      for (int e = 16; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[0][e]));
+#pragma unroll
+      for (int cc = 1; cc < 4; ++cc) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[cc][e]));
+      }
+      float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+      mx *= c;
+      // lazy rescale (warp-uniform decision because tcgen05.ld/st are warp-collective)
+      const bool need = (j > 0) && (mx > m_cur + RESCALE_THRESHOLD);
+      if (j == 0) {
+        m_cur = mx;
+      } else if (__any_sync(0xffffffffu, need)) {
+        const float m_new = fmaxf(m_cur, mx);
+        const float alpha = ex2(m_cur - m_new);
+        l *= alpha;
+        m_cur = m_new;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(tO + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+          tmem_st32(tO + cc * 32, r);
+        }
+      }
+      // P = exp2(S*c - m) (masked columns: exp2(-inf) = 0), 4 independent row-sum chains, bf16 pack into TMEM
+      float2 l4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_cur, -m_cur);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const int pr = e >> 1;   // pair index 0..15 inside the chunk
+          float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[cc][e]), __uint_as_float(sr[cc][e + 1])), c2, nm2);
+          float2 pv;
+          if ((pr & 7) < 3) {      // 6 of 16 pairs: FMA/ALU-pipe exponential
+            pv = exp2_poly2(x);
+          } else {                 // MUFU exponential
+            pv.x = ex2(x.x);
+            pv.y = ex2(x.y);
+          }
+          l4[pr & 3] = __fadd2_rn(l4[pr & 3], pv);
+          pk[pr] = pack_bf16x2(pv.x, pv.y);
+        }
+        tmem_st16(tS + cc * 16, pk);
+        if (cc & 1) {   // a 64-key half of P is complete: hand it to the MMA warp now
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[i * 2 + (cc >> 1)]);
+        }
+      }
+      {
+        const float2 a = __fadd2_rn(__fadd2_rn(l4[0], l4[1]), __fadd2_rn(l4[2], l4[3]));
+        l += a.x + a.y;
       }
     }
-    tc_commit_a(bars + 8 * (V_EMPTY + vs));
-    if (has_next) tc_commit_a(bars + 8 * (K_EMPTY + ks));
-  }
-}
 
-// ------------------------------------ softmax warpgroups (thread = one row of Q tile i) -----------
-__device__ __forceinline__ void softmax_role(const Params& p, uint32_t sbase, uint32_t tmem_base, int warp, int lane) {
-  const Unit u = decode_unit(p);
-  const int n_kv = u.n_kv;
-  const uint32_t bars = sbase + OFF_BAR;
-  const int i = warp >> 2;    // which Q tile
-  const int quad = warp & 3;  // TMEM lane quadrant
-  const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-  const uint32_t tS = tmem_base + i * 128 + lane_sel;
-  const uint32_t tO = tmem_base + 256 + i * 128 + lane_sel;
-  float c = p.scale_log2;
-  if (p.q_sumsq) {          // this thread's Q row carries its RMSNorm factor in the softmax scale
-    const int qrow = min(u.q_row0 + i * BQ + quad * 32 + lane, p.Lq - 1);
-    c *= rsqrtf(__ldg(p.q_sumsq + (long long)qrow * p.q_ss_ld) * p.q_inv_d + p.q_eps);
-  }
-  float m_cur = -INFINITY;  // running row max (scaled, log2 domain); reference point of P and O
-  float l = 0.f;            // running row sum of P
-
-  for (int j = 0; j < n_kv; ++j) {
-    mbar_wait_a(bars + 8 * (S_FULL + i), j & 1);
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(&o_full[i], 0);
     tc_fence_after();
-    const int limit = p.Lk - kv_tile_at(u.j_begin + j, p.kv_first_tile, u.n_kv_total) * BKV;  // valid key columns (>=128: all)
-    // single pass: the whole 128-wide S row of this thread lives in registers (4 TMEM loads in flight, one wait)
-    uint32_t sr[4][32];
-    tmem_ld32(tS + 0, sr[0]);
-    tmem_ld32(tS + 32, sr[1]);
-    tmem_ld32(tS + 64, sr[2]);
-    tmem_ld32(tS + 96, sr[3]);
-    tmem_ld_wait();
-    if (limit < BKV) {
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (cc * 32 + e >= limit) sr[cc][e] = 0xff800000u;  // -inf: masked key column
-    }
-    // row max: 8 independent chains (the 128-long serial fmax chain was the critical path)
-    float m8[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) m8[q] = fmaxf(__uint_as_float(sr[0][q]), __uint_as_float(sr[0][q + 8]));
-#pragma unroll
-    for (int e = 16; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[0][e]));
-#pragma unroll
-    for (int cc = 1; cc < 4; ++cc) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[cc][e]));
-    }
-    float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-    mx *= c;
-    // lazy rescale (warp-uniform decision because tcgen05.ld/st are warp-collective)
-    const bool need = (j > 0) && (mx > m_cur + RESCALE_THRESHOLD);
-    if (j == 0) {
-      m_cur = mx;
-    } else if (__any_sync(0xffffffffu, need)) {
-      const float m_new = fmaxf(m_cur, mx);
-      const float alpha = ex2(m_cur - m_new);
-      l *= alpha;
-      m_cur = m_new;
+    const int row = q_row0 + i * BQ + quad * 32 + lane;
+    if (slice_slot >= 0 && p.split > 1) {
+      // one slice of the K/V stream: leave (O, m, l) for attn_merge_kernel
+      const long long prow = (long long)slice_slot * (2 * BQ) + i * BQ + quad * 32 + lane;
+      float4* dst = reinterpret_cast<float4*>(p.ws_o + prow * HD);
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t r[32];
         tmem_ld32(tO + cc * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-        tmem_st32(tO + cc * 32, r);
+        for (int g = 0; g < 8; ++g)
+          dst[cc * 8 + g] = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                        __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
       }
-    }
-    // P = exp2(S*c - m) (masked columns: exp2(-inf) = 0), 4 independent row-sum chains, bf16 pack into TMEM
-    float2 l4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-    const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_cur, -m_cur);
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      uint32_t pk[16];
-#pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const int pr = e >> 1;   // pair index 0..15 inside the chunk
-        float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[cc][e]), __uint_as_float(sr[cc][e + 1])), c2, nm2);
-        float2 pv;
-        if (pr < SVI_ATTN_POLY16) {   // FMA/ALU-pipe exponential
-          pv = exp2_poly2(x);
-        } else {                      // MUFU exponential
-          pv.x = ex2(x.x);
-          pv.y = ex2(x.y);
-        }
-        l4[pr & 3] = __fadd2_rn(l4[pr & 3], pv);
-        pk[pr] = pack_bf16x2(pv.x, pv.y);
-      }
-      tmem_st16(tS + cc * 16, pk);
-      if (cc & 1) {   // a 64-key half of P is complete: hand it to the MMA warp now
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_a(bars + 8 * (P_READY + i * 2 + (cc >> 1)));
-      }
-    }
-    {
-      const float2 a = __fadd2_rn(__fadd2_rn(l4[0], l4[1]), __fadd2_rn(l4[2], l4[3]));
-      l += a.x + a.y;
-    }
-  }
-
-  // epilogue: O / l -> bf16 -> global
-  mbar_wait_a(bars + 8 * (O_FULL + i), 0);
-  tc_fence_after();
-  const int row = u.q_row0 + i * BQ + quad * 32 + lane;
-  if (u.slice_slot >= 0 && p.split > 1) {
-    // one slice of the K/V stream: leave (O, m, l) for attn_merge_kernel
-    const long long prow = (long long)u.slice_slot * (2 * BQ) + i * BQ + quad * 32 + lane;
-    float4* dst = reinterpret_cast<float4*>(p.ws_o + prow * HD);
-#pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-      uint32_t r[32];
-      tmem_ld32(tO + cc * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        dst[cc * 8 + g] = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
-                                      __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
-    }
-    p.ws_ml[prow] = make_float2(m_cur, l);
-  } else {
+      p.ws_ml[prow] = make_float2(m_cur, l);
+    } else {
     const float inv_l = 1.0f / l;
-    __nv_bfloat16* orow = p.O + (long long)row * p.ldo + u.head * HD;
+    __nv_bfloat16* orow = p.O + (long long)row * p.ldo + head * HD;
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
       uint32_t r[32];
@@ -424,50 +410,7 @@ __device__ __forceinline__ void softmax_role(const Params& p, uint32_t sbase, ui
         }
       }
     }
-  }
-}
-
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t tmem_slot = sbase + OFF_BAR + 8 * NUM_BARS;
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-  }
-  if (warp == 9) {
-    if (lane == 0) {
-      const uint32_t bars = sbase + OFF_BAR;
-      for (uint32_t b = 0; b < NUM_BARS; ++b)
-        mbar_init_a(bars + 8 * b, (b >= P_READY && b < O_FULL) ? 4u : 1u);   // P_READY: one arrive per softmax warp
-      fence_mbar_init();
     }
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (warp >= 8) {
-    setmaxnreg_dec();
-    if (warp == 8) {
-      if (lane == 0) tma_role(&tmap_q, &tmap_k, &tmap_v, p, sbase);
-    } else if (warp == 9) {
-      mma_role(p, sbase, tmem_base);
-    }
-  } else {
-    setmaxnreg_inc();
-    softmax_role(p, sbase, tmem_base, warp, lane);
   }
 
   tc_fence_before();

@@ -1,0 +1,95 @@
+"""GPU: the reference harness' call sequence in ONE pass (test_svi.py:316-351, 457-470, 472-483) on checkpoint FILES:
+
+    ModelManager(device="cpu") -> load_models([[dit shard, dit shard], vae file]) -> load_lora_v2(lora file)
+    -> SVIVideoPipeline.from_model_manager(device="cuda") -> enable_vram_management() -> pipe(...) x 2 chained clips
+    -> save_video
+
+The DiT files hold the REAL Wan2.1-T2V-1.3B architecture (random init, 1.42 B parameters, key-set fingerprint 9269f8db…),
+so detection, meta construction, shard merging, dtype casting and the static LoRA merge run exactly as for a released
+checkpoint; the clip itself is tiny (9 frames, 64x96, 2 steps).  The result must equal the same pipeline built from
+in-memory models (no files) whose LoRA was merged by hand."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tools import synth, synth_vae
+
+pytestmark = [pytest.mark.gpu, pytest.mark.slow]
+H, W, FRAMES, STEPS, CTX = 64, 96, 9, 2, 32
+
+
+def _prompter(prompt, positive=True):
+    g = torch.Generator().manual_seed(21 if positive else 22)
+    return torch.randn(1, CTX, 4096, generator=g)
+
+
+def test_files_to_video_call_sequence(tmp_path):
+    from safetensors.torch import save_file
+    from diffsynth import ModelManager, SVIVideoPipeline, save_video
+    from diffsynth.models.wan_video_dit import WanModel
+    from diffsynth.models.wan_video_vae import WanVideoVAE
+    cfg = synth.CFG_T2V_1_3B
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.to(torch.bfloat16).contiguous() for k, v in synth.make_dit_state_dict(cfg, seed=5).items()}
+    keys = sorted(sd)
+    shards = [str(tmp_path / f"diffusion_pytorch_model-0000{i + 1}-of-00002.safetensors") for i in range(2)]
+    save_file({k: sd[k] for k in keys[::2]}, shards[0])
+    save_file({k: sd[k] for k in keys[1::2]}, shards[1])
+    vae_sd = {k[len("model."):]: v.to(torch.bfloat16).contiguous() for k, v in synth_vae.make_vae_state_dict(seed=0).items()}
+    vae_file = str(tmp_path / "Wan2.1_VAE.safetensors")
+    save_file(vae_sd, vae_file)
+    # an SVI-style LoRA file: 'pipe.dit.'-prefixed peft keys, rank 4, on q / o / ffn.0 of two blocks
+    g = torch.Generator().manual_seed(9)
+    lora, targets = {}, ["blocks.0.self_attn.q", "blocks.0.self_attn.o", "blocks.7.ffn.0", "blocks.29.cross_attn.k"]
+    for t in targets:
+        o, i = sd[t + ".weight"].shape
+        lora[f"pipe.dit.{t}.lora_A.default.weight"] = (torch.randn(4, i, generator=g) * 0.05).to(torch.bfloat16)
+        lora[f"pipe.dit.{t}.lora_B.default.weight"] = (torch.randn(o, 4, generator=g) * 0.05).to(torch.bfloat16)
+    lora_file = str(tmp_path / "svi_lora.safetensors")
+    save_file(lora, lora_file)
+
+    # ---- the harness sequence
+    mm = ModelManager(torch_dtype=torch.bfloat16, device="cpu")
+    mm.load_models([shards, vae_file])
+    mm.load_lora_v2(lora_file, lora_alpha=1.0)
+    pipe = SVIVideoPipeline.from_model_manager(mm, torch_dtype=torch.bfloat16, device="cuda", is_test=True)
+    pipe.enable_vram_management(num_persistent_param_in_dit=6 * 10 ** 9)
+    assert isinstance(pipe.dit, WanModel) and isinstance(pipe.vae, WanVideoVAE)
+    assert next(pipe.dit.parameters()).is_cuda and next(pipe.vae.parameters()).is_cuda
+    pipe.prompter = _prompter                                  # umT5-XXL (11 GB) is not written to disk for this test
+    kw = dict(prompt="a prompt", negative_prompt="neg", num_inference_steps=STEPS, cfg_scale={"text": 5.0}, tiled=False,
+              height=H, width=W, num_frames=FRAMES, progress_bar_cmd=lambda x: x)
+    clips = [pipe(seed=42 * k, **kw) for k in range(2)]
+    assert all(len(c) == FRAMES and c[0].size == (W, H) for c in clips)
+    out = save_video(clips[0] + clips[1], str(tmp_path / "out.mp4"), fps=16, quality=5)
+    assert os.path.exists(out)
+
+    # ---- the same models built in memory, LoRA merged by hand in fp32
+    merged = {k: v.float() for k, v in sd.items()}
+    for t in targets:
+        a = lora[f"pipe.dit.{t}.lora_A.default.weight"].float()
+        b = lora[f"pipe.dit.{t}.lora_B.default.weight"].float()
+        merged[t + ".weight"] = merged[t + ".weight"] + b @ a
+    got_w = dict(pipe.dit.named_parameters())
+    for t in targets:
+        want = merged[t + ".weight"].to(torch.bfloat16)
+        diff = (got_w[t + ".weight"].detach().cpu().float() - want.float()).abs().max().item()
+        assert diff <= 2 ** -8 * want.float().abs().max().item(), (t, diff)     # one bf16 ulp of the largest weight
+    dit = WanModel(**cfg).eval()
+    dit.load_state_dict({k: v.to(torch.bfloat16) for k, v in merged.items()})
+    for t in targets:                                           # identical bits to the file path's merge
+        dict(dit.named_parameters())[t + ".weight"].data.copy_(got_w[t + ".weight"].detach().cpu())
+    vae = WanVideoVAE().eval()
+    vae.load_state_dict({"model." + k: v for k, v in vae_sd.items()})
+    mm2 = ModelManager(torch_dtype=torch.bfloat16, device="cuda")
+    mm2.add_model("wan_video_dit", dit.to(torch.bfloat16).to("cuda"))
+    mm2.add_model("wan_video_vae", vae.to(torch.bfloat16).to("cuda"))
+    pipe2 = SVIVideoPipeline.from_model_manager(mm2, torch_dtype=torch.bfloat16, device="cuda", is_test=True)
+    pipe2.prompter = _prompter
+    ref = pipe2(seed=42, **kw)
+    a = np.stack([np.array(f) for f in clips[1]]).astype(np.int32)
+    b = np.stack([np.array(f) for f in ref]).astype(np.int32)
+    print(f"files vs in-memory clip: max |diff| = {np.abs(a - b).max()} levels")
+    assert np.abs(a - b).max() <= 1            # same weights, same kernels (fp32 atomics may reassociate)

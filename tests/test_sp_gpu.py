@@ -1,0 +1,24 @@
+"""GPU (>= 2 devices): the multi-GPU plan (CFG-parallel x sequence-parallel, K|V peer exchange) under torchrun, against
+the single-GPU kernels AND against the CPU oracle at shapes whose rows per rank are not a multiple of the attention tile
+(tools/sp_check.py: L = 1260 and the benchmark's L = 32760).  Skipped on boxes with fewer GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("n", [2, 4])
+def test_plan_matches_single_gpu_and_oracle(n):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29650 + n), os.path.join(ROOT, "tools", "sp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    print(r.stdout[-6000:])
+    assert r.returncode == 0 and "SP_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -440,6 +440,20 @@ def sec_perf_ew():
         timed(lambda: nv.rmsnorm_rope(qkv[:, :d], ss, 0, 1e-6, w, cos, sin, 0), L * d * 4, "rmsnorm_rope (q slice of qkv)", cold)
 
 
+def sec_perf_attn_quick():
+    """Self-attention at the bench shape only (with the launch-plan workspace), for A/B runs of kernel variants
+    (SVI_B200_LIB selects the library)."""
+    g = torch.Generator(device="cpu").manual_seed(6)
+    scale = 128 ** -0.5
+    L, H = 32760, 12
+    q, k, v = (torch.randn(L, H * 128, generator=g).to(dev, torch.bfloat16) for _ in range(3))
+    out = torch.empty(L, H * 128, device=dev, dtype=torch.bfloat16)
+    ws = torch.empty(nv.attention_workspace_bytes(L, L, H) // 4 + 1, device=dev)
+    ms = time_ms(lambda: nv.attention(q, k, v, out, H, scale, workspace=ws), iters=8, warm=3)
+    fl = 4.0 * L * L * H * 128
+    print(f"[PERF] attn L={L} H={H} + workspace lib={os.path.basename(nv.lib_path())}: {ms:.3f} ms = {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+
+
 def sec_perf_attn():
     g = torch.Generator(device="cpu").manual_seed(6)
     scale = 128 ** -0.5
