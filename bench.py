@@ -423,9 +423,17 @@ def main():
             tt = torch.tensor([e2e_ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_ms = tt.item()
+        # how much of an e2e step is the per-step prompt work (H2D of the embeddings + text MLP + every layer's K|V projection)
+        ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ca.record()
+        for _ in range(3):
+            eng.context_state(ctx_pos_host.to(dev, non_blocking=True), clip_dev)
+        cb.record()
+        torch.cuda.synchronize()
+        ctx_ms = ca.elapsed_time(cb) / 3
         h2d = lat_host.numel() * 4 + (int(own0) + int(own1)) * ctx_pos_host.numel() * 4
         e2e = {"value": f / (CLIP_STEPS * e2e_ms / 1e3), "unit": "latent_frames/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4, "context_state_ms_per_prompt": ctx_ms,
                "api": "SVIVideoPipeline.denoise_step (WanDiTEngine.context_state + the plan's forwards + svi_cfg_euler_step), "
                       "pinned host buffers per rank",
                "mode": "CUDA-graph replay of each forward" if eng.use_graphs else "eager"}
