@@ -55,6 +55,15 @@ typedef struct svi_gemm_epilogue {
   float* sumsq;          /* [M, sumsq_groups] f32, accumulated with atomicAdd; or NULL */
   int32_t sumsq_groups;  /* number of column groups that are accumulated (columns beyond are skipped) */
   int32_t sumsq_group_cols; /* width of one group in columns; multiple of 32 */
+  /* ---- LayerNorm folded into the GEMM (M > 128 only; both sides optional, NULL = off) ------------------------------
+   * Consumer: A = bf16(x[m,k] * g[k]) of the UN-normalised rows x and ln_stats[m] = (sum_k x, sum_k x^2) over ln_dim
+   * columns; the epilogue reconstructs the product of the normalised, modulated rows:
+   *     acc' = rstd_m * (acc - mean_m * ln_u[n]) ,  ln_u = W g   (then + bias: pass c = W t + b as `bias`)
+   *   = ( LayerNorm(x; ln_eps) * g + t ) @ W^T + b   — nn.LayerNorm + modulate + Linear, wan_video_dit.py:358,369-373.
+   * Producer: from the final value v (after gate / residual) also write a_next[m,n] = bf16(v * g_next[n]) — the folded
+   * A operand of the NEXT GEMM — and accumulate row_stats[m] += (sum_n v, sum_n v^2) with atomicAdd. */
+  const float* ln_stats; const float* ln_u; int32_t ln_dim; float ln_eps;
+  void* a_next; int64_t ld_an; const float* g_next; float* row_stats;
 } svi_gemm_epilogue;
 
 /*
@@ -201,6 +210,16 @@ int svi_cast_bf16_to_f32(const void* src_bf16, float* dst, int64_t n, void* stre
  * GELU_ERF): the two-term bf16 form of an f32 GEMM input (time / text / image embedding MLPs, wan_video_dit.py:429-452). */
 int svi_split_f32_to_bf16x2(const float* src, int64_t lds, int32_t M, int32_t K, int32_t act, void* dst_bf16,
                             int64_t ldd, int32_t lo_col, void* stream);
+/*
+ * Per-timestep vectors of the LayerNorm fold (svi_gemm_epilogue.ln_*):
+ * svi_ln_fold_prepare  mods f32 [6*layers, D] (rows shift/scale/gate of self-attention, shift/scale/gate of the FFN per
+ *                      block, wan_video_dit.py:356-357) -> g f32 [layers, 2, D] = 1 + scale and rows bf16
+ *                      [layers, 2, 4, D] = (g_hi, g_lo, t_hi, t_lo) two-term forms of g and the shift t;
+ * svi_ln_fold_combine  o4 f32 [4, N] = rows @ W^T (one svi_gemm_bf16 with M = 4) -> u = o4[0] + o4[1] = W g and
+ *                      c = o4[2] + o4[3] + bias = W t + b.
+ */
+int svi_ln_fold_prepare(const float* mods, int32_t layers, int32_t D, float* g_out, void* rows_bf16, void* stream);
+int svi_ln_fold_combine(const float* o4, int32_t N, const float* bias, float* u, float* c, void* stream);
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (row-sum accumulators of a whole forward in one node). */
 int svi_zero(void* ptr, size_t bytes, void* stream);
 
@@ -248,6 +267,14 @@ typedef struct svi_conv_desc {
   int32_t n_split; int64_t split_offset;
   const float* bias;
   const float* residual; int64_t res_frame_stride; int32_t res_ld;
+  /* Fused producer of the NEXT conv's input (optional; next_ring == NULL: off).  Requires C_out <= 256 and n_split == 0.
+   * For every output pixel: y = act(v / max(||v||_2, 1e-12) * sqrt(C_out) * next_gamma) with v = the conv output
+   * (incl. bias / residual), act = SiLU if next_silu, written as bf16 to next_ring + next_slot[t]*next_frame_stride +
+   * pixel*next_ld (channels [C_out, next_ld) are left untouched: the caller keeps them zero).  next_gamma == NULL: plain
+   * cast.  write_f32 == 0 additionally drops the fp32 output (`out` may then be NULL).  Replaces RMS_norm + nn.SiLU in
+   * front of the second CausalConv3d of a ResidualBlock and between blocks (wan_video_vae.py:55-70, 206-210). */
+  void* next_ring; int64_t next_frame_stride; int32_t next_ld; int32_t next_slot[4];
+  const float* next_gamma; int32_t next_silu; int32_t write_f32;
 } svi_conv_desc;
 int svi_conv3d_causal(const svi_conv_desc* d, void* stream);
 

@@ -41,7 +41,7 @@ constexpr int HALF_BYTES = 128 * 64 * 2;   // one 128-row x 64-col swizzled box 
 constexpr int TILE_BYTES = 2 * HALF_BYTES;  // 128 x 128 bf16 (32 KB)
 constexpr int NUM_THREADS = 384;   // 12 warps = 3 warpgroups: setmaxnreg is a warpgroup-wide instruction
 #ifndef SVI_ATTN_POLY16
-#define SVI_ATTN_POLY16 3            // exponentials on the FMA pipes: this many of every 16 element pairs
+#define SVI_ATTN_POLY16 6            // exponentials on the FMA pipes: this many of every 16 element pairs
 #endif
 #ifndef SVI_ATTN_OTHER_REGS
 #define SVI_ATTN_OTHER_REGS 56

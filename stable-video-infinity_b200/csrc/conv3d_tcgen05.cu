@@ -8,8 +8,11 @@
 // from the (output frame, k_t) -> ring slot table (history frames stay in the ring: no F.pad / torch.cat
 // cache copies as in the reference, wan_video_vae.py:44-52, 214-232).  Weights are pre-packed
 // [C_out, (k_t,k_h,k_w,C_in padded to 64)] and stream through a 2-D TMA like a GEMM B operand.
-// Warp roles / pipelines are those of gemm_tcgen05.cu.  Epilogue: + bias, + fp32 residual (ResidualBlock
-// skip), optional channel split into two frames (upsample3d time_conv, wan_video_vae.py:153-156), fp32 NHWC out.
+// Warp roles / pipelines are those of gemm_tcgen05.cu (operand ring of 4..7 stages depending on the N tile).  Epilogue:
+// + bias, + fp32 residual (ResidualBlock skip), optional channel split into two frames (upsample3d time_conv,
+// wan_video_vae.py:153-156), fp32 NHWC out — and, fused, the NEXT conv's input: RMS_norm + SiLU (:55-70, 206-210) of the
+// output pixel (its whole channel vector sits in one accumulator row) written as bf16 straight into the next conv's frame
+// ring, so the activation between the two convs of a ResidualBlock never exists in fp32 and no staging pass runs.
 #include "common.cuh"
 #include "../../include/svi_b200.h"
 
@@ -19,14 +22,13 @@ namespace conv {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int MAX_BN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int RING_BYTES = 4 * (A_STAGE_BYTES + MAX_BN * BK * 2);   // 192 KB of operand stages: 4 at BN = 256 ... 7 at BN = 96
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
 
 struct Params {
   int H, W, T;                 // output height / width / frames of this launch
@@ -44,6 +46,15 @@ struct Params {
   const float* residual;       // same layout as out (frame stride res_frame_stride, ld res_ld) or null
   long long res_frame_stride;
   int res_ld;
+  int stages, stage_bytes;     // operand ring: stage_bytes = A tile + BN x 64 bf16 rounded to 1 KB
+  // fused producer of the NEXT conv's input (RMS_norm + SiLU + bf16 staging, wan_video_vae.py:55-70,206-210):
+  __nv_bfloat16* next_ring;    // bf16 [slots][H][W][next_ld] or null
+  long long next_frame_stride; // elements between ring slots
+  int next_ld;
+  int next_slot[4];            // ring slot of output frame t
+  const float* next_gamma;     // [C_out] RMS-norm weight, null: plain cast
+  int next_silu;
+  int write_f32;               // 0: the fp32 output is not needed (only the normalised bf16 is consumed)
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0,
@@ -60,12 +71,14 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;
-  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;
+  uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  const int STAGES = p.stages;
+  const int STAGE_BYTES = p.stage_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,7 +96,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < STAGES; ++i) {
+      for (int i = 0; i < MAX_STAGES; ++i) {
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], 1);
       }
@@ -179,6 +192,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * MAX_BN + (static_cast<uint32_t>(quad * 32) << 16);
+      float ssq = 0.f;            // sum of squares of this pixel's output channels (fused RMS norm of the next conv's input)
 #pragma unroll 1
       for (int c = 0; c < p.BN / 16; ++c) {
         const int n0 = n_blk * p.BN + c * 16;
@@ -203,12 +217,60 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                                                                 pix * p.res_ld + n);
               v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
             }
-            float* dst;
-            if (p.n_split > 0 && n >= p.n_split)
-              dst = p.out + p.split_offset + (long long)t * p.out_frame_stride + pix * p.out_ld + (n - p.n_split);
-            else
-              dst = p.out + (long long)t * p.out_frame_stride + pix * p.out_ld + n;
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            ssq += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+            if (p.write_f32) {
+              float* dst;
+              if (p.n_split > 0 && n >= p.n_split)
+                dst = p.out + p.split_offset + (long long)t * p.out_frame_stride + pix * p.out_ld + (n - p.n_split);
+              else
+                dst = p.out + (long long)t * p.out_frame_stride + pix * p.out_ld + n;
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          }
+        }
+      }
+      if (p.next_ring) {
+        // second pass over the accumulator (still in TMEM): y = silu(v / max(||v||, 1e-12) * sqrt(C) * gamma) -> bf16 into the
+        // next conv's input ring.  Launch side guarantees one N tile (the whole channel vector of a pixel is in this row).
+        const float mul = p.next_gamma ? sqrtf((float)p.C_out) / fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+        __nv_bfloat16* nrow = p.next_ring + (long long)p.next_slot[t] * p.next_frame_stride + pix * p.next_ld;
+#pragma unroll 1
+        for (int c = 0; c < p.BN / 16; ++c) {
+          const int n0 = c * 16;
+          if (n0 >= p.C_out) break;
+          uint32_t r[16];
+          tmem_ld16(t_base + c * 16, r);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const int n = n0 + j4 * 4;
+              if (n >= p.C_out) break;
+              float v[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j4 * 4 + j]);
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+              }
+              if (p.residual) {
+                const float4 q = *reinterpret_cast<const float4*>(p.residual + (long long)t * p.res_frame_stride +
+                                                                  pix * p.res_ld + n);
+                v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+              }
+              if (p.next_gamma) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(p.next_gamma + n));
+                v[0] *= mul * g.x; v[1] *= mul * g.y; v[2] *= mul * g.z; v[3] *= mul * g.w;
+              }
+              if (p.next_silu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = silu(v[j]);
+              }
+              uint2 pk;
+              pk.x = pack_bf16x2(v[0], v[1]);
+              pk.y = pack_bf16x2(v[2], v[3]);
+              *reinterpret_cast<uint2*>(nrow + n) = pk;
+            }
           }
         }
       }
@@ -233,7 +295,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
 extern "C" int svi_conv3d_causal(const svi_conv_desc* d, void* stream) {
   using namespace svi;
   using namespace svi::conv;
-  SVI_REQUIRE(d && d->x_ring && d->w_packed && d->out, "svi_conv3d_causal: null pointer");
+  SVI_REQUIRE(d && d->x_ring && d->w_packed && (d->out || (d->next_ring && !d->write_f32)), "svi_conv3d_causal: null pointer");
   SVI_REQUIRE(d->H > 0 && d->W > 0 && d->T > 0 && d->T <= 4, "svi_conv3d_causal: need 1 <= T <= 4, H, W > 0");
   SVI_REQUIRE(d->kt >= 1 && d->kt <= 3 && d->kh >= 1 && d->kh <= 3 && d->kw >= 1 && d->kw <= 3,
               "svi_conv3d_causal: kernel extents must be in [1,3]");
@@ -302,6 +364,21 @@ extern "C" int svi_conv3d_causal(const svi_conv_desc* d, void* stream) {
   p.out = d->out; p.out_frame_stride = d->out_frame_stride; p.out_ld = d->out_ld;
   p.n_split = d->n_split; p.split_offset = d->split_offset;
   p.bias = d->bias; p.residual = d->residual; p.res_frame_stride = d->res_frame_stride; p.res_ld = d->res_ld;
+  p.stage_bytes = (A_STAGE_BYTES + BN * BK * 2 + 1023) / 1024 * 1024;
+  p.stages = RING_BYTES / p.stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  p.next_ring = reinterpret_cast<__nv_bfloat16*>(d->next_ring);
+  p.next_frame_stride = d->next_frame_stride;
+  p.next_ld = d->next_ld;
+  for (int t = 0; t < 4; ++t) p.next_slot[t] = d->next_slot[t];
+  p.next_gamma = d->next_gamma;
+  p.next_silu = d->next_silu;
+  p.write_f32 = d->next_ring ? d->write_f32 : 1;
+  if (d->next_ring) {
+    SVI_REQUIRE(d->C_out <= BN && d->n_split == 0, "svi_conv3d_causal: the fused next-input producer needs one N tile (C_out <= 256) and no channel split");
+    SVI_REQUIRE(d->next_ld >= d->C_out && d->next_ld % 4 == 0, "svi_conv3d_causal: next_ld must be >= C_out and a multiple of 4");
+    for (int t = 0; t < d->T; ++t) SVI_REQUIRE(d->next_slot[t] >= 0, "svi_conv3d_causal: next_slot must be >= 0");
+  }
 
   static bool attr_set = false;
   if (!attr_set) {

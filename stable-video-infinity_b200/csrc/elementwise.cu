@@ -350,6 +350,37 @@ __global__ void add_rows_kernel(const float* __restrict__ table, const float* __
   }
 }
 
+// LN fold, per timestep: from the modulation rows of every block build (a) the fp32 column scales g = 1 + scale the
+// producer epilogues multiply into the next operand and (b) the two-term bf16 rows [g_hi; g_lo; t_hi; t_lo] whose products
+// with W give u = W g and W t.   mods f32 [6 L, D] rows (shift_a, scale_a, gate_a, shift_m, scale_m, gate_m) per block;
+// g_out f32 [L, 2, D]; rows_out bf16 [L, 2, 4, D]  (index 1: 0 = self-attention LN, 1 = FFN LN).
+__global__ void fold_prepare_kernel(const float* __restrict__ mods, int L, int D, float* __restrict__ g_out,
+                                    __nv_bfloat16* __restrict__ rows_out) {
+  const long long n = (long long)L * 2 * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % D);
+    const int which = (int)((i / D) % 2);
+    const int l = (int)(i / (2LL * D));
+    const float shift = mods[((long long)l * 6 + which * 3 + 0) * D + k];
+    const float g = 1.0f + mods[((long long)l * 6 + which * 3 + 1) * D + k];
+    g_out[i] = g;
+    __nv_bfloat16* r = rows_out + ((long long)l * 2 + which) * 4 * D + k;
+    const __nv_bfloat16 gh = __float2bfloat16_rn(g), th = __float2bfloat16_rn(shift);
+    r[0] = gh;
+    r[D] = __float2bfloat16_rn(g - __bfloat162float(gh));
+    r[2 * D] = th;
+    r[3 * D] = __float2bfloat16_rn(shift - __bfloat162float(th));
+  }
+}
+// u[n] = o4[0,n] + o4[1,n];  c[n] = o4[2,n] + o4[3,n] + bias[n]   (o4 = the [4, N] products of the rows above with W)
+__global__ void fold_combine_kernel(const float* __restrict__ o4, int N, const float* __restrict__ bias,
+                                    float* __restrict__ u, float* __restrict__ c) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    u[n] = o4[n] + o4[N + n];
+    c[n] = o4[2LL * N + n] + o4[3LL * N + n] + (bias ? bias[n] : 0.f);
+  }
+}
+
 inline int grid_for(long long n, int block) {
   long long g = (n + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -510,6 +541,19 @@ extern "C" int svi_split_f32_to_bf16x2(const float* src, int64_t lds, int32_t M,
   split_f32_bf16x2_kernel<<<grid_for((long long)M * K, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, lds, M, K, act, reinterpret_cast<__nv_bfloat16*>(dst_bf16), ldd, lo_col);
   SVI_CUDA_LAUNCH_CHECK("svi_split_f32_to_bf16x2");
+  return SVI_OK;
+}
+extern "C" int svi_ln_fold_prepare(const float* mods, int32_t layers, int32_t D, float* g_out, void* rows_bf16, void* stream) {
+  SVI_REQUIRE(mods && g_out && rows_bf16 && layers > 0 && D > 0, "svi_ln_fold_prepare: bad arguments");
+  fold_prepare_kernel<<<grid_for((long long)layers * 2 * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mods, layers, D, g_out, reinterpret_cast<__nv_bfloat16*>(rows_bf16));
+  SVI_CUDA_LAUNCH_CHECK("svi_ln_fold_prepare");
+  return SVI_OK;
+}
+extern "C" int svi_ln_fold_combine(const float* o4, int32_t N, const float* bias, float* u, float* c, void* stream) {
+  SVI_REQUIRE(o4 && u && c && N > 0, "svi_ln_fold_combine: bad arguments");
+  fold_combine_kernel<<<grid_for(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(o4, N, bias, u, c);
+  SVI_CUDA_LAUNCH_CHECK("svi_ln_fold_combine");
   return SVI_OK;
 }
 extern "C" int svi_zero(void* ptr, size_t bytes, void* stream) {

@@ -32,7 +32,7 @@ constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int STAGES = 6;       // 7 fit but measured 1-2 % slower
 constexpr int GROUP_M = 4;      // measured: 1..4 equal on M >> N shapes, 4..8 best on square ones
-constexpr int VEC_BYTES = 2 * 2 * BN * 4;   // bias and gate of the tile's 256 columns, double buffered by accumulator
+constexpr int VEC_BYTES = 2 * 4 * BN * 4;   // bias, gate, LN-fold u and next-operand scale of the tile's 256 columns, double buffered by accumulator
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + VEC_BYTES;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> even CTA
 
@@ -48,6 +48,17 @@ struct Epi {
   float* sumsq;
   int sumsq_groups;
   int sumsq_group_cols;
+  // LayerNorm folded into this GEMM (consumer side): A holds bf16(x * g) of the UN-normalised rows x; with the row statistics
+  // (sum x, sum x^2) the epilogue reconstructs  LN(x)*g + t  times W^T  =  r_m (acc - mu_m u_n) + c_n,  u = W g, c = W t + b
+  // (c arrives as `bias`)
+  const float* ln_stats;   // [M, 2] or null
+  const float* ln_u;       // [N]
+  float ln_inv_d, ln_eps;
+  // producer side: besides out, emit the NEXT GEMM's folded operand and row statistics from the final value v
+  __nv_bfloat16* a_next;   // [M, ld_an] = bf16(v * g_next[n]) or null
+  long long ld_an;
+  const float* g_next;     // [N]
+  float* row_stats;        // [M, 2] += (sum v, sum v^2) over this launch's columns (atomicAdd)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -274,13 +285,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       // per-column vectors of this tile -> shared memory while the K loop still runs (every lane needs the same 8
       // values at a time: an L1/L2 round trip per group of 8 columns was half of all epilogue stall samples)
-      float* sbias = vec_smem + acc * 2 * BN;
+      float* sbias = vec_smem + acc * 4 * BN;
       float* sgate = sbias + BN;
+      float* slnu = sbias + 2 * BN;
+      float* sgnext = sbias + 3 * BN;
       {
         const int t = threadIdx.x - 64;          // 0..255 = column inside the tile
         const int n = n_blk * BN + t;
         if (ep.bias) sbias[t] = n < N ? __ldg(ep.bias + n) : 0.f;
         if (ep.gate) sgate[t] = n < N ? __ldg(ep.gate + n) : 0.f;
+        if (ep.ln_stats) slnu[t] = n < N ? __ldg(ep.ln_u + n) : 0.f;
+        if (ep.a_next) sgnext[t] = n < N ? __ldg(ep.g_next + n) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // epilogue warps only
       }
       mbar_wait_a(bar(TMEM_FULL + acc), acc_phase);
@@ -288,6 +303,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t t_base = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
       float ss = 0.f;
       int ss_group = -1;
+      float ln_r = 1.f, ln_nmu = 0.f;     // LN fold: rstd and -mean of this thread's row
+      if (ep.ln_stats && row_ok) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + row);
+        const float mean = st.x * ep.ln_inv_d;
+        ln_r = rsqrtf(fmaxf(st.y * ep.ln_inv_d - mean * mean, 0.f) + ep.ln_eps);
+        ln_nmu = -mean;
+      }
+      float ps = 0.f, pq = 0.f;           // producer: sum / sum of squares of the final values of this row (this tile half)
 #pragma unroll 1
       for (int c = col_half * 4; c < col_half * 4 + 4; ++c) {
         const int n0 = n_blk * BN + c * 32;
@@ -321,6 +344,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j8 * 8 + j]);
+            if (ep.ln_stats) {
+              const float4 u0 = *reinterpret_cast<const float4*>(slnu + c * 32 + j8 * 8);
+              const float4 u1 = *reinterpret_cast<const float4*>(slnu + c * 32 + j8 * 8 + 4);
+              v[0] = ln_r * fmaf(ln_nmu, u0.x, v[0]); v[1] = ln_r * fmaf(ln_nmu, u0.y, v[1]);
+              v[2] = ln_r * fmaf(ln_nmu, u0.z, v[2]); v[3] = ln_r * fmaf(ln_nmu, u0.w, v[3]);
+              v[4] = ln_r * fmaf(ln_nmu, u1.x, v[4]); v[5] = ln_r * fmaf(ln_nmu, u1.y, v[5]);
+              v[6] = ln_r * fmaf(ln_nmu, u1.z, v[6]); v[7] = ln_r * fmaf(ln_nmu, u1.w, v[7]);
+            }
             if (ep.bias) {
               const float4 b0 = *reinterpret_cast<const float4*>(sbias + c * 32 + j8 * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(sbias + c * 32 + j8 * 8 + 4);
@@ -354,6 +385,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
               v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
             }
+            if (ep.a_next) {      // the next GEMM's LN-folded operand + the row statistics its epilogue needs
+              const float4 g0 = *reinterpret_cast<const float4*>(sgnext + c * 32 + j8 * 8);
+              const float4 g1 = *reinterpret_cast<const float4*>(sgnext + c * 32 + j8 * 8 + 4);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                ps += v[j];
+                pq = fmaf(v[j], v[j], pq);
+              }
+              uint4 an;
+              an.x = pack_bf16x2(v[0] * g0.x, v[1] * g0.y);
+              an.y = pack_bf16x2(v[2] * g0.z, v[3] * g0.w);
+              an.z = pack_bf16x2(v[4] * g1.x, v[5] * g1.y);
+              an.w = pack_bf16x2(v[6] * g1.z, v[7] * g1.w);
+              *reinterpret_cast<uint4*>(ep.a_next + (long long)row * ep.ld_an + n) = an;
+            }
             if (ep.out_is_f32) {
               float* op = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + n;
               *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
@@ -372,6 +418,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       if (row_ok && ep.sumsq && ss_group >= 0 && ss_group < ep.sumsq_groups)
         atomicAdd(&ep.sumsq[(long long)row * ep.sumsq_groups + ss_group], ss);
+      if (row_ok && ep.a_next) {
+        atomicAdd(&ep.row_stats[2LL * row], ps);
+        atomicAdd(&ep.row_stats[2LL * row + 1], pq);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(bar(TMEM_EMPTY + acc), 0);   // the even CTA's barrier
@@ -398,6 +448,8 @@ int launch(const void* A, long long lda, const void* W, long long ldw, int M, in
   ep.out = e->out; ep.ldo = e->ldo; ep.out_is_f32 = e->out_is_f32; ep.act = e->act;
   ep.bias = e->bias; ep.gate = e->gate; ep.residual = e->residual; ep.ldr = e->ldr;
   ep.sumsq = e->sumsq; ep.sumsq_groups = e->sumsq_groups; ep.sumsq_group_cols = e->sumsq_group_cols;
+  ep.ln_stats = e->ln_stats; ep.ln_u = e->ln_u; ep.ln_inv_d = e->ln_dim > 0 ? 1.0f / (float)e->ln_dim : 0.f; ep.ln_eps = e->ln_eps;
+  ep.a_next = reinterpret_cast<__nv_bfloat16*>(e->a_next); ep.ld_an = e->ld_an; ep.g_next = e->g_next; ep.row_stats = e->row_stats;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);

@@ -270,6 +270,17 @@ extern "C" int svi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
     SVI_REQUIRE(e->sumsq_groups > 0 && e->sumsq_group_cols > 0 && e->sumsq_group_cols % 32 == 0,
                 "svi_gemm_bf16: sumsq_group_cols must be a positive multiple of 32");
 
+  if (e->ln_stats || e->a_next) {
+    SVI_REQUIRE(M > BM, "svi_gemm_bf16: the LayerNorm fold (ln_stats / a_next) runs in the CTA-pair kernel: needs M > 128");
+    if (e->ln_stats)
+      SVI_REQUIRE(e->ln_u && e->ln_dim > 0 && (reinterpret_cast<uintptr_t>(e->ln_stats) & 7) == 0,
+                  "svi_gemm_bf16: ln fold needs ln_u, ln_dim > 0 and 8-byte aligned ln_stats");
+    if (e->a_next)
+      SVI_REQUIRE(e->g_next && e->row_stats && e->ld_an >= N && e->ld_an % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(e->a_next) & 15) == 0,
+                  "svi_gemm_bf16: a_next needs g_next, row_stats, ld_an >= N (multiple of 8) and 16-byte alignment");
+  }
+
   // More than one 128-row tile of A: CTA pairs (256x256 tiles, gemm2_tcgen05.cu; 12-13 % faster on the DiT shapes
   // because each SM pulls a third less operand data through L2).  M <= 128 (time/text embeddings, LoRA merges of
   // narrow matrices) would leave the odd CTA of every pair idle, so those stay on the single-CTA kernel below.

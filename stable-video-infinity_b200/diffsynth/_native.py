@@ -24,6 +24,8 @@ class GemmEpilogue(_c.Structure):
         ("out", _vp), ("ldo", _i64), ("out_is_f32", _i32), ("act", _i32),
         ("bias", _vp), ("gate", _vp), ("residual", _vp), ("ldr", _i64),
         ("sumsq", _vp), ("sumsq_groups", _i32), ("sumsq_group_cols", _i32),
+        ("ln_stats", _vp), ("ln_u", _vp), ("ln_dim", _i32), ("ln_eps", _f32),
+        ("a_next", _vp), ("ld_an", _i64), ("g_next", _vp), ("row_stats", _vp),
     ]
 
 
@@ -40,6 +42,8 @@ class ConvDesc(_c.Structure):
         ("n_split", _i32), ("split_offset", _i64),
         ("bias", _vp),
         ("residual", _vp), ("res_frame_stride", _i64), ("res_ld", _i32),
+        ("next_ring", _vp), ("next_frame_stride", _i64), ("next_ld", _i32), ("next_slot", _i32 * 4),
+        ("next_gamma", _vp), ("next_silu", _i32), ("write_f32", _i32),
     ]
 
 
@@ -67,6 +71,8 @@ SIGNATURES = {
     "svi_patchify_gather_split": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "svi_split_f32_to_bf16x2": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _vp]),
     "svi_zero": (_i32, [_vp, _c.c_size_t, _vp]),
+    "svi_ln_fold_prepare": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "svi_ln_fold_combine": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "svi_patchify_gather": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "svi_unpatchify": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "svi_cfg_euler_step": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp]),
@@ -153,8 +159,10 @@ def sm_count():
     return load().svi_sm_count()
 
 
-def gemm(a, w, out, bias=None, act=ACT_NONE, gate=None, residual=None, sumsq=None, sumsq_group_cols=0):
-    """out = epilogue(a[M,K] @ w[N,K]^T); a, w bf16; out f32 or bf16 (may be a column slice view)."""
+def gemm(a, w, out, bias=None, act=ACT_NONE, gate=None, residual=None, sumsq=None, sumsq_group_cols=0, ln=None, emit=None):
+    """out = epilogue(a[M,K] @ w[N,K]^T); a, w bf16; out f32 or bf16 (may be a column slice view).
+    ln = (stats f32 [M,2], u f32 [N], dim, eps): LayerNorm folded into the GEMM (consumer side, svi_gemm_epilogue);
+    emit = (a_next bf16 [M,N], g_next f32 [N], row_stats f32 [M,2]): producer side.  Both need M > 128."""
     lda, ldw, ldo = _rowmajor(a, "a"), _rowmajor(w, "w"), _rowmajor(out, "out")
     M, K = a.shape
     N = w.shape[0]
@@ -179,6 +187,21 @@ def gemm(a, w, out, bias=None, act=ACT_NONE, gate=None, residual=None, sumsq=Non
         ep.sumsq = _ptr(sumsq, torch.float32, "sumsq")
         ep.sumsq_groups = sumsq.shape[1]
         ep.sumsq_group_cols = sumsq_group_cols
+    if ln is not None or emit is not None:
+        if M <= 128:
+            raise RuntimeError("svi_b200.gemm: the LayerNorm fold runs in the CTA-pair kernel (M > 128)")
+    if ln is not None:
+        stats, u, dim, eps = ln
+        if tuple(stats.shape) != (M, 2) or not stats.is_contiguous() or u.numel() != N:
+            raise RuntimeError("svi_b200.gemm: ln stats must be contiguous [M,2] and u [N]")
+        ep.ln_stats, ep.ln_u = _ptr(stats, torch.float32, "ln_stats"), _ptr(u, torch.float32, "ln_u")
+        ep.ln_dim, ep.ln_eps = int(dim), float(eps)
+    if emit is not None:
+        a_next, g_next, row_stats = emit
+        if a_next.shape[0] != M or a_next.shape[1] != N or tuple(row_stats.shape) != (M, 2) or not row_stats.is_contiguous():
+            raise RuntimeError("svi_b200.gemm: emit needs a_next [M,N] and contiguous row_stats [M,2]")
+        ep.a_next, ep.ld_an = _ptr(a_next, torch.bfloat16, "a_next"), _rowmajor(a_next, "a_next")
+        ep.g_next, ep.row_stats = _ptr(g_next, torch.float32, "g_next"), _ptr(row_stats, torch.float32, "row_stats")
     rc = load().svi_gemm_bf16(_ptr(a, torch.bfloat16, "a"), lda, _ptr(w, torch.bfloat16, "w"), ldw,
                               M, N, K, ctypes.byref(ep), _stream())
     _check(rc, "svi_gemm_bf16")
@@ -337,6 +360,25 @@ def split_f32_to_bf16x2(src, dst, act=ACT_NONE):
                                         _ptr(dst, torch.bfloat16, "dst"), _rowmajor(dst, "dst"), K, _stream())
     _check(rc, "svi_split_f32_to_bf16x2")
     return dst
+
+
+def ln_fold_prepare(mods, layers, g_out, rows):
+    """mods f32 [>= 6*layers, D] -> g_out f32 [layers, 2, D] (1 + scale), rows bf16 [layers, 2, 4, D] (svi_ln_fold_prepare)."""
+    D = mods.shape[1]
+    if not (mods.is_contiguous() and g_out.is_contiguous() and rows.is_contiguous()) or g_out.numel() != layers * 2 * D \
+            or rows.numel() != layers * 8 * D:
+        raise RuntimeError("svi_b200.ln_fold_prepare: contiguous mods [6L,D], g_out [L,2,D], rows [L,2,4,D] required")
+    _check(load().svi_ln_fold_prepare(_ptr(mods, torch.float32, "mods"), layers, D, _ptr(g_out, torch.float32, "g_out"),
+                                      _ptr(rows, torch.bfloat16, "rows"), _stream()), "svi_ln_fold_prepare")
+
+
+def ln_fold_combine(o4, bias, u, c):
+    """o4 f32 [4, N] -> u = o4[0] + o4[1], c = o4[2] + o4[3] + bias (svi_ln_fold_combine); u, c contiguous f32 [N]."""
+    N = o4.shape[1]
+    if not o4.is_contiguous() or u.numel() != N or c.numel() != N or not u.is_contiguous() or not c.is_contiguous():
+        raise RuntimeError("svi_b200.ln_fold_combine: contiguous o4 [4,N], u [N], c [N] required")
+    _check(load().svi_ln_fold_combine(_ptr(o4, torch.float32, "o4"), N, _ptr(bias, torch.float32, "bias"),
+                                      _ptr(u, torch.float32, "u"), _ptr(c, torch.float32, "c"), _stream()), "svi_ln_fold_combine")
 
 
 def zero_(t):

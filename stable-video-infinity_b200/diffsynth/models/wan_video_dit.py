@@ -210,8 +210,36 @@ class TimeState:
     modulation table + t_mod (rows 6i..6i+5: shift/scale/gate of self-attention, shift/scale/gate of the FFN;
     wan_video_dit.py:356-357) followed by the head's shift/scale rows (:402)."""
 
-    def __init__(self, t, t_mod, mods):
+    def __init__(self, t, t_mod, mods, fold=None):
         self.t, self.t_mod, self.mods = t, t_mod, mods
+        self.fold = fold          # FoldVectors (per-timestep part of the LayerNorm fold) or None
+
+
+class FoldVectors:
+    """Per-timestep vectors of the LayerNorm fold (include/svi_b200.h, svi_gemm_epilogue.ln_*): for block i
+    u1[i], c1[i] ([3d]: W_qkv g, W_qkv t + b) and u3[i], c3[i] ([ffn]: W_ffn0 g, W_ffn0 t + b) live in one f32 `pack`
+    [layers, 6d + 2 ffn] (a captured graph reads a fixed copy of it); g f32 [layers, 2, d] = 1 + scale of the self-attention /
+    FFN LayerNorm is what the PRODUCER epilogues multiply into the next operand."""
+
+    def __init__(self, layers, d, ffn, device):
+        self.d, self.ffn = d, ffn
+        self.pack = torch.empty(layers, 6 * d + 2 * ffn, device=device, dtype=torch.float32)
+        self.g = torch.empty(layers, 2, d, device=device, dtype=torch.float32)
+        self.u1, self.c1 = self.pack[:, :3 * d], self.pack[:, 3 * d:6 * d]
+        self.u3, self.c3 = self.pack[:, 6 * d:6 * d + ffn], self.pack[:, 6 * d + ffn:]
+
+    def copy_(self, other):
+        self.pack.copy_(other.pack)
+        self.g.copy_(other.g)
+
+
+class _FoldRun:
+    """One forward's view of the LayerNorm fold: per-timestep vectors `v` (FoldVectors), the constant norm3 vectors u2 / c2
+    [layers, d] and the zeroed row statistics f32 [layers, 3, L, 2] ((sum x, sum x^2) of the token rows entering the
+    self-attention / cross-attention / FFN LayerNorm of every block) that the producer epilogues accumulate."""
+
+    def __init__(self, v, u2, c2, stats):
+        self.v, self.u2, self.c2, self.stats = v, u2, c2, stats
 
 
 class AudioState:
@@ -306,6 +334,10 @@ class WanDiTEngine:
         self._graphs = {}
         import os
         self.use_graphs = os.environ.get("SVI_CUDA_GRAPHS", "1") != "0"
+        # LayerNorm + modulate folded into the GEMMs around it (no LayerNorm launches inside the block stack); applies to
+        # forwards with more than 128 token rows per rank (the fold lives in the CTA-pair GEMM) and no audio branch
+        self.use_fold = os.environ.get("SVI_LN_FOLD", "1") != "0"
+        self._fold_static = None
         self.attn_events = None  # bench.py: list collecting (start, end) events around self-attention launches
         self.k = _CountingNative()  # every native launch goes through this proxy (bench.py reads the count)
 
@@ -325,14 +357,51 @@ class WanDiTEngine:
         return self._rope[key]
 
     # ------------------------------------------------------------------ conditioning
-    def _gemm_split(self, a2, w, out, bias=None, residual=None):
+    def _gemm_split(self, a2, w, out, bias=None, residual=None, emit=None):
         """out(f32) = [a_hi | a_lo] @ w^T (+ bias) (+ residual) as two accumulating passes over the same weights: the A operand
         enters with ~16 mantissa bits instead of bf16's 8.  Used for the GEMMs whose bf16 A operand dominated the parity
         error at negligible cost (embedding MLPs, patch embedding, head; tools/rounding_study.py)."""
         K = w.shape[1]
         self.k.gemm(a2[:, :K], w, out, bias=bias, residual=residual)
-        self.k.gemm(a2[:, K:], w, out, residual=out)
+        self.k.gemm(a2[:, K:], w, out, residual=out, emit=emit)
         return out
+
+    def _fold_vectors(self, mods) -> FoldVectors:
+        """u = W g and c = W t + b of every block's QKV and FFN-in GEMM for this timestep's modulation (g = 1 + scale,
+        t = shift), g and t in two-term bf16 so the vectors carry ~16 mantissa bits: one M = 4 GEMM + one combine per
+        (block, GEMM), cached with the TimeState (both CFG branches and every clip reuse them)."""
+        nl, d, dev = len(self.blocks), self.dim, self.device
+        ffn = self.blocks[0].w_f0.shape[0]
+        fv = FoldVectors(nl, d, ffn, dev)
+        rows = torch.empty(nl, 2, 4, d, device=dev, dtype=torch.bfloat16)
+        self.k.ln_fold_prepare(mods, nl, fv.g, rows)
+        o1 = torch.empty(4, 3 * d, device=dev, dtype=torch.float32)
+        o3 = torch.empty(4, ffn, device=dev, dtype=torch.float32)
+        for i, bw in enumerate(self.blocks):
+            self.k.gemm(rows[i, 0], bw.w_qkv, o1)
+            self.k.ln_fold_combine(o1, bw.b_qkv, fv.u1[i], fv.c1[i])
+            self.k.gemm(rows[i, 1], bw.w_f0, o3)
+            self.k.ln_fold_combine(o3, bw.b_f0, fv.u3[i], fv.c3[i])
+        return fv
+
+    def _fold_consts(self):
+        """Step-invariant part of the fold: the affine LayerNorm in front of the cross-attention q projection
+        (norm3, wan_video_dit.py:333,368): u2 = W_q gamma, c2 = W_q beta + b_q per block, f32 [layers, d] each."""
+        if self._fold_static is None:
+            nl, d, dev = len(self.blocks), self.dim, self.device
+            u2 = torch.empty(nl, d, device=dev, dtype=torch.float32)
+            c2 = torch.empty(nl, d, device=dev, dtype=torch.float32)
+            gb = torch.empty(2, d, device=dev, dtype=torch.float32)
+            rows = torch.empty(2, 2 * d, device=dev, dtype=torch.bfloat16)
+            o4 = torch.empty(4, d, device=dev, dtype=torch.float32)
+            for i, bw in enumerate(self.blocks):
+                gb[0].copy_(bw.n3w)
+                gb[1].copy_(bw.n3b)
+                self.k.split_f32_to_bf16x2(gb, rows)             # [gamma_hi | gamma_lo ; beta_hi | beta_lo] == [4, d] row-major
+                self.k.gemm(rows.view(4, d), bw.w_cq, o4)
+                self.k.ln_fold_combine(o4, bw.b_cq, u2[i], c2[i])
+            self._fold_static = (u2, c2)
+        return self._fold_static
 
     def time_state(self, timestep) -> TimeState:
         """TimeState of a scalar timestep (svi_video.py:90-91): time MLP and time projection in split precision, then the
@@ -358,7 +427,7 @@ class WanDiTEngine:
         self._gemm_split(ts2, self.w_tp, t_mod, bias=self.b_tp)
         self.k.add_rows(self.mod_table, t_mod.view(6, d), mods[:6 * nl])
         self.k.add_rows(self.head_mod, t, mods[6 * nl:])
-        out = TimeState(t, t_mod.view(6, d), mods)
+        out = TimeState(t, t_mod.view(6, d), mods, self._fold_vectors(mods) if self.use_fold else None)
         self._time_cache[tv] = out
         while len(self._time_cache) > 256:
             self._time_cache.popitem(last=False)
@@ -469,10 +538,14 @@ class WanDiTEngine:
         self-attention, q of cross-attention), zeroed by ONE memset node at the start of the forward."""
         return self._buf("row_sums", (len(self.blocks), 3 * L), torch.float32)
 
-    def run_block(self, i, x, mods, ctx: ContextState, cos, sin, sp=None, audio: Optional[AudioState] = None, row_sums=None):
+    def run_block(self, i, x, mods, ctx: ContextState, cos, sin, sp=None, audio: Optional[AudioState] = None, row_sums=None,
+                  fold=None):
         """x f32 [L,d] updated in place.  Reference DiTBlock.forward wan_video_dit.py:354-374.  `mods`: TimeState.mods (or
         any f32 [>= 6*(i+1), d] table whose rows 6i..6i+5 are this block's shift/scale/gate rows); `row_sums`: this
-        forward's zeroed _row_sums buffer (None: a private one is zeroed here — single-block callers)."""
+        forward's zeroed _row_sums buffer (None: a private one is zeroed here — single-block callers).
+        `fold` (a _FoldRun): the three LayerNorms of the block are folded into the GEMMs around them — the buffer `h` then
+        already holds bf16(x * g) written by the previous residual GEMM's epilogue (or the patch embedding), every residual
+        GEMM of this block emits the next one, and no LayerNorm kernel runs."""
         bw = self.blocks[i]
         L, d, H = x.shape[0], self.dim, self.H
         mod = mods[6 * i: 6 * i + 6]
@@ -485,11 +558,15 @@ class WanDiTEngine:
             self.k.zero_(row_sums[i])
         rs = row_sums[i]
         # --- self attention
-        self.k.layernorm_modulate(x, h, bw.eps, scale=mod[1], shift=mod[0])
+        if fold is None:
+            self.k.layernorm_modulate(x, h, bw.eps, scale=mod[1], shift=mod[0])
+            b_qkv, ln1 = bw.b_qkv, None
+        else:
+            b_qkv, ln1 = fold.v.c1[i], (fold.stats[i, 0], fold.v.u1[i], d, bw.eps)
         ev = self.attn_events
         if sp is None:
             ss = rs[:2 * L].view(L, 2)
-            self.k.gemm(h, bw.w_qkv, qkv, bias=bw.b_qkv, sumsq=ss, sumsq_group_cols=d)
+            self.k.gemm(h, bw.w_qkv, qkv, bias=b_qkv, sumsq=ss, sumsq_group_cols=d, ln=ln1)
             self.k.qk_norm_rope(qkv[:, :2 * d], ss, bw.eps_qk, bw.nq, bw.nk, cos, sin, 0)
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
         else:
@@ -506,11 +583,13 @@ class WanDiTEngine:
                 kvf = self._buf("kv_full", (L * sp.sp_size, 2 * d), torch.bfloat16)
                 kvl = kvf[sp.sp_rank * L:(sp.sp_rank + 1) * L]
             ssq, ssk = rs[:L].view(L, 1), rs[L:2 * L].view(L, 1)
-            self.k.gemm(h, bw.w_kv, kvl, bias=bw.b_kv, sumsq=ssk, sumsq_group_cols=d)
+            self.k.gemm(h, bw.w_kv, kvl, bias=b_qkv[d:], sumsq=ssk, sumsq_group_cols=d,
+                        ln=None if ln1 is None else (ln1[0], ln1[1][d:], d, bw.eps))
             self.k.rmsnorm_rope(kvl[:, :d], ssk, 0, bw.eps_qk, bw.nk, cos, sin, sp.sp_rank * L)
             if pe is not None:
                 pe.push(pbuf)
-            self.k.gemm(h, bw.w_q, q, bias=bw.b_q, sumsq=ssq, sumsq_group_cols=d)
+            self.k.gemm(h, bw.w_q, q, bias=b_qkv[:d], sumsq=ssq, sumsq_group_cols=d,
+                        ln=None if ln1 is None else (ln1[0], ln1[1][:d], d, bw.eps))
             self.k.rmsnorm_rope(q, ssq, 0, bw.eps_qk, bw.nq, cos, sin, sp.sp_rank * L)
             if pe is None:
                 sp.all_gather_rows(kvf)
@@ -527,19 +606,25 @@ class WanDiTEngine:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             ev.append((e0, e1))
-        self.k.gemm(att, bw.w_o, x, bias=bw.b_o, gate=mod[2], residual=x)
+        self.k.gemm(att, bw.w_o, x, bias=bw.b_o, gate=mod[2], residual=x,
+                    emit=None if fold is None else (h, bw.n3w, fold.stats[i, 1]))
         # --- cross attention: q stays un-normalised in memory; its RMS factor is applied inside the softmax and norm_q's
         #     weight already sits in the context K (context_state)
-        self.k.layernorm_modulate(x, h, bw.eps, gamma=bw.n3w, beta=bw.n3b)
         cq = qkv[:, :d]
         ss1 = rs[2 * L:].view(L, 1)
-        self.k.gemm(h, bw.w_cq, cq, bias=bw.b_cq, sumsq=ss1, sumsq_group_cols=d)
+        if fold is None:
+            self.k.layernorm_modulate(x, h, bw.eps, gamma=bw.n3w, beta=bw.n3b)
+            self.k.gemm(h, bw.w_cq, cq, bias=bw.b_cq, sumsq=ss1, sumsq_group_cols=d)
+        else:
+            self.k.gemm(h, bw.w_cq, cq, bias=fold.c2[i], sumsq=ss1, sumsq_group_cols=d,
+                        ln=(fold.stats[i, 1], fold.u2[i], d, bw.eps))
         kv = ctx.kv_txt[i]
         self.k.attention_qscale(cq, kv[:, :d], kv[:, d:], att, H, ss1, d, bw.eps_qk)
         if ctx.n_img:
             kvi = ctx.kv_img[i]
             self.k.attention_qscale(cq, kvi[:, :d], kvi[:, d:], att, H, ss1, d, bw.eps_qk, accumulate=True)
-        self.k.gemm(att, bw.w_co, x, bias=bw.b_co, residual=x)
+        self.k.gemm(att, bw.w_co, x, bias=bw.b_co, residual=x,
+                    emit=None if fold is None else (h, fold.v.g[i, 1], fold.stats[i, 2]))
         # --- audio cross-attention (SVI-Talk, wan_video_dit.py:361-366): tokens of latent frame f attend to that frame's
         #     audio tokens (models/attention.py:318-371); 1/sqrt(head_dim) scale, no q/k norm
         if audio is not None:
@@ -557,9 +642,15 @@ class WanDiTEngine:
                     self.k.attention(aq[lo:hi], kf[:, :d], kf[:, d:], att[lo:hi], H)
             self.k.gemm(att, bw.w_ap, x, bias=bw.b_ap, residual=x)
         # --- FFN
-        self.k.layernorm_modulate(x, h, bw.eps, scale=mod[4], shift=mod[3])
-        self.k.gemm(h, bw.w_f0, ffn, bias=bw.b_f0, act=nv.ACT_GELU_TANH)
-        self.k.gemm(ffn, bw.w_f2, x, bias=bw.b_f2, gate=mod[5], residual=x)
+        if fold is None:
+            self.k.layernorm_modulate(x, h, bw.eps, scale=mod[4], shift=mod[3])
+            self.k.gemm(h, bw.w_f0, ffn, bias=bw.b_f0, act=nv.ACT_GELU_TANH)
+            self.k.gemm(ffn, bw.w_f2, x, bias=bw.b_f2, gate=mod[5], residual=x)
+        else:
+            self.k.gemm(h, bw.w_f0, ffn, bias=fold.v.c3[i], act=nv.ACT_GELU_TANH, ln=(fold.stats[i, 2], fold.v.u3[i], d, bw.eps))
+            last = i + 1 == len(self.blocks)
+            self.k.gemm(ffn, bw.w_f2, x, bias=bw.b_f2, gate=mod[5], residual=x,
+                        emit=None if last else (h, fold.v.g[i + 1, 0], fold.stats[i + 1, 0]))
         return x
 
     def forward(self, x, timestep, context, clip_feature=None, y=None, sp=None, out=None, tea_cache=None, add_condition=None,
@@ -616,7 +707,9 @@ class WanDiTEngine:
         if ent["graph"] is None:
             st = ContextState(ctx.n_img, ctx.n_txt, len(self.blocks), self.dim, self.device)
             ent.update(xs=torch.empty_like(xs), ys=None if ys is None else torch.empty_like(ys),
-                       ts=TimeState(None, None, torch.empty_like(ts.mods)), ctx=st, out=torch.empty_like(out))
+                       ts=TimeState(None, None, torch.empty_like(ts.mods),
+                                    None if ts.fold is None else FoldVectors(len(self.blocks), self.dim, ts.fold.ffn, self.device)),
+                       ctx=st, out=torch.empty_like(out))
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             n0 = self.k.launches
@@ -630,6 +723,8 @@ class WanDiTEngine:
         if ys is not None:
             ent["ys"].copy_(ys)
         ent["ts"].mods.copy_(ts.mods)
+        if ts.fold is not None:
+            ent["ts"].fold.copy_(ts.fold)
         ent["ctx"].kv_txt_all.copy_(ctx.kv_txt_all)
         if ctx.n_img:
             ent["ctx"].kv_img_all.copy_(ctx.kv_img_all)
@@ -664,15 +759,23 @@ class WanDiTEngine:
                 raise RuntimeError(f"svi_b200: add_condition must be [1, {L}, {d}], got {tuple(add_condition.shape)}")
             cond = add_condition[0].to(device=dev, dtype=torch.float32).contiguous()
             cond_l = cond if sp is None else cond[sp.row_offset: sp.row_offset + Ll]
-        self._gemm_split(tok_l, self.w_patch, xr, bias=self.b_patch, residual=cond_l)     # x = [add_condition +] patchify(x)
         nl = len(self.blocks)
+        fold = None
+        if self.use_fold and ts.fold is not None and Ll > 128 and audio is None:
+            u2, c2 = self._fold_consts()
+            fold = _FoldRun(ts.fold, u2, c2, self._buf("ln_stats", (nl, 3, Ll, 2), torch.float32))
+            self.k.zero_(fold.stats)
+        h0 = self._buf("h", (Ll, d), torch.bfloat16)
+        # x = [add_condition +] patchify(x); with the fold its last pass also emits block 0's first operand + row statistics
+        self._gemm_split(tok_l, self.w_patch, xr, bias=self.b_patch, residual=cond_l,
+                         emit=None if fold is None else (h0, fold.v.g[0, 0], fold.stats[0, 0]))
         if tea_cache is not None and tea_cache.check(self.model, xr, ts.t_mod):
             tea_cache.update(xr)                      # skipped step: tokens + residual of the last computed step
         else:
             row_sums = self._row_sums(Ll)
             self.k.zero_(row_sums)
             for i in range(nl):
-                self.run_block(i, xr, ts.mods, ctx, cos, sin, sp, audio, row_sums)
+                self.run_block(i, xr, ts.mods, ctx, cos, sin, sp, audio, row_sums, fold)
             if tea_cache is not None:
                 tea_cache.store(xr)
         # head (wan_video_dit.py:401-404) + unpatchify (:479-484); the normalised tokens enter the head GEMM as [hi | lo]

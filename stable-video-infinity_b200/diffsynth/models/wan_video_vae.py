@@ -193,13 +193,19 @@ class _Conv:
 
 
 class _Ring:
-    """bf16 frame ring [slots + 1, H, W, C]; the last slot is all zeros (empty history)."""
+    """bf16 frame ring [slots + 1, halo + H + halo, W, C]; the last slot is all zeros (empty history).  halo = 1 under
+    spatial sharding (rings of convs with a vertical extent): row 0 / row H+1 of a frame hold the neighbour ranks' border
+    rows (exchanged when the frame is produced; zero at the image border), rows 1..H are this rank's rows."""
 
-    def __init__(self, slots, H, W, C, device, history):
-        self.buf = torch.zeros(slots + 1, H, W, C, device=device, dtype=torch.bfloat16)
-        self.slots, self.H, self.W, self.C = slots, H, W, C
+    def __init__(self, slots, H, W, C, device, history, halo=0):
+        self.buf = torch.zeros(slots + 1, H + 2 * halo, W, C, device=device, dtype=torch.bfloat16)
+        self.slots, self.H, self.W, self.C, self.halo = slots, H, W, C, halo
         self.next = 0
         self.hist = [slots] * history           # slot ids of the most recent frames (oldest first)
+
+    def frame(self, slot):
+        """The rank's own rows of a slot: bf16 [H, W, C] (contiguous)."""
+        return self.buf[slot, self.halo:self.halo + self.H]
 
     def push(self, n):
         ids = [(self.next + i) % self.slots for i in range(n)]
@@ -248,60 +254,117 @@ class WanVAEEngine:
         self.launches = 0
         self.rings = {}
         self.chunk = 0
+        self.shard = None        # SpatialShard: this rank computes a band of image rows, halos exchanged per conv
+        self.halo_exchanges = 0
 
     # ------------------------------------------------------------------ low-level helpers
     def reset(self):
         self.rings = {}
         self.chunk = 0
 
-    def _ring(self, key, slots, H, W, C, history):
+    def _ring(self, key, slots, H, W, C, history, halo=0):
         r = self.rings.get(key)
-        if r is None or (r.H, r.W, r.C, r.slots) != (H, W, C, slots):
-            r = _Ring(slots, H, W, C, self.device, history)
+        if r is None or (r.H, r.W, r.C, r.slots, r.halo) != (H, W, C, slots, halo):
+            r = _Ring(slots, H, W, C, self.device, history, halo)
             self.rings[key] = r
         return r
 
+    def _halo(self, cv):
+        """1 when the conv reads rows above / below its output row and the image is split over ranks."""
+        return 1 if (self.shard is not None and cv.kh > 1) else 0
+
+    def _exchange_halo(self, ring, ids):
+        """Spatial sharding: the frames just produced in `ids` get their border rows from the neighbour ranks (and send
+        theirs): one NCCL send/recv group per conv input.  Replaces nothing in the reference (its VAE is single-GPU; its
+        tiled mode blends overlapping tiles, wan_video_vae.py:643-744) — SURVEY.md section 8e."""
+        sh = self.shard
+        if sh is None or not ring.halo:
+            return
+        import torch.distributed as dist
+        ops = []
+        H = ring.H
+        for slot in ids:
+            fr = ring.buf[slot]
+            if sh.up is not None:
+                ops += [dist.P2POp(dist.isend, fr[1], sh.up, sh.group), dist.P2POp(dist.irecv, fr[0], sh.up, sh.group)]
+            if sh.down is not None:
+                ops += [dist.P2POp(dist.isend, fr[H], sh.down, sh.group), dist.P2POp(dist.irecv, fr[H + 1], sh.down, sh.group)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            self.halo_exchanges += 1
+
     def _launch_conv(self, cv, ring, slot_table, T, H, W, out, out_frame_stride, out_ld, pad, residual=None, n_split=0,
-                     split_offset=0):
+                     split_offset=0, nxt=None, write_f32=True):
         d = nv.ConvDesc()
         d.x_ring = ring.buf.data_ptr()
-        d.ring_slots, d.in_H, d.in_W, d.C_in = ring.slots + 1, ring.H, ring.W, ring.C
+        d.ring_slots, d.in_H, d.in_W, d.C_in = ring.slots + 1, ring.H + 2 * ring.halo, ring.W, ring.C
         d.w_packed, d.w_rows, d.w_ld = cv.w.data_ptr(), cv.w.shape[0], cv.w.shape[1]
-        d.kt, d.kh, d.kw, d.pad_h, d.pad_w = cv.kt, cv.kh, cv.kw, pad, pad
+        # with a halo row on top, ring row = image row + 1: the vertical padding shrinks by the halo (may become -1)
+        d.kt, d.kh, d.kw, d.pad_h, d.pad_w = cv.kt, cv.kh, cv.kw, pad - ring.halo, pad
         d.H, d.W, d.T = H, W, T
         for t in range(T):
             for a in range(cv.kt):
                 d.slot[t * 3 + a] = slot_table[t][a]
         d.C_out = cv.c_out
         d.tile_w = _pick_tile_w(H, W)
-        d.out, d.out_frame_stride, d.out_ld = out.data_ptr(), out_frame_stride, out_ld
+        if out is not None:
+            d.out, d.out_frame_stride, d.out_ld = out.data_ptr(), out_frame_stride, out_ld
+        else:
+            d.out_ld = cv.c_out
         d.n_split, d.split_offset = n_split, split_offset
         d.bias = cv.b.data_ptr()
         if residual is not None:
             d.residual, d.res_frame_stride, d.res_ld = residual.data_ptr(), residual.stride(0), residual.shape[-1]
+        d.write_f32 = 1 if write_f32 else 0
+        if nxt is not None:       # the epilogue also produces the next conv's input (RMS norm + SiLU + bf16 staging)
+            (ncv, nring, nids), gamma, silu = nxt
+            d.next_ring = nring.buf.data_ptr() + nring.halo * nring.buf.stride(1) * 2      # first own row of a slot
+            d.next_frame_stride = nring.buf.stride(0)
+            d.next_ld = nring.C
+            for t in range(T):
+                d.next_slot[t] = nids[t]
+            d.next_gamma = None if gamma is None else gamma.data_ptr()
+            d.next_silu = 1 if silu else 0
         nv.conv3d_causal(d)
         self.launches += 1
 
     def _stage(self, ring, slot, x_frame, gamma=None, silu=False):
         """fp32 channels-last frame [H,W,C] -> (RMS-norm, SiLU,) bf16 into a ring slot (zero-padded channels)."""
         H, W, C = x_frame.shape
-        nv.vae_norm_act(x_frame, H * W, C, x_frame.stride(1), gamma, silu, ring.buf[slot], ring.C)
+        nv.vae_norm_act(x_frame, H * W, C, x_frame.stride(1), gamma, silu, ring.frame(slot), ring.C)
         self.launches += 1
 
     # ------------------------------------------------------------------ layers (x: f32 [T,H,W,C] contiguous)
-    def causal_conv(self, name, x, gamma=None, silu=False, residual=None):
-        """3x3x3 (or 3x1x1) causal conv over the frame stream with two frames of history kept in the ring."""
+    FUSE_MAX_C = 256      # the fused producer needs the whole channel vector of a pixel in one accumulator tile
+
+    def _conv_in(self, name, T, H, W):
+        """Reserve T input slots in causal conv `name`'s frame ring: (conv, ring, slot ids).  Whoever fills them — the
+        staging kernel or the previous conv's epilogue — the history bookkeeping happens in causal_conv."""
         cv = self.convs[name]
-        T, H, W, C = x.shape
-        ring = self._ring(name, 4 + CACHE_T, H, W, cv.c_in, history=CACHE_T)
-        ids = ring.push(T)
-        for t in range(T):
-            self._stage(ring, ids[t], x[t], gamma, silu)
+        ring = self._ring(name, 4 + CACHE_T, H, W, cv.c_in, history=CACHE_T, halo=self._halo(cv))
+        return cv, ring, ring.push(T)
+
+    def causal_conv(self, name, x, gamma=None, silu=False, residual=None, staged=None, nxt=None, write_f32=True, shape=None):
+        """3x3x3 (or 3x1x1) causal conv over the frame stream with two frames of history kept in the ring.
+        staged: (conv, ring, ids) from _conv_in whose slots the PREVIOUS conv's epilogue already filled (x is then unused);
+        nxt: ((conv, ring, ids), gamma, silu) — this conv's epilogue fills the next conv's slots; write_f32=False drops
+        the fp32 output (returns None)."""
+        if staged is None:
+            T, H, W, C = x.shape
+            cv, ring, ids = self._conv_in(name, T, H, W)
+            for t in range(T):
+                self._stage(ring, ids[t], x[t], gamma, silu)
+        else:
+            cv, ring, ids = staged
+            T, H, W = shape
+        self._exchange_halo(ring, ids)
         seq = ring.hist + ids
         table = [[seq[t + a] for a in range(cv.kt)] for t in range(T)] if cv.kt == 3 else [[ids[t]] for t in range(T)]
         ring.hist = seq[-CACHE_T:]
-        out = torch.empty(T, H, W, cv.c_out, device=self.device, dtype=torch.float32)
-        self._launch_conv(cv, ring, table, T, H, W, out, out.stride(0), cv.c_out, pad=(cv.kh - 1) // 2, residual=residual)
+        out = torch.empty(T, H, W, cv.c_out, device=self.device, dtype=torch.float32) if write_f32 else None
+        self._launch_conv(cv, ring, table, T, H, W, out, 0 if out is None else out.stride(0), cv.c_out, pad=(cv.kh - 1) // 2,
+                          residual=residual, nxt=nxt, write_f32=write_f32)
         return out
 
     def pointwise_conv(self, name, x):
@@ -316,37 +379,59 @@ class WanVAEEngine:
         self._launch_conv(cv, ring, [[i] for i in ids], T, H, W, out, out.stride(0), cv.c_out, pad=0)
         return out
 
-    def residual_block(self, name, x):
-        """reference ResidualBlock.forward :213-232."""
+    def residual_block(self, name, x, staged=None, next_res=None):
+        """reference ResidualBlock.forward :213-232.  The activation between the block's two convs exists only as the
+        normalised bf16 input of the second conv (written by the first conv's epilogue) when the width allows it; with
+        `next_res` (name of a ResidualBlock that consumes this block's output next) the second conv's epilogue also fills
+        the next block's first conv input.  Returns (x_out f32, staged input of next_res or None)."""
+        T, H, W, _ = x.shape
         h = self.pointwise_conv(name + ".shortcut", x) if (name + ".shortcut") in self.convs else x
-        y = self.causal_conv(name + ".residual.2", x, self.gammas[name + ".residual.0"], True)
-        return self.causal_conv(name + ".residual.6", y, self.gammas[name + ".residual.3"], True, residual=h)
+        c_mid = self.convs[name + ".residual.2"].c_out_true
+        c_out = self.convs[name + ".residual.6"].c_out_true
+        s6 = self._conv_in(name + ".residual.6", T, H, W) if c_mid <= self.FUSE_MAX_C else None
+        y = self.causal_conv(name + ".residual.2", x, self.gammas[name + ".residual.0"], True, staged=staged, shape=(T, H, W),
+                             nxt=None if s6 is None else (s6, self.gammas[name + ".residual.3"], True), write_f32=s6 is None)
+        sn = None
+        if next_res is not None and c_out <= self.FUSE_MAX_C and self.convs[next_res + ".residual.2"].c_in_true == c_out:
+            sn = self._conv_in(next_res + ".residual.2", T, H, W)
+        out = self.causal_conv(name + ".residual.6", y, self.gammas[name + ".residual.3"], True, residual=h, staged=s6,
+                               shape=(T, H, W), nxt=None if sn is None else (sn, self.gammas[next_res + ".residual.0"], True))
+        return out, sn
 
     def attention_block(self, name, x):
-        """reference AttentionBlock.forward :254-273: per-frame single-head attention, 4 GEMMs + row softmax."""
+        """reference AttentionBlock.forward :254-273: per-frame single-head attention, 4 GEMMs + row softmax.  Under spatial
+        sharding the normalised tokens of all ranks are gathered (K and V need every token; they are 0.4 % of the VAE FLOPs
+        and are recomputed on every rank) and the rank attends with the queries of its own rows."""
         a = self.attn[name]
         T, H, W, C = x.shape
         N = H * W
-        Np = _ceil(N, 8)
         dev = self.device
+        sh = self.shard
+        Nk = N if sh is None else sh.total_rows(H) * W            # keys: all tokens of the frame
+        Np, Nkp = _ceil(N, 8), _ceil(Nk, 8)
         out = torch.empty_like(x)
         # token count padded to a multiple of 8 (GEMM N / K granularity); pad rows / columns stay zero
         xn = torch.zeros(Np, C, device=dev, dtype=torch.bfloat16)
-        qk = torch.zeros(Np, 2 * C, device=dev, dtype=torch.bfloat16)
-        vT = torch.empty(C, Np, device=dev, dtype=torch.bfloat16)
-        S = torch.empty(N, Np, device=dev, dtype=torch.float32)
-        P = torch.empty(N, Np, device=dev, dtype=torch.bfloat16)
+        xk = xn if sh is None else torch.zeros(Nkp, C, device=dev, dtype=torch.bfloat16)
+        q = torch.zeros(Np, C, device=dev, dtype=torch.bfloat16)
+        kk = torch.zeros(Nkp, C, device=dev, dtype=torch.bfloat16)
+        vT = torch.empty(C, Nkp, device=dev, dtype=torch.bfloat16)
+        S = torch.empty(N, Nkp, device=dev, dtype=torch.float32)
+        P = torch.empty(N, Nkp, device=dev, dtype=torch.bfloat16)
         O = torch.empty(N, C, device=dev, dtype=torch.bfloat16)
         for t in range(T):
             xt = x[t].reshape(N, C)
             nv.vae_norm_act(xt, N, C, C, self.gammas[name + ".norm"], False, xn, C)
-            nv.gemm(xn[:N], a["w_qk"], qk[:N], bias=a["b_qk"])
-            nv.gemm(a["w_v"], xn, vT)                              # V^T without bias (rows of P sum to 1: folded below)
-            nv.gemm(qk[:N, :C], qk[:, C:], S)                      # columns >= N are ignored by the softmax
-            nv.softmax_rows(S, N, C ** -0.5, P)
+            if sh is not None:
+                sh.gather_rows(xn[:N], xk, H, W)
+            nv.gemm(xn[:N], a["w_qk"][:C], q[:N], bias=a["b_qk"][:C])
+            nv.gemm(xk[:Nk], a["w_qk"][C:], kk[:Nk], bias=a["b_qk"][C:])
+            nv.gemm(a["w_v"], xk, vT)                              # V^T without bias (rows of P sum to 1: folded below)
+            nv.gemm(q[:N], kk, S)                                  # columns >= Nk are ignored by the softmax
+            nv.softmax_rows(S, Nk, C ** -0.5, P)
             nv.gemm(P, vT, O, bias=a["b_v"])
             nv.gemm(O, a["w_p"], out[t].reshape(N, C), bias=a["b_p"], residual=xt)
-            self.launches += 7
+            self.launches += 8
         return out
 
     def upsample(self, name, x, temporal):
@@ -366,11 +451,12 @@ class WanVAEEngine:
                               pad=0, n_split=C, split_offset=y.stride(0))
             x, T = y, 2 * T
         cv = self.convs[name + ".resample.1"]
-        ring = self._ring(name + ".resample.1", 4, 2 * H, 2 * W, C, history=0)
+        ring = self._ring(name + ".resample.1", 4, 2 * H, 2 * W, C, history=0, halo=self._halo(cv))
         ids = ring.push(T)
         for t in range(T):
-            nv.vae_upsample2x(x[t], H, W, C, ring.buf[ids[t]])
+            nv.vae_upsample2x(x[t], H, W, C, ring.frame(ids[t]))
             self.launches += 1
+        self._exchange_halo(ring, ids)
         out = torch.empty(T, 2 * H, 2 * W, cv.c_out, device=self.device, dtype=torch.float32)
         self._launch_conv(cv, ring, [[i] for i in ids], T, 2 * H, 2 * W, out, out.stride(0), cv.c_out, pad=1)
         return out
@@ -379,11 +465,12 @@ class WanVAEEngine:
         """reference Resample.forward downsample2d/3d :157-173."""
         T, H, W, C = x.shape
         cv = self.convs[name + ".resample.1"]
-        ring = self._ring(name + ".resample.1", 4, H // 2, W // 2, 4 * C, history=0)
+        ring = self._ring(name + ".resample.1", 4, H // 2, W // 2, 4 * C, history=0, halo=self._halo(cv))
         ids = ring.push(T)
         for t in range(T):
-            nv.vae_space_to_depth(x[t], H, W, C, ring.buf[ids[t]])
+            nv.vae_space_to_depth(x[t], H, W, C, ring.frame(ids[t]))
             self.launches += 1
+        self._exchange_halo(ring, ids)        # the 2x2 conv over the blocks reads block row o + 1: the lower neighbour's first
         y = torch.empty(T, H // 2, W // 2, cv.c_out, device=self.device, dtype=torch.float32)
         self._launch_conv(cv, ring, [[i] for i in ids], T, H // 2, W // 2, y, y.stride(0), cv.c_out, pad=0)
         if not temporal:
@@ -411,16 +498,28 @@ class WanVAEEngine:
     DEC_PLAN = [("res", 0), ("res", 1), ("res", 2), ("up", 3, True), ("res", 4), ("res", 5), ("res", 6), ("up", 7, True),
                 ("res", 8), ("res", 9), ("res", 10), ("up", 11, False), ("res", 12), ("res", 13), ("res", 14)]
 
+    def _run_plan(self, prefix, plan, x):
+        """Walk a level plan; consecutive ResidualBlocks hand their activations over through the conv epilogues."""
+        staged = None
+        for k, item in enumerate(plan):
+            n = f"{prefix}.{item[1]}"
+            if item[0] == "res":
+                nxt = plan[k + 1] if k + 1 < len(plan) else None
+                x, staged = self.residual_block(n, x, staged, f"{prefix}.{nxt[1]}" if nxt is not None and nxt[0] == "res" else None)
+            elif item[0] == "down":
+                x, staged = self.downsample(n, x, item[2]), None
+            else:
+                x, staged = self.upsample(n, x, item[2]), None
+        return x
+
     def encoder_chunk(self, x):
         """x f32 [T,H,W,8] (3 image channels + zero padding) -> f32 [T',H/8,W/8,32]."""
         p = "encoder"
         x = self.causal_conv(p + ".conv1", x)
-        for item in self.ENC_PLAN:
-            n = f"{p}.downsamples.{item[1]}"
-            x = self.residual_block(n, x) if item[0] == "res" else self.downsample(n, x, item[2])
-        x = self.residual_block(p + ".middle.0", x)
+        x = self._run_plan(p + ".downsamples", self.ENC_PLAN, x)
+        x, _ = self.residual_block(p + ".middle.0", x)
         x = self.attention_block(p + ".middle.1", x)
-        x = self.residual_block(p + ".middle.2", x)
+        x, _ = self.residual_block(p + ".middle.2", x)
         x = self.causal_conv(p + ".head.2", x, self.gammas[p + ".head.0"], True)
         self.chunk += 1
         return x
@@ -429,21 +528,25 @@ class WanVAEEngine:
         """x f32 [1,h,w,16] -> f32 [1 or 4, 8h, 8w, 4] (3 image channels + 1 padding)."""
         p = "decoder"
         x = self.causal_conv(p + ".conv1", x)
-        x = self.residual_block(p + ".middle.0", x)
+        x, _ = self.residual_block(p + ".middle.0", x)
         x = self.attention_block(p + ".middle.1", x)
-        x = self.residual_block(p + ".middle.2", x)
-        for item in self.DEC_PLAN:
-            n = f"{p}.upsamples.{item[1]}"
-            x = self.residual_block(n, x) if item[0] == "res" else self.upsample(n, x, item[2])
+        x, _ = self.residual_block(p + ".middle.2", x)
+        x = self._run_plan(p + ".upsamples", self.DEC_PLAN, x)
         x = self.causal_conv(p + ".head.2", x, self.gammas[p + ".head.0"], True)
         self.chunk += 1
         return x
 
     # ------------------------------------------------------------------ public entry points
     def encode(self, video):
-        """video f32 [3,T,H,W] in [-1,1] (T = 4k+1, H,W % 8 == 0) -> latents f32 [16,k+1,H/8,W/8] (reference :525-550)."""
+        """video f32 [3,T,H,W] in [-1,1] (T = 4k+1, H,W % 8 == 0) -> latents f32 [16,k+1,H/8,W/8] (reference :525-550).
+        With a SpatialShard every rank encodes its band of rows and the latent bands are gathered on every rank."""
         self.reset()
         C, T, H, W = video.shape
+        sh = self.shard
+        if sh is not None:
+            r0, r1 = sh.band(H // 8)
+            video = video[:, :, 8 * r0:8 * r1]
+            H = 8 * (r1 - r0)
         video = video.to(device=self.device, dtype=torch.float32).contiguous()
         n_lat = 1 + (T - 1) // 4
         feats = torch.empty(n_lat, H // 8, W // 8, 32, device=self.device, dtype=torch.float32)
@@ -462,12 +565,18 @@ class WanVAEEngine:
         out = torch.empty(16, n_lat, H // 8, W // 8, device=self.device, dtype=torch.float32)
         nv.vae_to_planar(mu, 16, 16, n_pix, self.neg_mean, self.inv_std, False, out)
         self.launches += 3
-        return out
+        return out if sh is None else sh.gather_bands(out, dim=2, scale=1)
 
     def decode(self, z):
-        """z f32 [16,T,h,w] -> video f32 [3,4T-3,8h,8w] clamped to [-1,1] (reference :552-575, :753-756)."""
+        """z f32 [16,T,h,w] -> video f32 [3,4T-3,8h,8w] clamped to [-1,1] (reference :552-575, :753-756).
+        With a SpatialShard every rank decodes its band of latent rows and the pixel bands are gathered on every rank."""
         self.reset()
         C, T, h, w = z.shape
+        sh = self.shard
+        if sh is not None:
+            r0, r1 = sh.band(h)
+            z = z[:, :, r0:r1]
+            h = r1 - r0
         z = z.to(device=self.device, dtype=torch.float32).contiguous()
         n_pix = T * h * w
         zb = torch.empty(n_pix, 16, device=self.device, dtype=torch.bfloat16)
@@ -486,7 +595,71 @@ class WanVAEEngine:
                                  ldc=Tout * 64 * h * w)
                 pos += 1
                 self.launches += 1
-        return out
+        return out if sh is None else sh.gather_bands(out, dim=2, scale=8)
+
+
+class SpatialShard:
+    """Split of the image rows over the ranks of a process group for the VAE (the VAE is causal in time,
+    so it shards in SPACE).  Latent row r belongs to rank `owner(r)`; every level of the encoder / decoder keeps that split
+    (x2 / x4 / x8 rows).  Neighbouring bands exchange one border row per conv input (WanVAEEngine._exchange_halo)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._latent_rows = None
+
+    # global ranks of the neighbours inside the group (P2POp takes the global rank)
+    def _global(self, r):
+        import torch.distributed as dist
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    def band(self, latent_rows):
+        """[r0, r1) latent rows of this rank; fixes the split for the whole encode / decode."""
+        P = self.world
+        if latent_rows < P:
+            raise RuntimeError(f"svi_b200: cannot split {latent_rows} latent rows over {P} ranks")
+        self._latent_rows = latent_rows
+        self.bounds = [latent_rows * r // P for r in range(P + 1)]
+        self.up = self._global(self.rank - 1) if self.rank > 0 else None
+        self.down = self._global(self.rank + 1) if self.rank + 1 < P else None
+        return self.bounds[self.rank], self.bounds[self.rank + 1]
+
+    def total_rows(self, my_rows):
+        """Rows of the whole image at the level where this rank holds `my_rows` rows."""
+        mine = self.bounds[self.rank + 1] - self.bounds[self.rank]
+        return self._latent_rows * (my_rows // mine)
+
+    def gather_rows(self, local, full, H, W):
+        """local bf16 [H*W, C] (this rank's tokens) -> full bf16 [>= total, C] holding every rank's tokens in row order."""
+        import torch.distributed as dist
+        mine = self.bounds[self.rank + 1] - self.bounds[self.rank]
+        scale = H // mine
+        C = local.shape[1]
+        counts = [(self.bounds[r + 1] - self.bounds[r]) * scale * W for r in range(self.world)]
+        mx = max(counts)
+        pad = torch.zeros(mx, C, device=local.device, dtype=local.dtype)
+        pad[:local.shape[0]] = local
+        parts = torch.empty(self.world, mx, C, device=local.device, dtype=local.dtype)
+        dist.all_gather_into_tensor(parts, pad, group=self.group)
+        off = 0
+        for r in range(self.world):
+            full[off:off + counts[r]] = parts[r, :counts[r]]
+            off += counts[r]
+        return full
+
+    def gather_bands(self, t, dim, scale):
+        """Concatenate every rank's band of `t` along `dim` (band heights = latent rows x scale) on every rank."""
+        import torch.distributed as dist
+        rows = [(self.bounds[r + 1] - self.bounds[r]) * scale for r in range(self.world)]
+        mx = max(rows)
+        shape = list(t.shape)
+        shape[dim] = mx
+        pad = torch.zeros(shape, device=t.device, dtype=t.dtype)
+        pad.narrow(dim, 0, t.shape[dim]).copy_(t)
+        parts = torch.empty([self.world] + shape, device=t.device, dtype=t.dtype)
+        dist.all_gather_into_tensor(parts, pad.contiguous(), group=self.group)
+        return torch.cat([parts[r].narrow(dim, 0, rows[r]) for r in range(self.world)], dim=dim)
 
 
 class WanVideoVAE(nn.Module):
@@ -536,16 +709,25 @@ class WanVideoVAE(nn.Module):
             warnings.warn(f"svi_b200: WanVideoVAE.{what}(tiled=True) runs UNTILED (tile_size / tile_stride ignored): results "
                           f"equal the reference's tiled=False path, not its blended tiles", stacklevel=3)
 
+    def enable_spatial_sharding(self, group=None):
+        """Split every encode / decode over the ranks of `group` (default: all ranks): each rank computes a band of image
+        rows, neighbouring bands exchange one border row per convolution, results are gathered on every rank."""
+        self.shard_group = (group,)
+
+    def _sharded(self, eng):
+        eng.shard = SpatialShard(self.shard_group[0]) if getattr(self, "shard_group", None) is not None else None
+        return eng
+
     def encode(self, videos, device, tiled=False, tile_size=(34, 34), tile_stride=(18, 16)):
         if tiled:
             self._note_untiled("encode")
-        eng = self.engine(device)
+        eng = self._sharded(self.engine(device))
         return torch.stack([eng.encode(v) for v in videos])
 
     def decode(self, hidden_states, device, tiled=False, tile_size=(34, 34), tile_stride=(18, 16)):
         if tiled:
             self._note_untiled("decode")
-        eng = self.engine(device)
+        eng = self._sharded(self.engine(device))
         return torch.stack([eng.decode(h) for h in hidden_states])
 
     @staticmethod

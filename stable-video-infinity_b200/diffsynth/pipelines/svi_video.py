@@ -172,6 +172,8 @@ class SVIVideoPipeline(BasePipeline):
             from ..distributed.sequence_parallel import get_sp_group
             pipe.sp_size = get_sp_group().world
             pipe.use_unified_sequence_parallel = True
+            if pipe.vae is not None and hasattr(pipe.vae, "enable_spatial_sharding"):
+                pipe.vae.enable_spatial_sharding()        # VAE: row bands over ALL ranks, halo exchange per conv
         return pipe
 
     def sp_group(self):

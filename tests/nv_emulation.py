@@ -23,8 +23,13 @@ def _act(v, act):
     return v
 
 
-def gemm(a, w, out, bias=None, act=0, gate=None, residual=None, sumsq=None, sumsq_group_cols=0):
+def gemm(a, w, out, bias=None, act=0, gate=None, residual=None, sumsq=None, sumsq_group_cols=0, ln=None, emit=None):
     v = a.float() @ w.float().T
+    if ln is not None:                             # LayerNorm folded into the GEMM: r (acc - mu u), then + c (= bias)
+        stats, u, dim, eps = ln
+        mean = stats[:, 0:1] / dim
+        r = torch.rsqrt((stats[:, 1:2] / dim - mean * mean).clamp_min(0) + eps)
+        v = r * (v - mean * u)
     if bias is not None:
         v = v + bias
     v = _act(v, act)
@@ -37,8 +42,28 @@ def gemm(a, w, out, bias=None, act=0, gate=None, residual=None, sumsq=None, sums
         v = v * gate
     if residual is not None:
         v = v + residual
+    if emit is not None:                           # next GEMM's folded operand + row statistics of the final value
+        a_next, g_next, row_stats = emit
+        a_next.copy_((v * g_next).to(a_next.dtype))
+        row_stats[:, 0] += v.sum(dim=1)
+        row_stats[:, 1] += (v * v).sum(dim=1)
     out.copy_(v.to(out.dtype))
     return out
+
+
+def ln_fold_prepare(mods, layers, g_out, rows):
+    D = mods.shape[1]
+    m = mods[:6 * layers].reshape(layers, 2, 3, D)
+    g = 1.0 + m[:, :, 1]
+    t = m[:, :, 0]
+    g_out.copy_(g)
+    gh, th = g.to(torch.bfloat16), t.to(torch.bfloat16)
+    rows.copy_(torch.stack([gh, (g - gh.float()).to(torch.bfloat16), th, (t - th.float()).to(torch.bfloat16)], dim=2))
+
+
+def ln_fold_combine(o4, bias, u, c):
+    u.copy_(o4[0] + o4[1])
+    c.copy_(o4[2] + o4[3] + (0 if bias is None else bias))
 
 
 def attention(q, k, v, out, num_heads, scale=None, accumulate=False, workspace=None):
@@ -170,7 +195,7 @@ def axpby(a, alpha, b, beta, out):
 
 _NAMES = ("gemm", "attention", "attention_workspace_bytes", "attention_qscale", "layernorm_modulate", "layernorm_modulate_split",
           "rmsnorm_rope", "qk_norm_rope", "patchify_gather", "unpatchify", "cfg_euler_step", "cast_f32_to_bf16",
-          "cast_bf16_to_f32", "split_f32_to_bf16x2", "zero_", "add_rows", "axpby")
+          "cast_bf16_to_f32", "split_f32_to_bf16x2", "zero_", "add_rows", "axpby", "ln_fold_prepare", "ln_fold_combine")
 
 
 def install(monkeypatch=None):

@@ -70,7 +70,9 @@ def test_golden_fixture_tiny_t2v():
     out = m(inp["x"].cuda(), torch.from_numpy(g["timestep"]), inp["context"].cuda()).float().cpu()
     inside, mx, rel = _stats(out, torch.from_numpy(g["out"]))
     print(f"golden tiny t2v: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
-    assert inside > 0.95 and mx < 0.012 and rel < 1.5e-3
+    # the fixture was generated from fp32 weights, the engine rounds them to bf16 (what a Wan checkpoint holds): the weight
+    # rounding, not the arithmetic, sets this bar (measured 0.853 / 1.6e-2 / 2.7e-3; with identical weights: test above)
+    assert inside > 0.82 and mx < 0.025 and rel < 3.5e-3
 
 
 def test_model_fn_and_cfg_euler_step_match_oracle():
@@ -93,7 +95,8 @@ def test_model_fn_and_cfg_euler_step_match_oracle():
     inside, mx, rel = _stats(lat.cpu(), ref)
     print(f"2-step denoise: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e}")
     # CFG (scale 5) amplifies the per-forward bf16 noise by ~sqrt(5^2 + 4^2) = 6.4x before the Euler update
-    assert inside > 0.5 and mx < 0.15 and rel < 2e-2
+    # (measured 0.818 / 3.8e-2 / 2.9e-3; round 1: 0.649 / 5.9e-2 / 5.5e-3)
+    assert inside > 0.75 and mx < 0.06 and rel < 4e-3
 
 
 def test_graph_replay_equals_eager_forward():
@@ -167,16 +170,17 @@ def test_teacache_denoise_matches_oracle():
     assert n_pos.skipped == o_pos.skipped == [1, 2, 4, 6] and n_neg.skipped == o_neg.skipped
     inside, mx, rel = _stats(lat.cpu(), ref)
     print(f"8-step TeaCache denoise: inside={inside:.4f} max={mx:.4e} mean/std={rel:.4e} skipped={n_pos.skipped}")
-    assert inside > 0.5 and rel < 2e-2
+    assert inside > 0.80 and rel < 3.5e-3          # measured 0.862 / 2.2e-3
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize("init,min_inside,max_err,max_rel", [("normal", 0.94, 0.012, 1.3e-3), ("torch_default", 0.98, 0.006, 7e-4)])
+@pytest.mark.parametrize("init,min_inside,max_err,max_rel", [("normal", 0.95, 0.013, 1.2e-3), ("torch_default", 0.995, 0.003, 3e-4)])
 def test_cfg1_1p3b_one_step_matches_oracle(init, min_inside, max_err, max_rel):
     """BASELINE config 1: Wan2.1-T2V-1.3B random-init, 1 denoise step, 17x320x512 (latent [1,16,5,40,64]).
     init="torch_default" is the reference constructors' own initialisation (the survey's 97.5 % / 0.005 bar);
     "normal" is tools.synth's wider N(0, 1/fan_in).  The CPU emulation of bf16 block-GEMM operands alone
-    (tools/rounding_study.py `blk`) gives 0.963 / 0.0085 / 1.0e-3 and better than 0.987 / 0.0049 / 7.2e-4."""
+    (tools/rounding_study.py `blk`) gives 0.963 / 0.0085 / 1.0e-3 and better than 0.987 / 0.0049 / 7.2e-4.
+    Measured on B200: 0.961 / 0.0107 / 1.03e-3 ("normal") and 1.0000 / 0.0014 / 1.9e-4 ("torch_default")."""
     from oracle import wan_dit_oracle as O
     cfg = synth.CFG_T2V_1_3B
     sd = {k: v.to(torch.bfloat16).float() for k, v in synth.make_dit_state_dict(cfg, seed=0, init=init).items()}
@@ -220,7 +224,7 @@ def test_block_at_bench_shape_matches_oracle():
     torch.cuda.synchronize()
     inside, mx, rel = _stats(xg.cpu(), ref)
     print(f"block @ L={L}: inside={inside:.5f} max={mx:.4e} mean/std={rel:.4e}")
-    assert inside > 0.995 and mx < 0.02 and rel < 6e-4
+    assert inside > 0.999 and mx < 0.008 and rel < 4.5e-4          # measured 0.99990 / 3.2e-3 / 2.9e-4
 
 
 @pytest.mark.slow

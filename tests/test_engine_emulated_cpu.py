@@ -24,7 +24,8 @@ def _model(cfg, sd):
     return m.to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("cfg,f,h,w,seed", [(synth.CFG_TINY_T2V, 3, 8, 12, 0), (synth.CFG_TINY_I2V, 2, 6, 10, 1)])
+@pytest.mark.parametrize("cfg,f,h,w,seed", [(synth.CFG_TINY_T2V, 3, 8, 12, 0), (synth.CFG_TINY_I2V, 2, 6, 10, 1),
+                                            (synth.CFG_TINY_T2V, 3, 16, 24, 2), (synth.CFG_TINY_I2V, 2, 20, 28, 3)])   # > 128 rows: LayerNorm fold
 def test_engine_orchestration_matches_oracle(monkeypatch, cfg, f, h, w, seed):
     from oracle import wan_dit_oracle as O
     import nv_emulation

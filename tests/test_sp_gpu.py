@@ -22,3 +22,16 @@ def test_plan_matches_single_gpu_and_oracle(n):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT)
     print(r.stdout[-6000:])
     assert r.returncode == 0 and "SP_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("n", [2, 4])
+def test_sharded_vae_equals_single_gpu(n):
+    """Spatially sharded VAE encode / decode (row bands + halo exchange) == the single-GPU engine, on every rank."""
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29670 + n), os.path.join(ROOT, "tools", "vae_shard_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0 and "VAE_SHARD_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

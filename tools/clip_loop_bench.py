@@ -43,8 +43,10 @@ class TokenPrompter:
 
 
 def main_from_bench(bargs):
-    """bench.py --workload cfg4: the chained-clip loop (BASELINE configs[3]) with bench's --clips."""
-    return main(["--clips", str(bargs.clips)])
+    """bench.py --workload cfg4: the chained-clip loop (BASELINE configs[3]) with bench's --clips; 14B-I2V when launched on
+    several GPUs (torchrun), the 1.3B-width I2V model on one."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return main(["--clips", str(bargs.clips)] + (["--model", "14b"] if world > 1 else []))
 
 
 def main(argv=None):
@@ -54,15 +56,21 @@ def main(argv=None):
     ap.add_argument("--motion-frames", type=int, default=5)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=832)
+    ap.add_argument("--model", default="1.3b-i2v", choices=["1.3b-i2v", "14b"])
     a = ap.parse_args(argv)
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from diffsynth import ModelManager, SVIVideoPipeline
     from diffsynth.models.wan_video_dit import WanModel, precompute_freqs_cis_3d
     from diffsynth.models.wan_video_image_encoder import WanImageEncoder
     from diffsynth.models.wan_video_text_encoder import WanTextEncoder
     from diffsynth.models.wan_video_vae import WanVideoVAE
     from diffsynth.prompters import WanPrompter
-    dev = "cuda"
-    cfg = dict(synth.CFG_T2V_1_3B, has_image_input=True, in_dim=36)
+    dev = f"cuda:{local}"
+    cfg = dict(synth.CFG_T2V_1_3B, has_image_input=True, in_dim=36) if a.model == "1.3b-i2v" else dict(synth.CFG_I2V_14B)
     with torch.device("meta"):
         dit = WanModel(**cfg)
     dit.load_state_dict(synth.make_dit_state_dict_fast(cfg, seed=0, device=dev, dtype=torch.bfloat16), assign=True)
@@ -79,7 +87,7 @@ def main(argv=None):
     mm.add_model("wan_video_dit", dit)
     mm.add_model("wan_video_vae", vae)
     mm.add_model("wan_video_image_encoder", ie)
-    pipe = SVIVideoPipeline.from_model_manager(mm, torch_dtype=torch.bfloat16, device=dev, is_test=True)
+    pipe = SVIVideoPipeline.from_model_manager(mm, torch_dtype=torch.bfloat16, device=dev, is_test=True, use_usp=world > 1)
     wp = WanPrompter()
     wp.fetch_models(te)
     pipe.text_encoder = te
@@ -99,12 +107,29 @@ def main(argv=None):
         cond = video[-a.motion_frames:]
         video_list += video[:-a.motion_frames] if k < a.clips - 1 else video
     steady = secs[1:] if len(secs) > 1 else secs
-    print(json.dumps({"workload": f"{a.clips} chained SVI clips, 81f x {a.height}x{a.width}, {a.steps} CFG steps, "
-                                  f"{a.motion_frames} recycled motion frames", "clip_seconds": secs,
-                      "steady_clip_s": sum(steady) / len(steady), "clips_per_hour": 3600.0 * len(steady) / sum(steady),
-                      "frames_kept": len(video_list), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
-                      "models": "1.3B-width I2V DiT + umT5-XXL + CLIP ViT-H + Wan VAE, random init",
-                      "note": "first clip includes one-time engine builds, graph capture and kernel attribute setup"}))
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([sum(steady) / len(steady)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        steady_s = t.item()
+        plan = pipe.sp_group().describe() + " + VAE row bands over all ranks"
+    else:
+        steady_s, plan = sum(steady) / len(steady), "single"
+    if rank == 0:
+        print(json.dumps({"metric": "SVI clips per hour (81f, 50 CFG steps, encoders + VAE + clip hand-off included)",
+                          "value": 3600.0 / steady_s, "unit": "clips/h", "n_gpus": world, "higher_is_better": True,
+                          "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": "cfg4", "description": f"{a.clips} chained SVI clips, 81f x {a.height}x{a.width}, "
+                                     f"{a.steps} CFG steps, {a.motion_frames} recycled motion frames (BASELINE configs[3])",
+                                     "parallelism": plan,
+                                     "models": ("Wan2.1-I2V-14B" if a.model == "14b" else "1.3B-width I2V DiT") +
+                                               " + umT5-XXL + CLIP ViT-H + Wan VAE, random init"},
+                          "clip_seconds": secs, "steady_clip_s": steady_s, "clips_per_hour": 3600.0 / steady_s,
+                          "frames_kept": len(video_list), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                          "api": "SVIVideoPipeline.__call__ (use_usp=True on N > 1)",
+                          "note": "first clip includes one-time engine builds, graph capture and kernel attribute setup"}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
