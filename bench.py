@@ -431,6 +431,25 @@ def main():
         cb.record()
         torch.cuda.synchronize()
         ctx_ms = ca.elapsed_time(cb) / 3
+        # one more e2e step with its phases bracketed (stderr): where the e2e - value difference goes
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        t_h0 = time.perf_counter()
+        evs[0].record()
+        xx = lat_h.to(dev, non_blocking=True)
+        evs[1].record()
+        cpx = eng.context_state(ctx_pos_host.to(dev, non_blocking=True), clip_dev) if own0 else None
+        cnx = eng.context_state(ctx_neg_host.to(dev, non_blocking=True), clip_dev) if own1 else pipe.OTHER_RANK
+        t_h1 = time.perf_counter()
+        evs[2].record()
+        step(0, x=xx, cpx=cpx, cnx=cnx)
+        evs[3].record()
+        out_host.copy_(xx, non_blocking=True)
+        evs[4].record()
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(f"e2e phases (ms): h2d latents {evs[0].elapsed_time(evs[1]):.2f} | prompt h2d + context_state {evs[1].elapsed_time(evs[2]):.2f} "
+                  f"(host {1e3 * (t_h1 - t_h0):.2f}) | step {evs[2].elapsed_time(evs[3]):.2f} | d2h {evs[3].elapsed_time(evs[4]):.2f}",
+                  file=sys.stderr, flush=True)
         h2d = lat_host.numel() * 4 + (int(own0) + int(own1)) * ctx_pos_host.numel() * 4
         e2e = {"value": f / (CLIP_STEPS * e2e_ms / 1e3), "unit": "latent_frames/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lat_host.numel() * 4, "context_state_ms_per_prompt": ctx_ms,

@@ -2,19 +2,20 @@
 //
 // One CTA owns TWO 128-row Q tiles of one head and streams K/V tiles of 128 rows past them:
 //
-//   warps 0-3  : softmax warpgroup for Q tile 0 (thread = row; TMEM lane quadrant = warp % 4)   224 registers
-//   warps 4-7  : softmax warpgroup for Q tile 1                                                 224 registers
-//   warp  8    : TMA producer (Q once, then K_j / V_j into 2-stage rings, 128B-swizzled boxes)   56 registers
-//   warp  9    : tcgen05.mma issuer + TMEM owner                                                 56 registers
+//   warps 0-3  : softmax warpgroup for Q tile 0 (thread = row; TMEM lane quadrant = warp % 4)   208 registers
+//   warps 4-7  : softmax warpgroup for Q tile 1                                                 208 registers
+//   warp  8    : TMA producer (Q once, then K_j / V_j into 2-stage rings, 128B-swizzled boxes)   88 registers
+//   warp  9    : tcgen05.mma issuer + TMEM owner                                                 88 registers
 //   warps 10-11: idle (they complete the third warpgroup: setmaxnreg is a warpgroup-wide instruction)
 //
-// What bounds it (ncu source view of the round-1 kernel, profiles/r02_attn_analysis.md): the softmax warps are bound by
-// ISSUE CYCLES on their SM sub-partition, not by latency — FFMA2 / FADD2 / FMNMX3 / IMAD each hold the issue port for two
-// cycles, and one sub-partition serves one warp of each softmax warpgroup.  Per 128x128 tile and warp the round-1 code
-// needed ~1125 issue cycles (x2 warps = 2250 per K/V step against 2048 tensor-pipe cycles).  This version: setmaxnreg
-// gives the softmax threads 224 registers (no spills, no register-shuffling IMAD.MOVs: 98 -> 29 IMADs), and the share of
-// exponentials computed by the FMA-pipe polynomial is 3 of 16 pairs instead of 6 (each polynomial pair costs 18 issue
-// cycles to save 16 XU cycles): ~825 issue cycles and ~830 XU cycles per tile and warp, both below the tensor time.
+// What bounds it (ncu source view of the round-1 kernel, profiles/r02_attn_analysis.md): in the softmax loop every issued
+// instruction carried ~1.1 cycles of `stall_wait` on top of its issue slot (FFMA2 / FADD2 / FMNMX3 / IMAD hold the port for two
+// cycles), ~100 IMADs were register shuffles forced by the 168-register ceiling, and one SM sub-partition serves one warp of
+// each softmax warpgroup — the round-1 loop needed ~2200 cycles per 128x128 tile and warp where the tensor pipe needs 1024.
+// This version: `setmaxnreg` moves registers from the TMA / MMA / idle warpgroup (88) to the softmax warpgroups (208): no
+// spills, 29 IMADs instead of 98; the share of exponentials computed by the FMA-pipe polynomial was re-swept with that
+// (TF/s at L = 32760, H = 12, same box: 4/16 1391, 6/16 1378, 8/16 1334, 10/16 1227, 16/16 1028; all-MUFU 1315 on a slower
+// box where 3/16 gave 1288) -> 5/16.  Same box, same run: round-1 kernel 1252 TF/s, this one 1411.
 //
 // TMEM (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,384) | O1 [384,512); P_i (bf16, 64 columns)
 // aliases the front of S_i and is consumed straight from TMEM by the P*V MMA (A operand in TMEM).
@@ -41,13 +42,13 @@ constexpr int HALF_BYTES = 128 * 64 * 2;   // one 128-row x 64-col swizzled box 
 constexpr int TILE_BYTES = 2 * HALF_BYTES;  // 128 x 128 bf16 (32 KB)
 constexpr int NUM_THREADS = 384;   // 12 warps = 3 warpgroups: setmaxnreg is a warpgroup-wide instruction
 #ifndef SVI_ATTN_POLY16
-#define SVI_ATTN_POLY16 6            // exponentials on the FMA pipes: this many of every 16 element pairs
+#define SVI_ATTN_POLY16 5            // exponentials on the FMA pipes: this many of every 16 element pairs
 #endif
 #ifndef SVI_ATTN_OTHER_REGS
-#define SVI_ATTN_OTHER_REGS 56
+#define SVI_ATTN_OTHER_REGS 88
 #endif
 #ifndef SVI_ATTN_SOFTMAX_REGS
-#define SVI_ATTN_SOFTMAX_REGS 224
+#define SVI_ATTN_SOFTMAX_REGS 208
 #endif
 // setmaxnreg only redistributes the registers the CTA was launched with (384 threads x 168): a larger request than the
 // pool holds blocks forever
@@ -132,7 +133,7 @@ __device__ __forceinline__ void wait_kv_chunk(const uint32_t* flags, int chunk, 
 
 // Register budget: the kernel starts with 65536 / 384 = 168 registers per thread; once the roles are fixed the TMA / MMA /
 // idle warpgroup drops to SVI_ATTN_OTHER_REGS and the two softmax warpgroups grow to SVI_ATTN_SOFTMAX_REGS
-// (256*224 + 128*56 = 64512 = the launch allocation: setmaxnreg can only redistribute what the CTA already owns).
+// (256*208 + 128*88 = 64512 = the launch allocation: setmaxnreg can only redistribute what the CTA already owns).
 __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SVI_ATTN_SOFTMAX_REGS));
 }

@@ -30,10 +30,11 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quadrant, each draining one 128-column half of the tile
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
-constexpr int STAGES = 6;       // 7 fit but measured 1-2 % slower
+constexpr int STAGES = 5;       // 6 before the epilogue got its transposition tiles (7 fit then but measured 1-2 % slower)
 constexpr int GROUP_M = 4;      // measured: 1..4 equal on M >> N shapes, 4..8 best on square ones
 constexpr int VEC_BYTES = 2 * 4 * BN * 4;   // bias, gate, LN-fold u and next-operand scale of the tile's 256 columns, double buffered by accumulator
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + VEC_BYTES;
+constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;   // one 32 x 32 fp32 tile per epilogue warp (residual-class epilogue)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + VEC_BYTES + XPOSE_BYTES;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> even CTA
 
 struct Epi {
@@ -166,7 +167,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   enum : uint32_t { FULL = 0, EMPTY = STAGES, TMEM_FULL = 2 * STAGES, TMEM_EMPTY = 2 * STAGES + 2, NUM_BARS = 2 * STAGES + 4 };
   auto bar = [&](uint32_t n) { return sbase + OFF_BAR + 8u * n; };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_raw + (sbase - sraw) + OFF_BAR + 8 * NUM_BARS);
-  float* vec_smem = reinterpret_cast<float*>(smem_raw + (sbase - sraw) + OFF_BAR + 256);   // [2 acc][bias | gate][BN]
+  float* vec_smem = reinterpret_cast<float*>(smem_raw + (sbase - sraw) + OFF_BAR + 256);   // [2 acc][bias | gate | u | g_next][BN]
+  uint8_t* xpose_smem = smem_raw + (sbase - sraw) + OFF_BAR + 256 + VEC_BYTES;            // [EPI_WARPS][32 rows][128 B], 16 B chunks XOR-swizzled
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -264,8 +266,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tile_coords(tile, num_m, num_n, group_m, m_blk, n_blk);
       const int row = m_blk * 2 * BM + (int)rank * BM + row_in_tile;
       const bool row_ok = row < M;
-      if (ep.residual) {
-        // Residual rows -> L2 ahead of use.  When the epilogue is the slower side (K = 1536 with an fp32 residual) it
+      if (ep.residual && !(ep.out_is_f32 && ep.act == SVI_ACT_NONE && !ep.sumsq && !ep.ln_stats)) {
+        // Residual rows -> L2 ahead of use (row-owner epilogues only; the coalesced residual class reads whole lines).  When the epilogue is the slower side (K = 1536 with an fp32 residual) it
         // starts a tile the moment it has finished the previous one, so a prefetch of THIS tile would be issued only
         // nanoseconds before its first loads; the tile this CTA drains NEXT is prefetched instead (one K loop ahead),
         // and the very first tile prefetches itself.
@@ -311,11 +313,72 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ln_nmu = -mean;
       }
       float ps = 0.f, pq = 0.f;           // producer: sum / sum of squares of the final values of this row (this tile half)
+      // Residual-class epilogue (fp32 out = residual + gate * (acc + bias): o / cross-o / ffn.2 / patch embedding).  With the
+      // thread = row mapping of tcgen05.ld every 16-byte access of a warp touches 32 different rows, and the LSU tag stage
+      // (one 128-byte line per clock) capped the o-projection class at 2.2 TB/s (219 us against a 100 us HBM floor).  Here
+      // the 32 x 32 chunk is transposed through a warp-private swizzled shared-memory tile so that global loads / stores
+      // run with 8 lanes per 128-byte row segment: 4 lines per instruction instead of 32.
+      const bool coal = ep.out_is_f32 && ep.residual && ep.act == SVI_ACT_NONE && !ep.sumsq && !ep.ln_stats;
+      uint8_t* xt = xpose_smem + (warp - 2) * 4096;
+      const int cq = lane & 7, cg = lane >> 3;          // column chunk (4 floats) / row group of this lane in the coalesced phase
+      float ps8[8], pq8[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) ps8[it] = pq8[it] = 0.f;
 #pragma unroll 1
       for (int c = col_half * 4; c < col_half * 4 + 4; ++c) {
         const int n0 = n_blk * BN + c * 32;
         if (n0 >= N) break;
         const bool whole = n0 + 32 <= N;     // all 32 columns of the chunk exist (always, except in the last N tile)
+        if (coal && whole) {
+          const int row_w0 = m_blk * 2 * BM + (int)rank * BM + quad * 32;      // first row of this warp's 32
+          float4 res[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int gr = row_w0 + it * 4 + cg;
+            res[it] = gr < M ? *reinterpret_cast<const float4*>(ep.residual + (long long)gr * ep.ldr + n0 + cq * 4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          uint32_t r[32];
+          tmem_ld32(t_base + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {       // bias / gate in the row-owner form, then into the transposition tile
+            float4 v = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                                   __uint_as_float(r[q * 4 + 3]));
+            if (ep.bias) {
+              const float4 b = *reinterpret_cast<const float4*>(sbias + c * 32 + q * 4);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (ep.gate) {
+              const float4 g = *reinterpret_cast<const float4*>(sgate + c * 32 + q * 4);
+              v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+            }
+            *reinterpret_cast<float4*>(xt + lane * 128 + ((q ^ (lane & 7)) << 4)) = v;
+          }
+          __syncwarp();
+          float4 gn = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.a_next) gn = *reinterpret_cast<const float4*>(sgnext + c * 32 + cq * 4);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + cg;
+            const int gr = row_w0 + rr;
+            float4 v = *reinterpret_cast<const float4*>(xt + rr * 128 + ((cq ^ (rr & 7)) << 4));
+            v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w;
+            if (gr < M) {
+              if (ep.a_next) {
+                ps8[it] += (v.x + v.y) + (v.z + v.w);
+                pq8[it] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                uint2 an;
+                an.x = pack_bf16x2(v.x * gn.x, v.y * gn.y);
+                an.y = pack_bf16x2(v.z * gn.z, v.w * gn.w);
+                *reinterpret_cast<uint2*>(ep.a_next + (long long)gr * ep.ld_an + n0 + cq * 4) = an;
+              }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (long long)gr * ep.ldo + n0 + cq * 4) = v;
+            }
+          }
+          __syncwarp();       // the tile is rewritten by the next chunk
+          continue;
+        }
         // residual of the whole chunk first: eight independent 16-byte loads in flight under the TMEM load (with an
         // in-place residual the compiler may not move them above the stores of the previous group itself)
         float4 res[8];
@@ -418,9 +481,28 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       if (row_ok && ep.sumsq && ss_group >= 0 && ss_group < ep.sumsq_groups)
         atomicAdd(&ep.sumsq[(long long)row * ep.sumsq_groups + ss_group], ss);
-      if (row_ok && ep.a_next) {
-        atomicAdd(&ep.row_stats[2LL * row], ps);
-        atomicAdd(&ep.row_stats[2LL * row + 1], pq);
+      if (ep.a_next) {
+        if (coal) {       // row sums of the coalesced phase: 8 lanes share a row
+          const int row_w0 = m_blk * 2 * BM + (int)rank * BM + quad * 32;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            float a = ps8[it], b = pq8[it];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, o);
+              b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            const int gr = row_w0 + it * 4 + cg;
+            if (cq == 0 && gr < M) {
+              atomicAdd(&ep.row_stats[2LL * gr], a);
+              atomicAdd(&ep.row_stats[2LL * gr + 1], b);
+            }
+          }
+        }
+        if (row_ok && (ps != 0.f || pq != 0.f)) {     // chunks that took the row-owner path (ragged last N tile)
+          atomicAdd(&ep.row_stats[2LL * row], ps);
+          atomicAdd(&ep.row_stats[2LL * row + 1], pq);
+        }
       }
       tc_fence_before();
       __syncwarp();

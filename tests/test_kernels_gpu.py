@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("section", ["gemm", "gemm_epi", "attn", "attn_cross", "attn_bench", "abi3", "ew", "conv"])
+@pytest.mark.parametrize("section", ["gemm", "gemm_epi", "attn", "attn_cross", "attn_bench", "abi3", "ln_fold", "ew", "conv"])
 def test_kernel_section(section):
     from tools import gpu_check as G
     G.RESULTS.clear()

@@ -106,6 +106,46 @@ def sec_gemm_epi():
     report("epi sumsq", ss, ref_ss, 2e-3)
 
 
+def sec_ln_fold():
+    """LayerNorm folded into the CTA-pair GEMM: producer (a_next = bf16(v * g), row statistics) and consumer
+    (r (acc - mu u) + c) against the explicit LayerNorm -> modulate -> Linear in fp32."""
+    g = torch.Generator(device="cpu").manual_seed(21)
+    for (M, d, N) in [(300, 1536, 4608), (1000, 256, 512), (777, 1536, 1536)]:
+        x0 = (torch.randn(M, d, generator=g) * 1.5 + 0.2).to(dev)
+        a = (torch.randn(M, 512, generator=g) * 0.3).to(dev, torch.bfloat16)
+        wo = (torch.randn(d, 512, generator=g) * 0.05).to(dev, torch.bfloat16)
+        bo, gate = torch.randn(d, generator=g).to(dev) * 0.1, torch.randn(d, generator=g).to(dev)
+        gmod = (1 + 0.1 * torch.randn(d, generator=g)).to(dev)
+        tmod = (0.1 * torch.randn(d, generator=g)).to(dev)
+        # producer: x = x0 + gate * (a wo^T + bo), emits bf16(x * gmod) and (sum x, sum x^2)
+        x = x0.clone()
+        a_next = torch.full((M, d), float("nan"), device=dev, dtype=torch.bfloat16)
+        stats = torch.zeros(M, 2, device=dev)
+        nv.gemm(a, wo, x, bias=bo, gate=gate, residual=x, emit=(a_next, gmod, stats))
+        x_ref = x0 + gate * (a.float() @ wo.float().t() + bo)
+        report(f"fold producer out M={M} d={d}", x, x_ref, 2e-3)
+        report(f"fold producer a_next M={M} d={d}", a_next, x_ref * gmod, 6e-3)
+        report(f"fold producer row stats M={M} d={d}", stats, torch.stack([x_ref.sum(1), (x_ref ** 2).sum(1)], 1), 2e-3)
+        # consumer: (LN(x) * gmod + tmod) w^T + b  ==  r (acc - mu u) + c with u = w gmod, c = w tmod + b
+        w = (torch.randn(N, d, generator=g) / d ** 0.5).to(dev, torch.bfloat16)
+        b = torch.randn(N, generator=g).to(dev) * 0.1
+        u = w.float() @ gmod
+        cvec = w.float() @ tmod + b
+        out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+        ss = torch.zeros(M, 1, device=dev)
+        nv.gemm(a_next, w, out, bias=cvec, sumsq=ss, sumsq_group_cols=N, ln=(stats, u, d, 1e-6))
+        h = torch.nn.functional.layer_norm(x_ref, (d,), eps=1e-6) * gmod + tmod
+        ref = h @ w.float().t() + b
+        report(f"fold consumer M={M} d={d} N={N}", out, ref, 1.5e-2, min_inside=0.97)
+        report(f"fold consumer sumsq M={M}", ss, (ref ** 2).sum(1, keepdim=True), 1e-2)
+        # the unfused path on the same numbers, for scale: LN kernel -> bf16 -> GEMM
+        hb = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
+        nv.layernorm_modulate(x, hb, 1e-6, scale=gmod - 1, shift=tmod)
+        out2 = torch.empty_like(out)
+        nv.gemm(hb, w, out2, bias=b)
+        report(f"(unfused LN -> GEMM on the same inputs) M={M} d={d} N={N}", out2, ref, 1.5e-2, min_inside=0.97)
+
+
 def attn_ref(q, k, v, H, scale):
     Lq, Lk = q.shape[0], k.shape[0]
     qh = q.float().view(Lq, H, 128).transpose(0, 1)
@@ -378,6 +418,39 @@ def sec_perf_gemm_epi():
     for name, fn, fl in cases:
         ms = time_ms(fn)
         print(f"[PERF] gemm {name}: {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
+def sec_perf_ln_fold():
+    """The LayerNorm fold's cost per GEMM at the bench shape: consumer (ffn.0 with GELU, qkv with the row sums) and producer
+    (o-projection class emitting the next operand + row statistics) against the same GEMMs without the fold and the
+    LayerNorm kernel they replace."""
+    g = torch.Generator(device="cpu").manual_seed(7)
+    L, d, f = 32760, 1536, 8960
+    h = torch.randn(L, d, generator=g).to(dev, torch.bfloat16)
+    x = torch.randn(L, d, generator=g).to(dev)
+    gate = torch.randn(d, generator=g).to(dev)
+    mk = lambda n, k: (torch.randn(n, k, generator=g) * 0.02).to(dev, torch.bfloat16)
+    w_qkv, w_o, w_f0 = mk(3 * d, d), mk(d, d), mk(f, d)
+    b3, b1, bf_ = torch.randn(3 * d, generator=g).to(dev), torch.randn(d, generator=g).to(dev), torch.randn(f, generator=g).to(dev)
+    u3, u0 = torch.randn(3 * d, generator=g).to(dev), torch.randn(f, generator=g).to(dev)
+    stats = torch.stack([torch.randn(L, generator=g) * 10, torch.rand(L, generator=g) * d + d], 1).to(dev).contiguous()
+    qkv = torch.empty(L, 3 * d, device=dev, dtype=torch.bfloat16)
+    ffn = torch.empty(L, f, device=dev, dtype=torch.bfloat16)
+    a_next = torch.empty(L, d, device=dev, dtype=torch.bfloat16)
+    rs = torch.zeros(L, 2, device=dev)
+    ss = torch.zeros(L, 2, device=dev)
+    cases = [
+        ("ffn0 bias+gelu", lambda: nv.gemm(h, w_f0, ffn, bias=bf_, act=nv.ACT_GELU_TANH), 2.0 * L * f * d),
+        ("ffn0 bias+gelu + LN consumer", lambda: nv.gemm(h, w_f0, ffn, bias=bf_, act=nv.ACT_GELU_TANH, ln=(stats, u0, d, 1e-6)), 2.0 * L * f * d),
+        ("qkv bias+sumsq", lambda: nv.gemm(h, w_qkv, qkv, bias=b3, sumsq=ss, sumsq_group_cols=d), 2.0 * L * 3 * d * d),
+        ("qkv bias+sumsq + LN consumer", lambda: nv.gemm(h, w_qkv, qkv, bias=b3, sumsq=ss, sumsq_group_cols=d, ln=(stats, u3, d, 1e-6)), 2.0 * L * 3 * d * d),
+        ("o gate+residual", lambda: nv.gemm(h, w_o, x, bias=b1, gate=gate, residual=x), 2.0 * L * d * d),
+        ("o gate+residual + emit", lambda: nv.gemm(h, w_o, x, bias=b1, gate=gate, residual=x, emit=(a_next, gate, rs)), 2.0 * L * d * d),
+        ("layernorm_modulate (the launch a folded pair replaces)", lambda: nv.layernorm_modulate(x, a_next, 1e-6, scale=gate, shift=b1), 0.0),
+    ]
+    for name, fn, fl in cases:
+        ms = time_ms(fn)
+        print(f"[PERF] {name}: {ms * 1e3:.1f} us" + (f" = {fl / ms / 1e9:.1f} TFLOP/s" if fl else ""), flush=True)
 
 
 def sec_perf_attn4():
