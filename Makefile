@@ -33,9 +33,10 @@ fastmath:
 # attention A/B builds (measurement only, selected with SVI_B200_LIB): share of exponentials on the FMA-pipe polynomial
 attn_variants:
 	@mkdir -p $(PKG)/lib build
-	for q in 4 6; do $(NVCC) $(NVFLAGS) -DSVI_ATTN_POLY16=$$q -shared -o $(PKG)/lib/libsvi_b200_attn_poly$$q.so $(SRCS) -cudart shared || exit 1; done
-	$(NVCC) $(NVFLAGS) -DSVI_ATTN_OTHER_REGS=104 -DSVI_ATTN_SOFTMAX_REGS=200 -shared -o $(PKG)/lib/libsvi_b200_attn_regs200.so $(SRCS) -cudart shared
-	$(NVCC) $(NVFLAGS) -DSVI_ATTN_OTHER_REGS=56 -DSVI_ATTN_SOFTMAX_REGS=224 -shared -o $(PKG)/lib/libsvi_b200_attn_regs224.so $(SRCS) -cudart shared
+	$(NVCC) $(NVFLAGS) -DSVI_ATTN_COLSPLIT=1 -shared -o $(PKG)/lib/libsvi_b200_attn_colsplit.so $(SRCS) -cudart shared
+	$(NVCC) $(NVFLAGS) -DSVI_ATTN_COLSPLIT=1 -DSVI_ATTN_POLY16=4 -shared -o $(PKG)/lib/libsvi_b200_attn_colsplit_p4.so $(SRCS) -cudart shared
+	$(NVCC) $(NVFLAGS) -DSVI_ATTN_COLSPLIT=1 -DSVI_ATTN_POLY16=7 -shared -o $(PKG)/lib/libsvi_b200_attn_colsplit_p7.so $(SRCS) -cudart shared
+	$(NVCC) $(NVFLAGS) -DSVI_ATTN_COLSPLIT=1 -DSVI_ATTN_OTHER_REGS=120 -DSVI_ATTN_SOFTMAX_REGS=192 -shared -o $(PKG)/lib/libsvi_b200_attn_colsplit_r192.so $(SRCS) -cudart shared
 
 # the library with the ROUND-1 attention kernel (320 threads, 168 registers, 6/16 polynomial share) for same-box A/B runs
 attn_r1:

@@ -437,8 +437,17 @@ def main():
         evs[0].record()
         xx = lat_h.to(dev, non_blocking=True)
         evs[1].record()
+        prof = None
+        if os.environ.get("SVI_BENCH_PROFILE") == "1":
+            import cProfile
+            prof = cProfile.Profile()
+            prof.enable()
         cpx = eng.context_state(ctx_pos_host.to(dev, non_blocking=True), clip_dev) if own0 else None
         cnx = eng.context_state(ctx_neg_host.to(dev, non_blocking=True), clip_dev) if own1 else pipe.OTHER_RANK
+        if prof is not None:
+            import pstats
+            prof.disable()
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(18)
         t_h1 = time.perf_counter()
         evs[2].record()
         step(0, x=xx, cpx=cpx, cnx=cnx)

@@ -44,6 +44,9 @@ constexpr int NUM_THREADS = 384;   // 12 warps = 3 warpgroups: setmaxnreg is a w
 #ifndef SVI_ATTN_POLY16
 #define SVI_ATTN_POLY16 5            // exponentials on the FMA pipes: this many of every 16 element pairs
 #endif
+#ifndef SVI_ATTN_COLSPLIT
+#define SVI_ATTN_COLSPLIT 0         // 1: both softmax warpgroups work on the same Q tile (64 key columns each)
+#endif
 #ifndef SVI_ATTN_OTHER_REGS
 #define SVI_ATTN_OTHER_REGS 88
 #endif
@@ -55,7 +58,8 @@ constexpr int NUM_THREADS = 384;   // 12 warps = 3 warpgroups: setmaxnreg is a w
 static_assert(2 * SVI_ATTN_SOFTMAX_REGS + SVI_ATTN_OTHER_REGS <= 3 * 168, "register split exceeds the CTA's allocation");
 static_assert(SVI_ATTN_SOFTMAX_REGS % 8 == 0 && SVI_ATTN_OTHER_REGS % 8 == 0, "setmaxnreg takes multiples of 8");
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
+constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;   // row-max exchange between the two halves of a row: [parity][tile][half][row]
+constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256 + XCH_BYTES;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 __device__ __forceinline__ float ex2(float x) {
@@ -144,6 +148,7 @@ constexpr uint32_t OFF_Q = 0;                                   // [2][TILE_BYTE
 constexpr uint32_t OFF_K = 2 * TILE_BYTES;                      // [KV_STAGES][TILE_BYTES]
 constexpr uint32_t OFF_V = OFF_K + KV_STAGES * TILE_BYTES;      // [KV_STAGES][TILE_BYTES]
 constexpr uint32_t OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
+constexpr uint32_t OFF_XCH = OFF_BAR + 256;
 enum : uint32_t {
   Q_FULL = 0,    // [2]
   K_FULL = 2,    // [2]
@@ -270,6 +275,190 @@ __device__ __forceinline__ void mma_role(const Params& p, uint32_t sbase, uint32
   }
 }
 
+#if SVI_ATTN_COLSPLIT
+// ------------------------------------ softmax warpgroups -------------------------------------------
+// Column split: warpgroup h (warps 4h..4h+3) owns key columns [64h, 64h+64) of BOTH Q tiles' S; thread = one row x 64 keys.
+// Warps w and w+4 hold the same 32 rows (same TMEM lane quadrant, same SM sub-partition) and work on the same tile at the
+// same time, so the S -> softmax -> P leg of a tile's dependency chain takes half as long as with one warpgroup per tile
+// (the tensor pipe was idle ~40 % of the time waiting for that leg: profiles/r02_attn_analysis.md).  The two halves of a
+// row exchange their maxima through shared memory behind a 64-thread named barrier (one per tile and quadrant); that
+// barrier also orders "warpgroup 0 has loaded S columns 32..63" before "warpgroup 1 overwrites them with its half of P".
+// Each warpgroup hands its 64-key half of P to the MMA warp on its own p_ready barrier, keeps its half of the row sum and
+// rescales / normalises / stores its 64 output columns.
+__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__device__ __forceinline__ void softmax_role(const Params& p, uint32_t sbase, uint32_t tmem_base, int warp, int lane) {
+  const Unit u = decode_unit(p);
+  const int n_kv = u.n_kv;
+  const uint32_t bars = sbase + OFF_BAR;
+  const int h = warp >> 2;    // which 64-key half of every S tile
+  const int quad = warp & 3;  // TMEM lane quadrant = 32 rows of both Q tiles
+  const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+  const int rl = quad * 32 + lane;                                  // row inside a Q tile
+  float* xch = reinterpret_cast<float*>(__cvta_shared_to_generic(sbase + OFF_XCH));     // [2 parity][2 tile][2 half][128 rows]
+  float c[2], m_cur[2], l[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    c[i] = p.scale_log2;
+    if (p.q_sumsq) {          // this thread's Q rows carry their RMSNorm factor in the softmax scale
+      const int qrow = min(u.q_row0 + i * BQ + rl, p.Lq - 1);
+      c[i] *= rsqrtf(__ldg(p.q_sumsq + (long long)qrow * p.q_ss_ld) * p.q_inv_d + p.q_eps);
+    }
+    m_cur[i] = -INFINITY;     // running row max (scaled, log2 domain); reference point of P and O; identical in both halves
+    l[i] = 0.f;               // running sum of THIS half's P
+  }
+
+  for (int j = 0; j < n_kv; ++j) {
+    const int limit = p.Lk - kv_tile_at(u.j_begin + j, p.kv_first_tile, u.n_kv_total) * BKV - h * 64;  // valid columns of my half
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t tS = tmem_base + i * 128 + lane_sel;
+      const uint32_t tO = tmem_base + 256 + i * 128 + lane_sel;
+      mbar_wait_a(bars + 8 * (S_FULL + i), j & 1);
+      tc_fence_after();
+      uint32_t sr[2][32];
+      tmem_ld32(tS + h * 64, sr[0]);
+      tmem_ld32(tS + h * 64 + 32, sr[1]);
+      tmem_ld_wait();
+      if (limit < 64) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (cc * 32 + e >= limit) sr[cc][e] = 0xff800000u;  // -inf: masked key column
+      }
+      float m8[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) m8[q] = fmaxf(__uint_as_float(sr[0][q]), __uint_as_float(sr[0][q + 8]));
+#pragma unroll
+      for (int e = 16; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[0][e]));
+#pragma unroll
+      for (int e = 0; e < 32; ++e) m8[e & 7] = fmaxf(m8[e & 7], __uint_as_float(sr[1][e]));
+      const float mloc = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+      // exchange with the other half of the row (warp ^ 4): double-buffered by step parity
+      float* xr = xch + (((j & 1) * 2 + i) * 2) * 128;
+      xr[h * 128 + rl] = mloc;
+      pair_bar(1 + i * 4 + quad);
+      const float mx = fmaxf(mloc, xr[(h ^ 1) * 128 + rl]) * c[i];
+      // lazy rescale (warp-uniform decision; both halves of a row see the same mx, hence take the same decision)
+      const bool need = (j > 0) && (mx > m_cur[i] + RESCALE_THRESHOLD);
+      if (j == 0) {
+        m_cur[i] = mx;
+      } else if (__any_sync(0xffffffffu, need)) {
+        const float m_new = fmaxf(m_cur[i], mx);
+        const float alpha = ex2(m_cur[i] - m_new);
+        l[i] *= alpha;
+        m_cur[i] = m_new;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {          // my 64 output columns
+          uint32_t r[32];
+          tmem_ld32(tO + h * 64 + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+          tmem_st32(tO + h * 64 + cc * 32, r);
+        }
+        tmem_st_wait();
+        pair_bar(1 + i * 4 + quad);               // the P*V of either half accumulates into ALL 128 columns of O
+      }
+      // P = exp2(S*c - m) (masked columns: exp2(-inf) = 0), bf16 pack into TMEM columns [32h, 32h+32) of the tile
+      float2 l4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 c2 = make_float2(c[i], c[i]), nm2 = make_float2(-m_cur[i], -m_cur[i]);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const int pr = e >> 1;   // pair index 0..15 inside the chunk
+          float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[cc][e]), __uint_as_float(sr[cc][e + 1])), c2, nm2);
+          float2 pv;
+          if (pr < SVI_ATTN_POLY16) {   // FMA/ALU-pipe exponential
+            pv = exp2_poly2(x);
+          } else {                      // MUFU exponential
+            pv.x = ex2(x.x);
+            pv.y = ex2(x.y);
+          }
+          l4[pr & 3] = __fadd2_rn(l4[pr & 3], pv);
+          pk[pr] = pack_bf16x2(pv.x, pv.y);
+        }
+        tmem_st16(tS + h * 32 + cc * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(bars + 8 * (P_READY + i * 2 + h));
+      {
+        const float2 a = __fadd2_rn(__fadd2_rn(l4[0], l4[1]), __fadd2_rn(l4[2], l4[3]));
+        l[i] += a.x + a.y;
+      }
+    }
+  }
+
+  // epilogue: O / l -> bf16 -> global (my 64 columns of both tiles)
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t tO = tmem_base + 256 + i * 128 + lane_sel;
+    mbar_wait_a(bars + 8 * (O_FULL + i), 0);
+    tc_fence_after();
+    float* xr = xch + ((n_kv & 1) * 2 + i) * 2 * 128;     // parity after the last step: not in use by a straggling half
+    xr[h * 128 + rl] = l[i];
+    pair_bar(1 + i * 4 + quad);
+    const float lsum = l[i] + xr[(h ^ 1) * 128 + rl];
+    const int row = u.q_row0 + i * BQ + rl;
+    if (u.slice_slot >= 0 && p.split > 1) {
+      // one slice of the K/V stream: leave (O, m, l) for attn_merge_kernel
+      const long long prow = (long long)u.slice_slot * (2 * BQ) + i * BQ + rl;
+      float4* dst = reinterpret_cast<float4*>(p.ws_o + prow * HD + h * 64);
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tO + h * 64 + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          dst[cc * 8 + g] = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                        __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+      }
+      if (h == 0) p.ws_ml[prow] = make_float2(m_cur[i], lsum);
+    } else {
+      const float inv_l = 1.0f / lsum;
+      __nv_bfloat16* orow = p.O + (long long)row * p.ldo + u.head * HD + h * 64;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tO + h * 64 + cc * 32, r);
+        tmem_ld_wait();
+        if (row < p.Lq) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]) * inv_l;
+            uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + g * 8);
+            if (p.accumulate) {
+              const uint4 old = *dst;
+              const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(ob[e]);
+                v[2 * e] += f.x;
+                v[2 * e + 1] += f.y;
+              }
+            }
+            uint4 pk;
+            pk.x = pack_bf16x2(v[0], v[1]);
+            pk.y = pack_bf16x2(v[2], v[3]);
+            pk.z = pack_bf16x2(v[4], v[5]);
+            pk.w = pack_bf16x2(v[6], v[7]);
+            *dst = pk;
+          }
+        }
+      }
+    }
+  }
+}
+
+#else
 // ------------------------------------ softmax warpgroups (thread = one row of Q tile i) -----------
 __device__ __forceinline__ void softmax_role(const Params& p, uint32_t sbase, uint32_t tmem_base, int warp, int lane) {
   const Unit u = decode_unit(p);
@@ -427,6 +616,8 @@ __device__ __forceinline__ void softmax_role(const Params& p, uint32_t sbase, ui
     }
   }
 }
+
+#endif
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,

@@ -30,11 +30,12 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quadrant, each draining one 128-column half of the tile
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
-constexpr int STAGES = 5;       // 6 before the epilogue got its transposition tiles (7 fit then but measured 1-2 % slower)
+constexpr int MAX_STAGES = 6;   // operand ring: 6 stages (7 fit but measured 1-2 % slower); 5 when the residual-class epilogue needs its
+                                // transposition tiles in the same 227 KB (a runtime parameter: ffn.0 lost 16 % with a 5-stage ring)
 constexpr int GROUP_M = 4;      // measured: 1..4 equal on M >> N shapes, 4..8 best on square ones
 constexpr int VEC_BYTES = 2 * 4 * BN * 4;   // bias, gate, LN-fold u and next-operand scale of the tile's 256 columns, double buffered by accumulator
 constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;   // one 32 x 32 fp32 tile per epilogue warp (residual-class epilogue)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + VEC_BYTES + XPOSE_BYTES;
+constexpr int smem_bytes(int stages, bool xpose) { return stages * STAGE_BYTES + 1024 + 256 + VEC_BYTES + (xpose ? XPOSE_BYTES : 0); }
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> even CTA
 
 struct Epi {
@@ -159,12 +160,12 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
-                  int K, int group_m, Epi ep) {
+                  int K, int group_m, int STAGES, Epi ep) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sraw = smem_u32(smem_raw);
   const uint32_t sbase = (sraw + 1023u) & ~1023u;
-  constexpr uint32_t OFF_BAR = STAGES * STAGE_BYTES;
-  enum : uint32_t { FULL = 0, EMPTY = STAGES, TMEM_FULL = 2 * STAGES, TMEM_EMPTY = 2 * STAGES + 2, NUM_BARS = 2 * STAGES + 4 };
+  const uint32_t OFF_BAR = STAGES * STAGE_BYTES;
+  enum : uint32_t { FULL = 0, EMPTY = MAX_STAGES, TMEM_FULL = 2 * MAX_STAGES, TMEM_EMPTY = 2 * MAX_STAGES + 2, NUM_BARS = 2 * MAX_STAGES + 4 };
   auto bar = [&](uint32_t n) { return sbase + OFF_BAR + 8u * n; };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_raw + (sbase - sraw) + OFF_BAR + 8 * NUM_BARS);
   float* vec_smem = reinterpret_cast<float*>(smem_raw + (sbase - sraw) + OFF_BAR + 256);   // [2 acc][bias | gate | u | g_next][BN]
@@ -186,7 +187,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (uint32_t i = 0; i < STAGES; ++i) {
+      for (uint32_t i = 0; i < MAX_STAGES; ++i) {
         mbar_init_a(bar(FULL + i), 1);      // one expect_tx arrive by the even CTA's producer (+ bytes of both CTAs)
         mbar_init_a(bar(EMPTY + i), 1);     // one multicast commit
       }
@@ -534,7 +535,9 @@ int launch(const void* A, long long lda, const void* W, long long ldw, int M, in
   ep.a_next = reinterpret_cast<__nv_bfloat16*>(e->a_next); ep.ld_an = e->ld_an; ep.g_next = e->g_next; ep.row_stats = e->row_stats;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t ce = cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          smem_bytes(MAX_STAGES, false) > smem_bytes(MAX_STAGES - 1, true) ? smem_bytes(MAX_STAGES, false)
+                                                                                                           : smem_bytes(MAX_STAGES - 1, true));
     if (ce != cudaSuccess) {
       set_last_error("svi_gemm_bf16(pair): cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce));
       return SVI_ERR_LAUNCH;
@@ -546,7 +549,10 @@ int launch(const void* A, long long lda, const void* W, long long ldw, int M, in
   if (sms <= 0) return SVI_ERR_DRIVER;
   int pairs = sms / 2;
   if (num_tiles < pairs) pairs = num_tiles;
-  gemm2_bf16_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, GROUP_M, ep);
+  // the residual-class epilogue (same predicate as `coal` in the kernel) trades one operand stage for its transposition tiles
+  const bool xpose = ep.out_is_f32 && ep.residual && ep.act == SVI_ACT_NONE && !ep.sumsq && !ep.ln_stats;
+  const int stages = xpose ? MAX_STAGES - 1 : MAX_STAGES;
+  gemm2_bf16_kernel<<<2 * pairs, NUM_THREADS, smem_bytes(stages, xpose), stream>>>(ta, tb, M, N, K, GROUP_M, stages, ep);
   SVI_CUDA_LAUNCH_CHECK("svi_gemm_bf16(pair)");
   return SVI_OK;
 }

@@ -334,9 +334,13 @@ class WanDiTEngine:
         self._graphs = {}
         import os
         self.use_graphs = os.environ.get("SVI_CUDA_GRAPHS", "1") != "0"
-        # LayerNorm + modulate folded into the GEMMs around it (no LayerNorm launches inside the block stack); applies to
-        # forwards with more than 128 token rows per rank (the fold lives in the CTA-pair GEMM) and no audio branch
-        self.use_fold = os.environ.get("SVI_LN_FOLD", "1") != "0"
+        # SVI_LN_FOLD=1: LayerNorm + modulate folded into the GEMMs around it (no LayerNorm launch inside the block stack;
+        # forwards with more than 128 token rows per rank, no audio branch).  Built, parity-neutral (cfg-1: 0.961 either way)
+        # and MEASURED at the bench shape (profiles/r02_c4_perf.log, r02_step_breakdown_c4_*.txt): the three 51-58 us LayerNorm
+        # passes per block go away, but the consumer epilogues cost +28 us (ffn.0), +13 us (qkv / cross-q) and every producer
+        # +28 us (a further 100 MB bf16 write in an HBM-bound epilogue): 497.3 ms per step with the fold, 493.7 ms without.
+        # The faster path is the default; the fold stays selectable (and tested) as a design point.
+        self.use_fold = os.environ.get("SVI_LN_FOLD", "0") == "1"
         self._fold_static = None
         self.attn_events = None  # bench.py: list collecting (start, end) events around self-attention launches
         self.k = _CountingNative()  # every native launch goes through this proxy (bench.py reads the count)

@@ -136,14 +136,19 @@ def sec_ln_fold():
         nv.gemm(a_next, w, out, bias=cvec, sumsq=ss, sumsq_group_cols=N, ln=(stats, u, d, 1e-6))
         h = torch.nn.functional.layer_norm(x_ref, (d,), eps=1e-6) * gmod + tmod
         ref = h @ w.float().t() + b
-        report(f"fold consumer M={M} d={d} N={N}", out, ref, 1.5e-2, min_inside=0.97)
+        # (both forms feed a bf16 A operand: ~95.5 % of the elements inside the rms-relative tolerance either way)
+        report(f"fold consumer M={M} d={d} N={N}", out, ref, 1.5e-2, min_inside=0.94)
         report(f"fold consumer sumsq M={M}", ss, (ref ** 2).sum(1, keepdim=True), 1e-2)
         # the unfused path on the same numbers, for scale: LN kernel -> bf16 -> GEMM
         hb = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
         nv.layernorm_modulate(x, hb, 1e-6, scale=gmod - 1, shift=tmod)
         out2 = torch.empty_like(out)
         nv.gemm(hb, w, out2, bias=b)
-        report(f"(unfused LN -> GEMM on the same inputs) M={M} d={d} N={N}", out2, ref, 1.5e-2, min_inside=0.97)
+        report(f"(unfused LN -> GEMM on the same inputs) M={M} d={d} N={N}", out2, ref, 1.5e-2, min_inside=0.94)
+        e_fold, e_plain = (out.float() - ref).abs().mean().item(), (out2.float() - ref).abs().mean().item()
+        ok = e_fold <= 1.1 * e_plain
+        print(f"[{'OK ' if ok else 'BAD'}] fold mean |err| {e_fold:.3e} vs unfused {e_plain:.3e}", flush=True)
+        RESULTS.append((f"fold error not above the unfused path M={M}", ok))
 
 
 def attn_ref(q, k, v, H, scale):
