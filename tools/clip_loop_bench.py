@@ -34,7 +34,8 @@ class TokenPrompter:
         self.prompter, self.vocab = prompter, vocab
 
     def __call__(self, prompt, positive=True):
-        g = torch.Generator().manual_seed(hash(prompt) % 100000 + (0 if positive else 1))
+        import zlib
+        g = torch.Generator().manual_seed(zlib.crc32(prompt.encode()) % 100000 + (0 if positive else 1))   # same ids on every rank
         n = 60 if positive else 90
         ids = torch.zeros(1, 512, dtype=torch.int64)
         ids[0, :n] = torch.randint(2, self.vocab, (n,), generator=g)
