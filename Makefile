@@ -4,12 +4,12 @@ PKG := stable-video-infinity_b200
 CSRC := $(PKG)/csrc
 LIB := $(PKG)/lib/libsvi_b200.so
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
-SRCS := $(CSRC)/runtime.cu $(CSRC)/gemm_tcgen05.cu $(CSRC)/gemm2_tcgen05.cu $(CSRC)/attn_tcgen05.cu $(CSRC)/sp_exchange.cu $(CSRC)/elementwise.cu $(CSRC)/conv3d_tcgen05.cu $(CSRC)/vae_elementwise.cu $(CSRC)/encoder_kernels.cu
+SRCS := $(CSRC)/runtime.cu $(CSRC)/gemm_tcgen05.cu $(CSRC)/gemm2_tcgen05.cu $(CSRC)/attn_tcgen05.cu $(CSRC)/sp_exchange.cu $(CSRC)/elementwise.cu $(CSRC)/conv3d_tcgen05.cu $(CSRC)/conv3d2_tcgen05.cu $(CSRC)/vae_elementwise.cu $(CSRC)/encoder_kernels.cu
 OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 
 all: $(LIB)
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/svi_b200.h
+build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/conv3d_common.cuh include/svi_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

@@ -275,6 +275,13 @@ typedef struct svi_conv_desc {
    * front of the second CausalConv3d of a ResidualBlock and between blocks (wan_video_vae.py:55-70, 206-210). */
   void* next_ring; int64_t next_frame_stride; int32_t next_ld; int32_t next_slot[4];
   const float* next_gamma; int32_t next_silu; int32_t write_f32;
+  /* Kernel choice (same results up to accumulation order).  1: one CTA per 128-pixel patch, one input box per tap.
+   * 2: CTA pairs (tcgen05 cta_group::2) on two image rows x 128 pixels; the input row window is loaded once per
+   * (k_t, k_h, 64-channel chunk) and the k_w taps read it at shifted row offsets, the weight tile is split between the
+   * two CTAs — needs k_w == 3, pad_w == 1, C_out % 32 == 0.  0: 2 where it applies and W >= 192, else 1. */
+  int32_t variant;
+  int32_t flags;              /* bit 0 (variant 2, bring-up only): put the row phase of shifted operand start addresses into
+                               * the shared-memory descriptor's base-offset field */
 } svi_conv_desc;
 int svi_conv3d_causal(const svi_conv_desc* d, void* stream);
 
@@ -301,6 +308,11 @@ int svi_vae_from_planar(const float* x, int32_t C, int64_t n_pix, int64_t ldc, c
  * optional clamp to [-1,1] (WanVideoVAE.single_decode :753-756; latent normalisation :542-549) */
 int svi_vae_to_planar(const float* x, int64_t ldx, int32_t C, int64_t n_pix, const float* pre_shift,
                       const float* scale, int32_t clamp, float* out, int64_t ldc, void* stream);
+/* planar f32 video [3][n_pix] (channel c at video + c*plane_stride; n_pix = T*H*W) -> uint8 [n_pix][3]:
+ * clip((v + 1) * 127.5, 0, 255) truncated — the clip-boundary conversion of tensor2video (svi_video.py:366-370) on the
+ * device, so that 1 byte per sample instead of 4 crosses to the host and the frames stay available on the device for the
+ * next clip's conditioning (test_svi.py:472). */
+int svi_frames_to_uint8(const float* video, int64_t plane_stride, int64_t n_pix, void* out_u8, void* stream);
 /* p[r, 0:N] = bf16(softmax(s[r, 0:N] * scale)), p[r, N:ldp] = 0; s f32 [rows, lds] (VAE AttentionBlock :235-273) */
 int svi_softmax_rows(const float* s, int32_t rows, int32_t N, int64_t lds, float scale, void* p_bf16, int64_t ldp,
                      void* stream);

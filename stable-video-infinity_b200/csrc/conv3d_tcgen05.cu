@@ -15,6 +15,7 @@
 // ring, so the activation between the two convs of a ResidualBlock never exists in fp32 and no staging pass runs.
 #include "common.cuh"
 #include "../../include/svi_b200.h"
+#include "conv3d_common.cuh"
 
 namespace svi {
 namespace conv {
@@ -30,32 +31,6 @@ constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
 
-struct Params {
-  int H, W, T;                 // output height / width / frames of this launch
-  int kt, kh, kw;              // kernel extent
-  int pad_h, pad_w;            // input coordinate = output coordinate + k - pad
-  int slot[4][3];              // ring slot of the input frame for (output frame, k_t)
-  int cin_chunks;              // ceil(C_in / 64)
-  int C_out, BN, BW, BH;       // BH * BW == 128
-  float* out;                  // fp32 channels-last [frame][H][W][out_ld]
-  long long out_frame_stride;  // elements between output frames
-  int out_ld;                  // channels per output pixel in memory
-  int n_split;                 // columns >= n_split are written to out + split_offset (column - n_split); 0 = off
-  long long split_offset;
-  const float* bias;           // [C_out]
-  const float* residual;       // same layout as out (frame stride res_frame_stride, ld res_ld) or null
-  long long res_frame_stride;
-  int res_ld;
-  int stages, stage_bytes;     // operand ring: stage_bytes = A tile + BN x 64 bf16 rounded to 1 KB
-  // fused producer of the NEXT conv's input (RMS_norm + SiLU + bf16 staging, wan_video_vae.py:55-70,206-210):
-  __nv_bfloat16* next_ring;    // bf16 [slots][H][W][next_ld] or null
-  long long next_frame_stride; // elements between ring slots
-  int next_ld;
-  int next_slot[4];            // ring slot of output frame t
-  const float* next_gamma;     // [C_out] RMS-norm weight, null: plain cast
-  int next_silu;
-  int write_f32;               // 0: the fp32 output is not needed (only the normalised bf16 is consumed)
-};
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0,
                                             int c1, int c2, int c3) {
@@ -192,88 +167,10 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * MAX_BN + (static_cast<uint32_t>(quad * 32) << 16);
-      float ssq = 0.f;            // sum of squares of this pixel's output channels (fused RMS norm of the next conv's input)
-#pragma unroll 1
-      for (int c = 0; c < p.BN / 16; ++c) {
-        const int n0 = n_blk * p.BN + c * 16;
-        if (n0 >= p.C_out) break;
-        uint32_t r[16];
-        tmem_ld16(t_base + c * 16, r);
-        tmem_ld_wait();
-        if (ok) {
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const int n = n0 + j4 * 4;
-            if (n >= p.C_out) break;
-            float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j4 * 4 + j]);
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-            }
-            if (p.residual) {
-              const float4 q = *reinterpret_cast<const float4*>(p.residual + (long long)t * p.res_frame_stride +
-                                                                pix * p.res_ld + n);
-              v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
-            }
-            ssq += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
-            if (p.write_f32) {
-              float* dst;
-              if (p.n_split > 0 && n >= p.n_split)
-                dst = p.out + p.split_offset + (long long)t * p.out_frame_stride + pix * p.out_ld + (n - p.n_split);
-              else
-                dst = p.out + (long long)t * p.out_frame_stride + pix * p.out_ld + n;
-              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            }
-          }
-        }
-      }
-      if (p.next_ring) {
-        // second pass over the accumulator (still in TMEM): y = silu(v / max(||v||, 1e-12) * sqrt(C) * gamma) -> bf16 into the
-        // next conv's input ring.  Launch side guarantees one N tile (the whole channel vector of a pixel is in this row).
-        const float mul = p.next_gamma ? sqrtf((float)p.C_out) / fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
-        __nv_bfloat16* nrow = p.next_ring + (long long)p.next_slot[t] * p.next_frame_stride + pix * p.next_ld;
-#pragma unroll 1
-        for (int c = 0; c < p.BN / 16; ++c) {
-          const int n0 = c * 16;
-          if (n0 >= p.C_out) break;
-          uint32_t r[16];
-          tmem_ld16(t_base + c * 16, r);
-          tmem_ld_wait();
-          if (ok) {
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const int n = n0 + j4 * 4;
-              if (n >= p.C_out) break;
-              float v[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j4 * 4 + j]);
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-              }
-              if (p.residual) {
-                const float4 q = *reinterpret_cast<const float4*>(p.residual + (long long)t * p.res_frame_stride +
-                                                                  pix * p.res_ld + n);
-                v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
-              }
-              if (p.next_gamma) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(p.next_gamma + n));
-                v[0] *= mul * g.x; v[1] *= mul * g.y; v[2] *= mul * g.z; v[3] *= mul * g.w;
-              }
-              if (p.next_silu) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = silu(v[j]);
-              }
-              uint2 pk;
-              pk.x = pack_bf16x2(v[0], v[1]);
-              pk.y = pack_bf16x2(v[2], v[3]);
-              *reinterpret_cast<uint2*>(nrow + n) = pk;
-            }
-          }
-        }
-      }
+      // pass 1: + bias (+ residual) -> fp32 out, sum of squares of the pixel's channels; pass 2 (fused producer of the next
+      // conv's input; the launch side guarantees one N tile): RMS norm + SiLU -> bf16 ring   (conv3d_common.cuh)
+      const float ssq = epilogue_pass1(p, t_base, p.BN / 16, n_blk * p.BN, t, pix, ok);
+      if (p.next_ring) epilogue_pass2(p, t_base, p.BN / 16, 0, t, pix, ok, ssq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -287,6 +184,20 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+void* encode_tiled_fn() {
+  static void* fn = nullptr;
+  if (!fn) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp) {
+      set_last_error("svi_conv3d_causal: cuTensorMapEncodeTiled unavailable");
+      return nullptr;
+    }
+    fn = fp;
+  }
+  return fn;
 }
 
 }  // namespace conv
@@ -319,20 +230,47 @@ extern "C" int svi_conv3d_causal(const svi_conv_desc* d, void* stream) {
   }
   SVI_REQUIRE(d->w_rows >= d->C_out, "svi_conv3d_causal: packed weight has fewer rows than C_out");
 
-  // 4-D tensor map over the input ring [slots][in_H][in_W][C_in] (channels innermost)
+  Params p;
+  p.H = d->H; p.W = d->W; p.T = d->T;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw;
+  p.pad_h = d->pad_h; p.pad_w = d->pad_w;
+  for (int t = 0; t < 4; ++t)
+    for (int a = 0; a < 3; ++a) p.slot[t][a] = d->slot[t * 3 + a];
+  p.cin_chunks = cin_chunks;
+  p.C_out = d->C_out; p.BN = BN; p.BW = d->tile_w; p.BH = BM / d->tile_w;
+  p.out = d->out; p.out_frame_stride = d->out_frame_stride; p.out_ld = d->out_ld;
+  p.n_split = d->n_split; p.split_offset = d->split_offset;
+  p.bias = d->bias; p.residual = d->residual; p.res_frame_stride = d->res_frame_stride; p.res_ld = d->res_ld;
+  p.stage_bytes = (A_STAGE_BYTES + BN * BK * 2 + 1023) / 1024 * 1024;
+  p.stages = RING_BYTES / p.stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  p.next_ring = reinterpret_cast<__nv_bfloat16*>(d->next_ring);
+  p.next_frame_stride = d->next_frame_stride;
+  p.next_ld = d->next_ld;
+  for (int t = 0; t < 4; ++t) p.next_slot[t] = d->next_slot[t];
+  p.next_gamma = d->next_gamma;
+  p.next_silu = d->next_silu;
+  p.write_f32 = d->next_ring ? d->write_f32 : 1;
+  if (d->next_ring) {
+    SVI_REQUIRE(d->C_out <= BN && d->n_split == 0, "svi_conv3d_causal: the fused next-input producer needs one N tile (C_out <= 256) and no channel split");
+    SVI_REQUIRE(d->next_ld >= d->C_out && d->next_ld % 4 == 0, "svi_conv3d_causal: next_ld must be >= C_out and a multiple of 4");
+    for (int t = 0; t < d->T; ++t) SVI_REQUIRE(d->next_slot[t] >= 0, "svi_conv3d_causal: next_slot must be >= 0");
+  }
+
+
+  // kernel choice: 1 = single CTA, one input box per tap; 2 = CTA pairs with the input window reused across the horizontal
+  // taps (conv3d2_tcgen05.cu); 0 = pair kernel where it applies and the image rows are long enough to fill its 128-pixel row tiles
+  SVI_REQUIRE(d->variant >= 0 && d->variant <= 2, "svi_conv3d_causal: variant must be 0 (auto), 1 or 2");
+  const bool pair_ok = svi::conv2::eligible(d, BN);
+  SVI_REQUIRE(d->variant != 2 || pair_ok, "svi_conv3d_causal: variant 2 needs k_w = 3, pad_w = 1 and C_out (and its N tile) a multiple of 32");
+  if (d->variant == 2 || (d->variant == 0 && pair_ok && d->W >= svi::conv2::AUTO_MIN_W))
+    return svi::conv2::launch(d, p, BN, d->flags & 1, static_cast<cudaStream_t>(stream));
+
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeTiledFn enc = nullptr;
-  if (!enc) {
-    void* fp = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp) {
-      set_last_error("svi_conv3d_causal: cuTensorMapEncodeTiled unavailable");
-      return SVI_ERR_DRIVER;
-    }
-    enc = reinterpret_cast<EncodeTiledFn>(fp);
-  }
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(encode_tiled_fn());
+  if (!enc) return SVI_ERR_DRIVER;
   const int BW = d->tile_w, BH = BM / BW;
   CUtensorMap tx, tw;
   {
@@ -352,33 +290,6 @@ extern "C" int svi_conv3d_causal(const svi_conv_desc* d, void* stream) {
   }
   int rc = make_tmap_2d(&tw, d->w_packed, 2, (uint64_t)ktot, (uint64_t)d->w_rows, (uint64_t)d->w_ld * 2, BK, BN);
   if (rc) return rc;
-
-  Params p;
-  p.H = d->H; p.W = d->W; p.T = d->T;
-  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw;
-  p.pad_h = d->pad_h; p.pad_w = d->pad_w;
-  for (int t = 0; t < 4; ++t)
-    for (int a = 0; a < 3; ++a) p.slot[t][a] = d->slot[t * 3 + a];
-  p.cin_chunks = cin_chunks;
-  p.C_out = d->C_out; p.BN = BN; p.BW = BW; p.BH = BH;
-  p.out = d->out; p.out_frame_stride = d->out_frame_stride; p.out_ld = d->out_ld;
-  p.n_split = d->n_split; p.split_offset = d->split_offset;
-  p.bias = d->bias; p.residual = d->residual; p.res_frame_stride = d->res_frame_stride; p.res_ld = d->res_ld;
-  p.stage_bytes = (A_STAGE_BYTES + BN * BK * 2 + 1023) / 1024 * 1024;
-  p.stages = RING_BYTES / p.stage_bytes;
-  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  p.next_ring = reinterpret_cast<__nv_bfloat16*>(d->next_ring);
-  p.next_frame_stride = d->next_frame_stride;
-  p.next_ld = d->next_ld;
-  for (int t = 0; t < 4; ++t) p.next_slot[t] = d->next_slot[t];
-  p.next_gamma = d->next_gamma;
-  p.next_silu = d->next_silu;
-  p.write_f32 = d->next_ring ? d->write_f32 : 1;
-  if (d->next_ring) {
-    SVI_REQUIRE(d->C_out <= BN && d->n_split == 0, "svi_conv3d_causal: the fused next-input producer needs one N tile (C_out <= 256) and no channel split");
-    SVI_REQUIRE(d->next_ld >= d->C_out && d->next_ld % 4 == 0, "svi_conv3d_causal: next_ld must be >= C_out and a multiple of 4");
-    for (int t = 0; t < d->T; ++t) SVI_REQUIRE(d->next_slot[t] >= 0, "svi_conv3d_causal: next_slot must be >= 0");
-  }
 
   static bool attr_set = false;
   if (!attr_set) {

@@ -85,6 +85,6 @@ int sm_count() {
 
 }  // namespace svi
 
-extern "C" int svi_abi_version(void) { return 3; }  // 3: split-precision staging, q|k norm in one launch, attention with a per-row Q scale
+extern "C" int svi_abi_version(void) { return 4; }  // 4: LayerNorm-fold GEMM epilogues, conv epilogue feeding the next conv, svi_frames_to_uint8
 extern "C" const char* svi_last_error(void) { return svi::g_err; }
 extern "C" int svi_sm_count(void) { return svi::sm_count(); }

@@ -128,6 +128,19 @@ to_planar_kernel(const float* __restrict__ x, long long ldx, int C, long long n_
   }
 }
 
+// planar f32 video [3][T][H][W] in [-1, 1] -> uint8 frames [T][H][W][3]: clip((v + 1) * 127.5, 0, 255) truncated, the
+// arithmetic of the reference's tensor2video (svi_video.py:366-370) in the same fp32 order
+__global__ void __launch_bounds__(256)
+frames_to_uint8_kernel(const float* __restrict__ v, long long plane, long long n_pix, unsigned char* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pix; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float f = fminf(fmaxf((v[c * plane + i] + 1.0f) * 127.5f, 0.0f), 255.0f);
+      out[i * 3 + c] = (unsigned char)f;
+    }
+  }
+}
+
 // one 256-thread block per row
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ s, int N, long long lds, float scale, __nv_bfloat16* __restrict__ p,
@@ -221,6 +234,13 @@ extern "C" int svi_vae_to_planar(const float* x, int64_t ldx, int32_t C, int64_t
   to_planar_kernel<<<grid_for(n_pix * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, C, n_pix, pre_shift,
                                                                                            scale, clamp, out, ldc);
   SVI_CUDA_LAUNCH_CHECK("svi_vae_to_planar");
+  return SVI_OK;
+}
+extern "C" int svi_frames_to_uint8(const float* video, int64_t plane_stride, int64_t n_pix, void* out_u8, void* stream) {
+  SVI_REQUIRE(video && out_u8 && n_pix > 0 && plane_stride >= n_pix, "svi_frames_to_uint8: bad arguments");
+  frames_to_uint8_kernel<<<grid_for(n_pix, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      video, plane_stride, n_pix, static_cast<unsigned char*>(out_u8));
+  SVI_CUDA_LAUNCH_CHECK("svi_frames_to_uint8");
   return SVI_OK;
 }
 extern "C" int svi_softmax_rows(const float* s, int32_t rows, int32_t N, int64_t lds, float scale, void* p, int64_t ldp,

@@ -12,6 +12,7 @@ _LAZY = {
     "SVITalkVideoPipeline": ("diffsynth.pipelines.svi_video_talk", "SVITalkVideoPipeline"),
     "save_video": ("diffsynth.data.video", "save_video"),
     "VideoData": ("diffsynth.data.video", "VideoData"),
+    "StreamingVideoWriter": ("diffsynth.data.video", "StreamingVideoWriter"),
     "FlowMatchScheduler": ("diffsynth.schedulers.flow_match", "FlowMatchScheduler"),
     "WanPrompter": ("diffsynth.prompters.wan_prompter", "WanPrompter"),
 }

@@ -44,6 +44,7 @@ class ConvDesc(_c.Structure):
         ("residual", _vp), ("res_frame_stride", _i64), ("res_ld", _i32),
         ("next_ring", _vp), ("next_frame_stride", _i64), ("next_ld", _i32), ("next_slot", _i32 * 4),
         ("next_gamma", _vp), ("next_silu", _i32), ("write_f32", _i32),
+        ("variant", _i32), ("flags", _i32),
     ]
 
 
@@ -94,6 +95,7 @@ SIGNATURES = {
     "svi_vae_from_planar": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp]),
     "svi_vae_to_planar": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
     "svi_softmax_rows": (_i32, [_vp, _i32, _i32, _i64, _f32, _vp, _i64, _vp]),
+    "svi_frames_to_uint8": (_i32, [_vp, _i64, _i64, _vp, _vp]),
 }
 
 _lib = None
@@ -569,6 +571,16 @@ def vae_to_planar(x, ldx, C, n_pix, pre_shift, scale, clamp, out, ldc=None):
                                   _ptr(scale, torch.float32, "scale"), int(bool(clamp)), _ptr(out, torch.float32, "out"),
                                   n_pix if ldc is None else ldc, _stream())
     _check(rc, "svi_vae_to_planar")
+    return out
+
+
+def frames_to_uint8(video, out):
+    """video f32 [3, T, H, W] (contiguous, CUDA) -> out uint8 [T, H, W, 3]: clip((v + 1) * 127.5, 0, 255) truncated."""
+    C, T, H, W = video.shape
+    if C != 3 or not video.is_contiguous() or not out.is_contiguous() or out.dtype != torch.uint8 or out.numel() != 3 * T * H * W:
+        raise RuntimeError("svi_b200.frames_to_uint8: video must be contiguous f32 [3,T,H,W], out contiguous uint8 [T,H,W,3]")
+    _check(load().svi_frames_to_uint8(_ptr(video, torch.float32, "video"), T * H * W, T * H * W, _ptr(out, name="out"), _stream()),
+           "svi_frames_to_uint8")
     return out
 
 

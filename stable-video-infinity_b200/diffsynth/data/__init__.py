@@ -1,1 +1,1 @@
-from .video import VideoData, save_frames, save_video
+from .video import StreamingVideoWriter, VideoData, save_frames, save_video

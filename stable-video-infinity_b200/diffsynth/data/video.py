@@ -39,6 +39,53 @@ def save_video(frames, save_path, fps, quality=9, ffmpeg_params=None):
         return out_dir
 
 
+class StreamingVideoWriter:
+    """Appends clips to ONE output as they are produced instead of re-encoding everything generated so far after every clip
+    (the reference harness calls save_video(all_frames) per clip, test_svi.py:483 — quadratic in the number of clips).
+    Same writer choice as save_video: imageio, else OpenCV, else a directory of PNG frames.
+
+        w = StreamingVideoWriter(path, fps=16); w.append(clip_frames); ...; w.close()
+    """
+
+    def __init__(self, save_path, fps, quality=9, ffmpeg_params=None):
+        self.save_path, self.fps, self.count = save_path, fps, 0
+        self._w, self._kind = None, None
+        try:
+            import imageio
+            self._w, self._kind = imageio.get_writer(save_path, fps=fps, quality=quality, ffmpeg_params=ffmpeg_params), "imageio"
+        except ImportError:
+            try:
+                import cv2  # noqa: F401
+                self._kind = "cv2"
+            except ImportError:
+                self._kind = "png"
+                self.save_path = os.path.splitext(save_path)[0] + "_frames"
+                os.makedirs(self.save_path, exist_ok=True)
+
+    def append(self, frames):
+        for fr in frames:
+            if self._kind == "imageio":
+                self._w.append_data(np.array(fr))
+            elif self._kind == "cv2":
+                import cv2
+                a = np.array(fr)
+                if self._w is None:
+                    self._w = cv2.VideoWriter(self.save_path, cv2.VideoWriter_fourcc(*"mp4v"), self.fps, (a.shape[1], a.shape[0]))
+                self._w.write(cv2.cvtColor(a, cv2.COLOR_RGB2BGR))
+            else:
+                fr.save(os.path.join(self.save_path, f"{self.count}.png"))
+            self.count += 1
+        return self.count
+
+    def close(self):
+        if self._kind == "imageio" and self._w is not None:
+            self._w.close()
+        elif self._kind == "cv2" and self._w is not None:
+            self._w.release()
+        self._w = None
+        return self.save_path
+
+
 class VideoData:
     """Minimal image-folder / frame-list reader (reference data/video.py VideoData)."""
 

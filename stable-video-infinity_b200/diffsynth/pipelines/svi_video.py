@@ -205,7 +205,9 @@ class SVIVideoPipeline(BasePipeline):
         """reference svi_video.py:291-364: CLIP feature of the first frame, the 4-channel first-frame mask and
         the VAE latents of [condition frames ++ padding]; everything in fp32 then cast to the pipeline dtype."""
         dev = self.device
-        prep = lambda im: self.preprocess_image(im.resize((width, height))).to(device=dev, dtype=torch.float32)
+        def prep(im):
+            x = self._device_frame(im, width, height)           # recycled motion frames are already on the device
+            return x if x is not None else self.preprocess_image(im.resize((width, height))).to(device=dev, dtype=torch.float32)
         ref = prep(random_ref_frame)
         first = prep(first_frames[0])
         clip_context = self.image_encoder.encode_image([first])
@@ -235,9 +237,29 @@ class SVIVideoPipeline(BasePipeline):
         return {"clip_feature": clip_context.to(dtype=self.torch_dtype, device=dev), "y": y.to(dtype=self.torch_dtype, device=dev)}
 
     def tensor2video(self, frames):
-        """reference :366-370: [C,T,H,W] in [-1,1] -> list of uint8 PIL frames."""
+        """reference :366-370: [C,T,H,W] in [-1,1] -> list of uint8 PIL frames.  On the device the conversion is one native
+        kernel and ONE byte per sample crosses to the host (reference: the fp32 video, 4 bytes); the uint8 frames also stay
+        on the device (`_frames_u8`, keyed by the identity of the PIL frames handed out) so that the frames a caller feeds
+        back as the next clip's `input_image` (test_svi.py:472) are conditioned on without a host round trip."""
+        if frames.is_cuda and frames.shape[0] == 3:
+            v = frames.to(torch.float32).contiguous()
+            u8 = torch.empty(v.shape[1], v.shape[2], v.shape[3], 3, device=v.device, dtype=torch.uint8)
+            nv.frames_to_uint8(v, u8)
+            host = u8.cpu().numpy()
+            out = [Image.fromarray(f) for f in host]
+            self._frames_u8 = {id(im): (im, u8, t) for t, im in enumerate(out)}     # previous clip's entries are dropped here
+            return out
         fr = ((frames.float().permute(1, 2, 3, 0) + 1) * 127.5).clip(0, 255).cpu().numpy().astype(np.uint8)
         return [Image.fromarray(f) for f in fr]
+
+    def _device_frame(self, im, width, height):
+        """f32 [1,3,H,W] in [-1,1] on the device for a PIL frame this pipeline produced itself (same arithmetic as
+        preprocess_image), or None."""
+        hit = getattr(self, "_frames_u8", {}).get(id(im))
+        if hit is None or hit[0] is not im or im.size != (width, height):
+            return None
+        _, u8, t = hit
+        return (u8[t].to(torch.float32) * (2 / 255) - 1).permute(2, 0, 1).unsqueeze(0)
 
     def encode_video(self, input_video, tiled=True, tile_size=(34, 34), tile_stride=(18, 16)):
         lat = self.vae.encode(input_video.to(device=self.device, dtype=torch.float32), device=self.device, tiled=tiled,

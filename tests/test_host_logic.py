@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/svi_b200.h but not exported"
         assert name in nv.SIGNATURES, f"{name} has no ctypes signature in diffsynth/_native.py"
     assert sorted(nv.SIGNATURES) == declared
-    assert lib.svi_abi_version() == 3
+    assert lib.svi_abi_version() == 4
 
 
 def test_header_is_plain_c():
@@ -395,3 +395,20 @@ def test_model_manager_loads_a_sharded_vae_checkpoint_end_to_end(tmp_path):
         bad = str(tmp_path / "other.safetensors")
         save_file({"foo.weight": torch.zeros(2, 2)}, bad)
         mm.load_models([bad])
+
+
+def test_streaming_video_writer_appends_clips(tmp_path):
+    """StreamingVideoWriter (the clip loop's append-only output): frames of successive clips land in one output
+    in order, whatever writer backend this image has (none here: PNG frames)."""
+    import numpy as np
+    from PIL import Image
+    from diffsynth import StreamingVideoWriter
+    mk = lambda v: Image.fromarray(np.full((8, 12, 3), v, dtype=np.uint8))
+    w = StreamingVideoWriter(str(tmp_path / "out.mp4"), fps=16)
+    assert w.append([mk(1), mk(2), mk(3)]) == 3
+    assert w.append([mk(4), mk(5)]) == 5
+    out = w.close()
+    assert os.path.exists(out)
+    if os.path.isdir(out):
+        vals = [int(np.array(Image.open(os.path.join(out, f"{i}.png")))[0, 0, 0]) for i in range(5)]
+        assert vals == [1, 2, 3, 4, 5]

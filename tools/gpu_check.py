@@ -285,6 +285,12 @@ def sec_abi3():
         report(f"attention_qscale vs attention(normalised q) Lq={Lq} Lk={Lk} H={Hh_}", out, out2, 2e-2)
         nv.attention_qscale(q, k, v, out, Hh_, ssq, Dq, 1e-6, scale, accumulate=True)
         report(f"attention_qscale accumulate Lq={Lq} Lk={Lk} H={Hh_}", out, ref.bfloat16().float() + ref, 3e-2)
+    # clip-boundary conversion: planar f32 video -> uint8 frames, bit-identical to the reference's numpy formula
+    vid = (torch.rand(3, 5, 24, 40, generator=g) * 2.4 - 1.2).to(dev)
+    u8 = torch.empty(5, 24, 40, 3, device=dev, dtype=torch.uint8)
+    nv.frames_to_uint8(vid, u8)
+    want = ((vid.float().permute(1, 2, 3, 0) + 1) * 127.5).clip(0, 255).cpu().numpy().astype("uint8")
+    report("frames_to_uint8 == tensor2video arithmetic", u8.cpu().float().reshape(-1, 3), torch.from_numpy(want).float().reshape(-1, 3), 1e-9)
     # periodic add_rows + zero_
     tb = torch.randn(12, 256, generator=g).to(dev)
     tt = torch.randn(6, 256, generator=g).to(dev)
@@ -570,13 +576,12 @@ def sec_perf_attn():
     print(f"[PERF] cross attn L={L} Lk=512: {ms:.3f} ms = {4.0*L*512*H*128/ms/1e9:.1f} TFLOP/s", flush=True)
 
 
-def sec_conv():
-    """svi_conv3d_causal against torch conv3d on hand-built frame rings."""
-    import ctypes
+def _conv_runner():
+    """run(...) = one svi_conv3d_causal case against torch conv3d on a hand-built frame ring."""
     import torch.nn.functional as F
     g = torch.Generator(device="cpu").manual_seed(7)
 
-    def run(Cin, Cout, kt, kh, kw, T, H, W, pad, n_split=0, residual=False, fuse=None):
+    def run(Cin, Cout, kt, kh, kw, T, H, W, pad, n_split=0, residual=False, fuse=None, variant=1, flags=0, tag=""):
         S = T + 2
         xs = (torch.randn(S, H, W, Cin, generator=g) * 0.5)
         ring = torch.zeros(S + 1, H, W, Cin, dtype=torch.bfloat16, device=dev)
@@ -599,6 +604,7 @@ def sec_conv():
             for a in range(kt):
                 d.slot[t * 3 + a] = t + a + (3 - kt)   # frames t..t+2 of the ring are (t-2, t-1, t) of the stream
         d.C_out, d.tile_w = Cout, 8 if W <= 8 else 16
+        d.variant, d.flags = variant, flags
         res = torch.randn(T, H, W, Cout, generator=g).to(dev) if residual else None
         if n_split:
             out = torch.full((2 * T, H, W, n_split), float("nan"), device=dev)
@@ -633,16 +639,22 @@ def sec_conv():
         if fuse is not None:
             want = F.silu(F.normalize(ref, dim=-1) * Cout ** 0.5 * gamma)
             got = torch.stack([nring[(t + 1) % (T + 2)] for t in range(T)])
-            report(f"conv fused next-input ({fuse}) Cin={Cin} Cout={Cout} T={T} {H}x{W} res={residual}",
+            report(f"conv{tag} fused next-input ({fuse}) Cin={Cin} Cout={Cout} T={T} {H}x{W} res={residual}",
                    got[..., :Cout].reshape(-1, Cout), want.reshape(-1, Cout), 2e-2)
-            report("conv fused next-input: padding channels and unused slots stay zero",
+            report(f"conv{tag} fused next-input: padding channels and unused slots stay zero",
                    torch.cat([got[..., Cout:].reshape(-1), nring[0].reshape(-1)]).unsqueeze(0) + 1,
                    torch.ones(1, got[..., Cout:].numel() + nring[0].numel(), device=dev), 1e-7)
             if fuse != "both":
                 return
-        report(f"conv Cin={Cin} Cout={Cout} k=({kt},{kh},{kw}) T={T} {H}x{W} split={n_split} res={residual}",
+        report(f"conv{tag} Cin={Cin} Cout={Cout} k=({kt},{kh},{kw}) T={T} {H}x{W} split={n_split} res={residual}",
                out.reshape(-1, out.shape[-1]), ref.reshape(-1, ref.shape[-1]), 2e-2)
 
+    return run
+
+
+def sec_conv():
+    """svi_conv3d_causal against torch conv3d on hand-built frame rings."""
+    run = _conv_runner()
     run(64, 96, 3, 3, 3, 2, 16, 16, 1)
     run(96, 96, 3, 3, 3, 1, 12, 20, 1, residual=True)
     run(384, 384, 3, 3, 3, 1, 8, 8, 1)
@@ -655,6 +667,92 @@ def sec_conv():
     run(96, 96, 3, 3, 3, 2, 20, 24, 1, fuse="only")
     run(192, 192, 3, 3, 3, 4, 12, 20, 1, residual=True, fuse="both")
     run(192, 96, 3, 3, 3, 1, 9, 7, 1, residual=True, fuse="both")
+    # CTA-pair kernel (variant 2): rows longer than one 128-pixel tile, ragged last tile, odd row count (the odd CTA of the last
+    # pair has no row), partial last channel chunk (96 = 64 + 32), two N tiles (384), 2-D conv (k_t = 1)
+    pair_cases(run, PAIR_FLAGS, " [pair]")
+
+
+PAIR_FLAGS = int(os.environ.get("SVI_CONV_FLAGS", "0"))
+
+
+def pair_cases(run, flags, tag):
+    run(64, 96, 3, 3, 3, 2, 6, 150, 1, variant=2, flags=flags, tag=tag)
+    run(96, 96, 3, 3, 3, 1, 5, 200, 1, residual=True, variant=2, flags=flags, tag=tag)
+    run(96, 96, 3, 3, 3, 2, 4, 264, 1, fuse="only", variant=2, flags=flags, tag=tag)
+    run(192, 192, 3, 3, 3, 4, 3, 136, 1, residual=True, fuse="both", variant=2, flags=flags, tag=tag)
+    run(96, 384, 3, 3, 3, 1, 7, 130, 1, variant=2, flags=flags, tag=tag)
+    run(192, 96, 1, 3, 3, 3, 6, 257, 1, variant=2, flags=flags, tag=tag)
+    run(384, 384, 3, 3, 3, 1, 2, 40, 1, residual=True, variant=2, flags=flags, tag=tag)
+
+
+def sec_perf_conv():
+    """Both convolution kernels at the VAE layer shapes that carry the FLOPs (480p decode), T = 4 frames per launch:
+    mode 'mid' = first conv of a ResidualBlock (bf16 normalised output only), 'end' = second conv (+ fp32 residual, fp32 out and
+    the next block's normalised input)."""
+    g = torch.Generator(device="cpu").manual_seed(3)
+    shapes = [(96, 96, 3, 480, 832), (192, 192, 3, 240, 416), (384, 384, 3, 120, 208), (384, 384, 3, 60, 104),
+              (192, 96, 1, 480, 832), (96, 96, 3, 60, 832)]
+    for Cin, Cout, kt, H, W in shapes:
+        T, S = 4, 6
+        ring = (torch.randn(S + 1, H, W, Cin, generator=g) * 0.5).to(dev, torch.bfloat16)
+        cpad = (Cin + 63) // 64 * 64
+        wp = (torch.randn(Cout, kt * 9 * cpad, generator=g) / math.sqrt(Cin * kt * 9)).to(dev, torch.bfloat16)
+        bias = torch.zeros(Cout, device=dev)
+        out = torch.empty(T, H, W, Cout, device=dev)
+        res = torch.randn(T, H, W, Cout, device=dev)
+        ncp = (Cout + 63) // 64 * 64
+        nring = torch.zeros(T + 2, H, W, ncp, dtype=torch.bfloat16, device=dev)
+        gamma = torch.ones(Cout, device=dev)
+        fl = 2.0 * T * H * W * Cout * Cin * kt * 9
+        for mode in ("mid", "end"):
+            line = f"[PERF] conv {Cin}->{Cout} k=({kt},3,3) T={T} {H}x{W} {mode}:"
+            for variant in (1, 2):
+                d = nv.ConvDesc()
+                d.x_ring, d.ring_slots, d.in_H, d.in_W, d.C_in = ring.data_ptr(), S + 1, H, W, Cin
+                d.w_packed, d.w_rows, d.w_ld = wp.data_ptr(), Cout, wp.shape[1]
+                d.kt, d.kh, d.kw, d.pad_h, d.pad_w = kt, 3, 3, 1, 1
+                d.H, d.W, d.T = H, W, T
+                for t in range(T):
+                    for a in range(kt):
+                        d.slot[t * 3 + a] = t + a + (3 - kt)
+                d.C_out = Cout
+                from diffsynth.models.wan_video_vae import _pick_tile_w
+                d.tile_w = _pick_tile_w(H, W)
+                d.variant, d.flags = variant, PAIR_FLAGS
+                d.bias = bias.data_ptr()
+                d.out_ld = Cout
+                d.next_ring, d.next_frame_stride, d.next_ld = nring.data_ptr(), nring.stride(0), ncp
+                for t in range(T):
+                    d.next_slot[t] = t
+                d.next_gamma, d.next_silu = gamma.data_ptr(), 1
+                if mode == "end":
+                    d.out, d.out_frame_stride = out.data_ptr(), out.stride(0)
+                    d.residual, d.res_frame_stride, d.res_ld = res.data_ptr(), res.stride(0), Cout
+                    d.write_f32 = 1
+                else:
+                    d.write_f32 = 0
+                ms = time_ms(lambda: nv.conv3d_causal(d), iters=5, warm=2)
+                line += f"  v{variant} {ms * 1e3:.0f} us = {fl / ms / 1e9:.0f} TF/s"
+            print(line, flush=True)
+        del ring, wp, out, res, nring
+        torch.cuda.empty_cache()
+
+
+def sec_conv_pair_probe():
+    """Bring-up: the pair kernel with and without the descriptor base-offset convention (results are printed, not gated)."""
+    global RESULTS
+    keep = list(RESULTS)
+    for flags in ([int(os.environ["SVI_PROBE_FLAGS"])] if "SVI_PROBE_FLAGS" in os.environ else [0, 1]):
+        print(f"--- pair kernel, flags={flags}", flush=True)
+        RESULTS = []
+        try:
+            pair_cases(_conv_runner(), flags, f" [pair flags={flags}]")
+        except Exception as ex:  # noqa: BLE001
+            print("    raised:", repr(ex)[:300], flush=True)
+        n_ok = sum(ok for _, ok in RESULTS)
+        print(f"--- flags={flags}: {n_ok} of {len(RESULTS)} ok", flush=True)
+        print(f"PROBE flags={flags} allok={int(len(RESULTS) > 0 and n_ok == len(RESULTS))}", flush=True)
+    RESULTS = keep
 
 
 if __name__ == "__main__":
