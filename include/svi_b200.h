@@ -278,10 +278,8 @@ typedef struct svi_conv_desc {
   /* Kernel choice (same results up to accumulation order).  1: one CTA per 128-pixel patch, one input box per tap.
    * 2: CTA pairs (tcgen05 cta_group::2) on two image rows x 128 pixels; the input row window is loaded once per
    * (k_t, k_h, 64-channel chunk) and the k_w taps read it at shifted row offsets, the weight tile is split between the
-   * two CTAs — needs k_w == 3, pad_w == 1, C_out % 32 == 0.  0: 2 where it applies and W >= 192, else 1. */
+   * two CTAs — needs k_w == 3 and pad_w == 1.  0: 2 where it applies and W >= 192, else 1. */
   int32_t variant;
-  int32_t flags;              /* bit 0 (variant 2, bring-up only): put the row phase of shifted operand start addresses into
-                               * the shared-memory descriptor's base-offset field */
 } svi_conv_desc;
 int svi_conv3d_causal(const svi_conv_desc* d, void* stream);
 

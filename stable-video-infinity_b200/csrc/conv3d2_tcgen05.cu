@@ -108,7 +108,6 @@ struct Params {
   int stage_bytes, stages;
   int b_bytes;                  // one weight half-tile: (BN / 2) rows x 128 B
   int nk_last;                  // K = 16 steps of the last channel chunk that hold real channels
-  int desc_base_offset;         // 1: A descriptors carry the row phase of their start address in the base-offset field
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -222,12 +221,14 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
             const uint32_t sa = sbase + stage * pp.stage_bytes;
             const int nk = cc == p.cin_chunks - 1 ? pp.nk_last : 4;
             for (int c = 0; c < p.kw; ++c) {
-              // tap c of this row = the same box read c pixels (rows of 128 B) further in
+              // tap c of this row = the same box read c pixels (rows of 128 B) further in.  The 128B swizzle is a function of
+              // the absolute shared-memory address (TMA wrote the box into a 1024-byte aligned stage), so a start address that is
+              // not a multiple of 8 rows needs nothing else: the descriptor's base-offset field stays 0 (measured on B200:
+              // with the row phase in that field the results are wrong, profiles/r02_c6_pair_probe.log)
               const uint32_t a_lo = smem_desc_lo(sa + c * 128, 16);
-              const uint32_t a_hi = hi_kmaj | (pp.desc_base_offset ? ((uint32_t)(c & 7) << 17) : 0u);
               const uint32_t b_lo = smem_desc_lo(sa + A_BYTES + c * pp.b_bytes, 16);
               for (int k = 0; k < nk; ++k) {
-                mma2_ss(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, hi_kmaj, idesc, accumulate);
+                mma2_ss(d_tmem, a_lo + 2 * k, hi_kmaj, b_lo + 2 * k, hi_kmaj, idesc, accumulate);
                 accumulate = 1;
               }
             }
@@ -252,10 +253,11 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
       const int h = h0 + (int)rank, w = w0 + row_in_tile;
       const bool ok = (h < p.H) && (w < p.W);
       const long long pix = (long long)h * p.W + w;
+      const int col0 = n_blk * p.BN + half * cols_half;
+      svi::conv::residual_prefetch(p, cols_half, col0, t, pix, ok);     // while the K loop of this tile still runs
       mbar_wait_a(bar(TMEM_FULL + acc), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * MAX_BN + half * cols_half + (static_cast<uint32_t>(quad * 32) << 16);
-      const int col0 = n_blk * p.BN + half * cols_half;
       float ssq = svi::conv::epilogue_pass1(p, t_base, cols_half / 16, col0, t, pix, ok);
       if (p.next_ring) {
         if (p.next_gamma) {
@@ -281,12 +283,18 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   }
 }
 
-// the launch side: tensor maps + parameters come from svi_conv3d_causal (conv3d_tcgen05.cu)
-bool eligible(const svi_conv_desc* d, int BN) {
-  return d->kw == 3 && d->pad_w == 1 && d->C_out % 32 == 0 && BN % 32 == 0 && BN <= MAX_BN;
+// the launch side: validated descriptor + parameters come from svi_conv3d_causal (conv3d_tcgen05.cu)
+
+// N tile of the pair kernel for this convolution (a multiple of 32: each CTA loads half of it in 8-row swizzle groups and each
+// of the two epilogue warps of a lane quadrant drains a multiple of 16 columns), or 0 when the kernel does not apply.
+// Narrow outputs (the decoder head, 3 channels padded to 4) run with N = 32: weight rows past w_rows are zero-filled by TMA.
+int pair_bn(const svi_conv_desc* d, int BN) {
+  if (d->kw != 3 || d->pad_w != 1) return 0;
+  if (d->C_out <= MAX_BN) return (d->C_out + 31) / 32 * 32;
+  return BN % 32 == 0 && BN <= MAX_BN ? BN : 0;
 }
 
-int launch(const svi_conv_desc* d, const svi::conv::Params& base, int BN, int desc_base_offset, cudaStream_t stream) {
+int launch(const svi_conv_desc* d, const svi::conv::Params& base, int BN, cudaStream_t stream) {
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -323,7 +331,6 @@ int launch(const svi_conv_desc* d, const svi::conv::Params& base, int BN, int de
   SVI_REQUIRE(pp.stages >= 2, "svi_conv3d_causal(pair): stage of %d bytes does not fit twice", pp.stage_bytes);
   const int last = d->C_in - (cin_chunks - 1) * BK;
   pp.nk_last = (last + 15) / 16;
-  pp.desc_base_offset = desc_base_offset;
 
   static bool attr_set = false;
   if (!attr_set) {

@@ -164,6 +164,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
       const int h = h0 + hl, w = w0 + wl;
       const bool ok = (h < p.H) && (w < p.W);
       const long long pix = (long long)h * p.W + w;
+      residual_prefetch(p, p.BN, n_blk * p.BN, t, pix, ok);     // while the K loop of this tile still runs
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * MAX_BN + (static_cast<uint32_t>(quad * 32) << 16);
@@ -261,10 +262,10 @@ extern "C" int svi_conv3d_causal(const svi_conv_desc* d, void* stream) {
   // kernel choice: 1 = single CTA, one input box per tap; 2 = CTA pairs with the input window reused across the horizontal
   // taps (conv3d2_tcgen05.cu); 0 = pair kernel where it applies and the image rows are long enough to fill its 128-pixel row tiles
   SVI_REQUIRE(d->variant >= 0 && d->variant <= 2, "svi_conv3d_causal: variant must be 0 (auto), 1 or 2");
-  const bool pair_ok = svi::conv2::eligible(d, BN);
-  SVI_REQUIRE(d->variant != 2 || pair_ok, "svi_conv3d_causal: variant 2 needs k_w = 3, pad_w = 1 and C_out (and its N tile) a multiple of 32");
-  if (d->variant == 2 || (d->variant == 0 && pair_ok && d->W >= svi::conv2::AUTO_MIN_W))
-    return svi::conv2::launch(d, p, BN, d->flags & 1, static_cast<cudaStream_t>(stream));
+  const int pair_bn = svi::conv2::pair_bn(d, BN);
+  SVI_REQUIRE(d->variant != 2 || pair_bn > 0, "svi_conv3d_causal: variant 2 needs k_w = 3 and pad_w = 1");
+  if (d->variant == 2 || (d->variant == 0 && pair_bn > 0 && d->W >= svi::conv2::AUTO_MIN_W))
+    return svi::conv2::launch(d, p, pair_bn, static_cast<cudaStream_t>(stream));
 
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -44,7 +44,7 @@ class ConvDesc(_c.Structure):
         ("residual", _vp), ("res_frame_stride", _i64), ("res_ld", _i32),
         ("next_ring", _vp), ("next_frame_stride", _i64), ("next_ld", _i32), ("next_slot", _i32 * 4),
         ("next_gamma", _vp), ("next_silu", _i32), ("write_f32", _i32),
-        ("variant", _i32), ("flags", _i32),
+        ("variant", _i32),
     ]
 
 

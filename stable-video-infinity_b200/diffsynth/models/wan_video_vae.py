@@ -144,7 +144,6 @@ def _ceil(a, b):
 
 
 _CONV_VARIANT = int(os.environ.get("SVI_CONV_VARIANT", "0"))
-_CONV_FLAGS = int(os.environ.get("SVI_CONV_FLAGS", "0"))     # bring-up switch of the pair kernel (include/svi_b200.h: svi_conv_desc.flags)
 
 
 def _pick_tile_w(H, W):
@@ -314,7 +313,6 @@ class WanVAEEngine:
                 d.slot[t * 3 + a] = slot_table[t][a]
         d.C_out = cv.c_out
         d.tile_w = _pick_tile_w(H, W)
-        d.flags = _CONV_FLAGS
         d.variant = _CONV_VARIANT          # 0: the library picks (CTA-pair kernel on long rows); 1 / 2 force one kernel (A/B runs)
         if out is not None:
             d.out, d.out_frame_stride, d.out_ld = out.data_ptr(), out_frame_stride, out_ld

@@ -89,10 +89,14 @@ def test_files_to_video_call_sequence(tmp_path):
     pipe2 = SVIVideoPipeline.from_model_manager(mm2, torch_dtype=torch.bfloat16, device="cuda", is_test=True)
     pipe2.prompter = _prompter
     ref = pipe2(seed=42, **kw)
+    again = pipe2(seed=42, **kw)
     a = np.stack([np.array(f) for f in clips[1]]).astype(np.int32)
     b = np.stack([np.array(f) for f in ref]).astype(np.int32)
-    d = np.abs(a - b)
+    c = np.stack([np.array(f) for f in again]).astype(np.int32)
+    d, rr = np.abs(a - b), np.abs(b - c)
     print(f"files vs in-memory clip: max |diff| = {d.max()} levels, mean {d.mean():.4f}, differing pixels {100 * (d > 0).mean():.2f} %")
-    # same weights, same kernels; the only non-determinism is the order of the fp32 atomicAdds of the row sums of squares
-    # (q/k RMS norms), which flips an occasional bf16 rounding: isolated pixels, a few grey levels at most
-    assert d.max() <= 4 and d.mean() < 0.05
+    print(f"same pipeline, same seed, twice: max |diff| = {rr.max()} levels, mean {rr.mean():.4f}")
+    # same weights, same kernels: the two pipelines may differ by what one pipeline differs from itself run to run — the order of
+    # the fp32 atomicAdds behind the row sums of squares (q/k RMS norms) flips an occasional bf16 rounding, which the following
+    # layers spread to the bf16 noise level — and by nothing more
+    assert d.max() <= 4 and d.mean() <= max(0.05, 1.5 * rr.mean())

@@ -581,7 +581,7 @@ def _conv_runner():
     import torch.nn.functional as F
     g = torch.Generator(device="cpu").manual_seed(7)
 
-    def run(Cin, Cout, kt, kh, kw, T, H, W, pad, n_split=0, residual=False, fuse=None, variant=1, flags=0, tag=""):
+    def run(Cin, Cout, kt, kh, kw, T, H, W, pad, n_split=0, residual=False, fuse=None, variant=1, tag=""):
         S = T + 2
         xs = (torch.randn(S, H, W, Cin, generator=g) * 0.5)
         ring = torch.zeros(S + 1, H, W, Cin, dtype=torch.bfloat16, device=dev)
@@ -604,7 +604,7 @@ def _conv_runner():
             for a in range(kt):
                 d.slot[t * 3 + a] = t + a + (3 - kt)   # frames t..t+2 of the ring are (t-2, t-1, t) of the stream
         d.C_out, d.tile_w = Cout, 8 if W <= 8 else 16
-        d.variant, d.flags = variant, flags
+        d.variant = variant
         res = torch.randn(T, H, W, Cout, generator=g).to(dev) if residual else None
         if n_split:
             out = torch.full((2 * T, H, W, n_split), float("nan"), device=dev)
@@ -669,20 +669,19 @@ def sec_conv():
     run(192, 96, 3, 3, 3, 1, 9, 7, 1, residual=True, fuse="both")
     # CTA-pair kernel (variant 2): rows longer than one 128-pixel tile, ragged last tile, odd row count (the odd CTA of the last
     # pair has no row), partial last channel chunk (96 = 64 + 32), two N tiles (384), 2-D conv (k_t = 1)
-    pair_cases(run, PAIR_FLAGS, " [pair]")
+    pair_cases(run, " [pair]")
 
 
-PAIR_FLAGS = int(os.environ.get("SVI_CONV_FLAGS", "0"))
-
-
-def pair_cases(run, flags, tag):
-    run(64, 96, 3, 3, 3, 2, 6, 150, 1, variant=2, flags=flags, tag=tag)
-    run(96, 96, 3, 3, 3, 1, 5, 200, 1, residual=True, variant=2, flags=flags, tag=tag)
-    run(96, 96, 3, 3, 3, 2, 4, 264, 1, fuse="only", variant=2, flags=flags, tag=tag)
-    run(192, 192, 3, 3, 3, 4, 3, 136, 1, residual=True, fuse="both", variant=2, flags=flags, tag=tag)
-    run(96, 384, 3, 3, 3, 1, 7, 130, 1, variant=2, flags=flags, tag=tag)
-    run(192, 96, 1, 3, 3, 3, 6, 257, 1, variant=2, flags=flags, tag=tag)
-    run(384, 384, 3, 3, 3, 1, 2, 40, 1, residual=True, variant=2, flags=flags, tag=tag)
+def pair_cases(run, tag):
+    run(64, 96, 3, 3, 3, 2, 6, 150, 1, variant=2, tag=tag)
+    run(96, 96, 3, 3, 3, 1, 5, 200, 1, residual=True, variant=2, tag=tag)
+    run(96, 96, 3, 3, 3, 2, 4, 264, 1, fuse="only", variant=2, tag=tag)
+    run(192, 192, 3, 3, 3, 4, 3, 136, 1, residual=True, fuse="both", variant=2, tag=tag)
+    run(96, 384, 3, 3, 3, 1, 7, 130, 1, variant=2, tag=tag)
+    run(192, 96, 1, 3, 3, 3, 6, 257, 1, variant=2, tag=tag)
+    run(384, 384, 3, 3, 3, 1, 2, 40, 1, residual=True, variant=2, tag=tag)
+    run(96, 4, 3, 3, 3, 2, 5, 200, 1, variant=2, tag=tag)          # decoder head: 3 (+1) output channels on an N = 32 tile
+    run(16, 48, 3, 3, 3, 1, 4, 140, 1, fuse="both", variant=2, tag=tag)
 
 
 def sec_perf_conv():
@@ -718,10 +717,11 @@ def sec_perf_conv():
                 d.C_out = Cout
                 from diffsynth.models.wan_video_vae import _pick_tile_w
                 d.tile_w = _pick_tile_w(H, W)
-                d.variant, d.flags = variant, PAIR_FLAGS
+                d.variant = variant
                 d.bias = bias.data_ptr()
                 d.out_ld = Cout
-                d.next_ring, d.next_frame_stride, d.next_ld = nring.data_ptr(), nring.stride(0), ncp
+                if Cout <= 256:
+                    d.next_ring, d.next_frame_stride, d.next_ld = nring.data_ptr(), nring.stride(0), ncp
                 for t in range(T):
                     d.next_slot[t] = t
                 d.next_gamma, d.next_silu = gamma.data_ptr(), 1
@@ -729,30 +729,15 @@ def sec_perf_conv():
                     d.out, d.out_frame_stride = out.data_ptr(), out.stride(0)
                     d.residual, d.res_frame_stride, d.res_ld = res.data_ptr(), res.stride(0), Cout
                     d.write_f32 = 1
-                else:
+                elif Cout <= 256:
                     d.write_f32 = 0
+                else:
+                    d.out, d.out_frame_stride, d.write_f32 = out.data_ptr(), out.stride(0), 1
                 ms = time_ms(lambda: nv.conv3d_causal(d), iters=5, warm=2)
                 line += f"  v{variant} {ms * 1e3:.0f} us = {fl / ms / 1e9:.0f} TF/s"
             print(line, flush=True)
         del ring, wp, out, res, nring
         torch.cuda.empty_cache()
-
-
-def sec_conv_pair_probe():
-    """Bring-up: the pair kernel with and without the descriptor base-offset convention (results are printed, not gated)."""
-    global RESULTS
-    keep = list(RESULTS)
-    for flags in ([int(os.environ["SVI_PROBE_FLAGS"])] if "SVI_PROBE_FLAGS" in os.environ else [0, 1]):
-        print(f"--- pair kernel, flags={flags}", flush=True)
-        RESULTS = []
-        try:
-            pair_cases(_conv_runner(), flags, f" [pair flags={flags}]")
-        except Exception as ex:  # noqa: BLE001
-            print("    raised:", repr(ex)[:300], flush=True)
-        n_ok = sum(ok for _, ok in RESULTS)
-        print(f"--- flags={flags}: {n_ok} of {len(RESULTS)} ok", flush=True)
-        print(f"PROBE flags={flags} allok={int(len(RESULTS) > 0 and n_ok == len(RESULTS))}", flush=True)
-    RESULTS = keep
 
 
 if __name__ == "__main__":
