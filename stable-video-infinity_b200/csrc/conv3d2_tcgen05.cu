@@ -62,22 +62,41 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtenso
       "l"(m), "r"(bar_even), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
-// one K = 16 step of the M = 256 pair MMA (whole warp calls with uniform operands; one elected lane issues)
-__device__ __forceinline__ void mma2_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                        uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, q;\n"
-      ".reg .b64 da, db;\n"
-      "setp.ne.b32 p, %6, 0;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "mov.b64 da, {%1, %2};\n"
-      "mov.b64 db, {%3, %4};\n"
-      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
+// 1..4 K = 16 steps of the M = 256 pair MMA in ONE asm block (whole warp calls with uniform operands; one elected lane issues):
+// a C++ loop of single MMAs costs an elect + predicate + descriptor moves per 48-cycle MMA at N = 96
+#define SVI_MMA2_HEAD                      \
+  "{\n"                                    \
+  ".reg .pred p, q, t;\n"                  \
+  ".reg .b64 da, db;\n"                    \
+  ".reg .b32 a1, b1;\n"                    \
+  "setp.ne.b32 p, %6, 0;\n"                \
+  "setp.eq.b32 t, 0, 0;\n"                 \
+  "elect.sync _|q, 0xffffffff;\n"          \
+  "mov.b64 da, {%1, %2};\n"                \
+  "mov.b64 db, {%3, %4};\n"                \
+  "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+#define SVI_MMA2_STEP(off)                 \
+  "add.u32 a1, %1, " #off ";\n"            \
+  "add.u32 b1, %3, " #off ";\n"            \
+  "mov.b64 da, {a1, %2};\n"                \
+  "mov.b64 db, {b1, %4};\n"                \
+  "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, t;\n"
+#define SVI_MMA2_ARGS \
+  ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first) : "memory"
+__device__ __forceinline__ void mma2_ss_n(int nk, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t acc_first) {
+  if (nk == 4)
+    asm volatile(SVI_MMA2_HEAD SVI_MMA2_STEP(2) SVI_MMA2_STEP(4) SVI_MMA2_STEP(6) "}\n" SVI_MMA2_ARGS);
+  else if (nk == 2)
+    asm volatile(SVI_MMA2_HEAD SVI_MMA2_STEP(2) "}\n" SVI_MMA2_ARGS);
+  else if (nk == 3)
+    asm volatile(SVI_MMA2_HEAD SVI_MMA2_STEP(2) SVI_MMA2_STEP(4) "}\n" SVI_MMA2_ARGS);
+  else
+    asm volatile(SVI_MMA2_HEAD "}\n" SVI_MMA2_ARGS);
 }
+#undef SVI_MMA2_HEAD
+#undef SVI_MMA2_STEP
+#undef SVI_MMA2_ARGS
 __device__ __forceinline__ void commit2_multicast(uint32_t bar) {
   asm volatile(
       "{\n"
@@ -227,10 +246,8 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
               // with the row phase in that field the results are wrong, profiles/r02_c6_pair_probe.log)
               const uint32_t a_lo = smem_desc_lo(sa + c * 128, 16);
               const uint32_t b_lo = smem_desc_lo(sa + A_BYTES + c * pp.b_bytes, 16);
-              for (int k = 0; k < nk; ++k) {
-                mma2_ss(d_tmem, a_lo + 2 * k, hi_kmaj, b_lo + 2 * k, hi_kmaj, idesc, accumulate);
-                accumulate = 1;
-              }
+              mma2_ss_n(nk, d_tmem, a_lo, hi_kmaj, b_lo, hi_kmaj, idesc, accumulate);
+              accumulate = 1;
             }
             commit2_multicast(bar(EMPTY + stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }

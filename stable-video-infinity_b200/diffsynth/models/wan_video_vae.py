@@ -205,12 +205,19 @@ class _Ring:
     def __init__(self, slots, H, W, C, device, history, halo=0):
         self.buf = torch.zeros(slots + 1, H + 2 * halo, W, C, device=device, dtype=torch.bfloat16)
         self.slots, self.H, self.W, self.C, self.halo = slots, H, W, C, halo
-        self.next = 0
+        self.next, self.history = 0, history
         self.hist = [slots] * history           # slot ids of the most recent frames (oldest first)
 
     def frame(self, slot):
         """The rank's own rows of a slot: bf16 [H, W, C] (contiguous)."""
         return self.buf[slot, self.halo:self.halo + self.H]
+
+    def rewind(self):
+        """Start of a new video: empty history again.  The buffer is NOT cleared — every slot is written in full before it
+        is referenced, the padding channels and the outer halo rows are never written (they stay zero from the allocation),
+        and the history points at the all-zero slot until real frames exist."""
+        self.next = 0
+        self.hist = [self.slots] * self.history
 
     def push(self, n):
         ids = [(self.next + i) % self.slots for i in range(n)]
@@ -264,7 +271,10 @@ class WanVAEEngine:
 
     # ------------------------------------------------------------------ low-level helpers
     def reset(self):
-        self.rings = {}
+        # rings are kept across videos of the same geometry (re-allocating and zero-filling them was 2.5 % of a round trip,
+        # profiles/r02_c7_vae_launches.summary.txt); _ring() replaces one whose geometry changed
+        for r in self.rings.values():
+            r.rewind()
         self.chunk = 0
 
     def _ring(self, key, slots, H, W, C, history, halo=0):
