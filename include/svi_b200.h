@@ -52,7 +52,7 @@ typedef struct svi_gemm_epilogue {
   const float* gate;     /* [N] or NULL */
   const float* residual; /* [M, ldr] f32 or NULL; may alias out when out_is_f32 */
   int64_t ldr;
-  float* sumsq;          /* [M, sumsq_groups] f32, accumulated with atomicAdd; or NULL */
+  float* sumsq;          /* [M, sumsq_groups] f32, accumulated with atomicAdd (sumsq_parts == 0); or NULL */
   int32_t sumsq_groups;  /* number of column groups that are accumulated (columns beyond are skipped) */
   int32_t sumsq_group_cols; /* width of one group in columns; multiple of 32 */
   /* ---- LayerNorm folded into the GEMM (M > 128 only; both sides optional, NULL = off) ------------------------------
@@ -64,6 +64,11 @@ typedef struct svi_gemm_epilogue {
    * A operand of the NEXT GEMM — and accumulate row_stats[m] += (sum_n v, sum_n v^2) with atomicAdd. */
   const float* ln_stats; const float* ln_u; int32_t ln_dim; float ln_eps;
   void* a_next; int64_t ld_an; const float* g_next; float* row_stats;
+  /* ---- reproducible row sums of squares: sumsq_parts = sumsq_group_cols / 128 (> 0) makes every 128-column segment STORE
+   * its partial sum into sumsq[m, segment] (buffer [M, sumsq_groups * sumsq_parts], no zeroing needed) instead of the
+   * atomicAdd per group; the consumers (svi_rmsnorm_rope, svi_qk_norm_rope, svi_attn_fwd_qscale) add a group's partials in
+   * index order, so a forward is bit-identical from run to run.  Needs sumsq_group_cols % 128 == 0.  0: atomicAdd. */
+  int32_t sumsq_parts;
 } svi_gemm_epilogue;
 
 /*
@@ -94,15 +99,16 @@ int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const v
 size_t svi_attn_workspace_bytes(int32_t Lq, int32_t Lk, int32_t num_heads);
 /*
  * svi_attn_fwd with the full-width RMSNorm of Q folded into the softmax scale: row r of Q is used as
- * Q[r,:] * rsqrt(q_sumsq[r * q_ss_ld] / q_dim + q_eps), i.e. Q holds the UN-normalised projection and q_sumsq the row
- * sums of squares the GEMM epilogue accumulated (svi_gemm_epilogue.sumsq).  The norm's per-channel weight commutes with
+ * Q[r,:] * rsqrt(S_r / q_dim + q_eps), S_r = q_sumsq[r * q_ss_ld] (q_ss_parts <= 1) or the sum of the q_ss_parts partials
+ * q_sumsq[r * q_ss_ld + 0 .. q_ss_parts) in index order; i.e. Q holds the UN-normalised projection and q_sumsq the row
+ * sums of squares the GEMM epilogue produced (svi_gemm_epilogue.sumsq / sumsq_parts).  The norm's per-channel weight commutes with
  * the dot product and is applied to K by the caller (K' = K * w_q).  Replaces norm_q of CrossAttention.forward,
  * wan_video_dit.py:272, without a pass over Q.
  */
 int svi_attn_fwd_qscale(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
                         void* O, int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale,
-                        int32_t accumulate, const float* q_sumsq, int32_t q_ss_ld, int32_t q_dim, float q_eps,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        int32_t accumulate, const float* q_sumsq, int32_t q_ss_ld, int32_t q_ss_parts, int32_t q_dim,
+                        float q_eps, void* workspace, size_t workspace_bytes, void* stream);
 /* The launch plan svi_attn_fwd uses (pure host function, no device needed): `units` = num_heads * ceil(Lq/256) equal
  * CTAs, kv_tiles = ceil(Lk/128), on `sms` SMs with a workspace of workspace_bytes -> units [0, n_full) run whole, the
  * rest are cut into `split` K/V slices each (split == 1: nothing is sliced). */
@@ -158,19 +164,21 @@ int svi_layernorm_modulate_split(const float* x, int32_t M, int32_t D, float eps
                                  int64_t ldy, int32_t lo_col, void* stream);
 
 /*
- * In place on bf16 rows t[m, 0:D] (leading dim ldt):  t = t * rsqrt(sumsq[m*sumsq_ld + sumsq_col]/D + eps) * w[:]
+ * In place on bf16 rows t[m, 0:D] (leading dim ldt):  t = t * rsqrt(S_m/D + eps) * w[:],  S_m = sumsq[m*sumsq_ld + sumsq_col]
+ * (sumsq_parts <= 1) or the sum, in index order, of the partials sumsq[m*sumsq_ld + sumsq_col*sumsq_parts + 0 .. sumsq_parts)
  * then, if rope_cos != NULL, the interleaved-pair rotation of every head (head_dim 128):
  *   (t[2i], t[2i+1]) <- (t[2i] c_i - t[2i+1] s_i,  t[2i] s_i + t[2i+1] c_i),  c,s = rope[(m + row_offset), i], i<64.
  * Replaces RMSNorm (wan_video_dit.py:186-197, over the FULL width D) + rope_apply (:178-183).
  */
 int svi_rmsnorm_rope(void* t_bf16, int64_t ldt, int32_t M, int32_t D, const float* sumsq,
-                     int32_t sumsq_ld, int32_t sumsq_col, float eps, const float* w,
+                     int32_t sumsq_ld, int32_t sumsq_col, int32_t sumsq_parts, float eps, const float* w,
                      const float* rope_cos, const float* rope_sin, int32_t row_offset, void* stream);
 
 /* svi_rmsnorm_rope on q and k of the fused QKV buffer in ONE launch: row m holds q at [0, D) and k at [D, 2D);
- * sumsq[m*sumsq_ld + 0] / [.. + 1] are their row sums of squares, wq / wk the norm weights (wan_video_dit.py:227-231). */
+ * sumsq groups 0 / 1 (as in svi_rmsnorm_rope, sumsq_parts partials each) are their row sums of squares, wq / wk the norm
+ * weights (wan_video_dit.py:227-231). */
 int svi_qk_norm_rope(void* qk_bf16, int64_t ld, int32_t M, int32_t D, const float* sumsq, int32_t sumsq_ld,
-                     float eps, const float* wq, const float* wk, const float* rope_cos, const float* rope_sin,
+                     int32_t sumsq_parts, float eps, const float* wq, const float* wk, const float* rope_cos, const float* rope_sin,
                      int32_t row_offset, void* stream);
 
 /*

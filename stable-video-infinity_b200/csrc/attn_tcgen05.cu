@@ -106,11 +106,18 @@ struct Params {
   float* ws_o;               // [slices][256 rows][128] unnormalised partial O
   float2* ws_ml;             // [slices][256 rows] (row max in scaled log2 units, row sum)
   // optional per-row RMS scale of Q (full-width RMSNorm folded into the softmax scale): row r of Q is used as
-  // Q[r] * rsqrt(q_sumsq[r * q_ss_ld] * q_inv_d + q_eps); nullptr: none
+  // Q[r] * rsqrt(sum_{j < q_ss_parts} q_sumsq[r * q_ss_ld + j] * q_inv_d + q_eps); nullptr: none
   const float* q_sumsq;
-  int q_ss_ld;
+  int q_ss_ld, q_ss_parts;
   float q_inv_d, q_eps;
 };
+
+__device__ __forceinline__ float q_row_sumsq(const Params& p, int qrow) {   // partials added in index order: reproducible
+  const float* sp = p.q_sumsq + (long long)qrow * p.q_ss_ld;
+  float s = __ldg(sp);
+  for (int j = 1; j < p.q_ss_parts; ++j) s += __ldg(sp + j);
+  return s;
+}
 
 // KV tile visited at iteration j: the stream starts on the rank's own rows and wraps around
 __device__ __forceinline__ int kv_tile_at(int j, int first_tile, int n_kv) {
@@ -302,7 +309,7 @@ __device__ __forceinline__ void softmax_role(const Params& p, uint32_t sbase, ui
     c[i] = p.scale_log2;
     if (p.q_sumsq) {          // this thread's Q rows carry their RMSNorm factor in the softmax scale
       const int qrow = min(u.q_row0 + i * BQ + rl, p.Lq - 1);
-      c[i] *= rsqrtf(__ldg(p.q_sumsq + (long long)qrow * p.q_ss_ld) * p.q_inv_d + p.q_eps);
+      c[i] *= rsqrtf(q_row_sumsq(p, qrow) * p.q_inv_d + p.q_eps);
     }
     m_cur[i] = -INFINITY;     // running row max (scaled, log2 domain); reference point of P and O; identical in both halves
     l[i] = 0.f;               // running sum of THIS half's P
@@ -472,7 +479,7 @@ __device__ __forceinline__ void softmax_role(const Params& p, uint32_t sbase, ui
   float c = p.scale_log2;
   if (p.q_sumsq) {          // this thread's Q row carries its RMSNorm factor in the softmax scale
     const int qrow = min(u.q_row0 + i * BQ + quad * 32 + lane, p.Lq - 1);
-    c *= rsqrtf(__ldg(p.q_sumsq + (long long)qrow * p.q_ss_ld) * p.q_inv_d + p.q_eps);
+    c *= rsqrtf(q_row_sumsq(p, qrow) * p.q_inv_d + p.q_eps);
   }
   float m_cur = -INFINITY;  // running row max (scaled, log2 domain); reference point of P and O
   float l = 0.f;            // running row sum of P
@@ -740,6 +747,7 @@ static void plan_split(int units, int n_kv, int sms, size_t ws_bytes, int* n_ful
 struct QScale {
   const float* sumsq = nullptr;
   int ld = 0;
+  int parts = 1;
   int dim = 1;
   float eps = 0.f;
 };
@@ -789,6 +797,7 @@ static int launch_attn(const void* Q, int64_t ldq, const void* K, int64_t ldk, c
   p.kv_self_chunk = kv_self_chunk;
   p.q_sumsq = qs.sumsq;
   p.q_ss_ld = qs.ld;
+  p.q_ss_parts = qs.parts;
   p.q_inv_d = 1.0f / (float)qs.dim;
   p.q_eps = qs.eps;
   p.kv_first_tile = 0;
@@ -830,13 +839,15 @@ extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t l
 
 extern "C" int svi_attn_fwd_qscale(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
                                    void* O, int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale,
-                                   int32_t accumulate, const float* q_sumsq, int32_t q_ss_ld, int32_t q_dim, float q_eps,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+                                   int32_t accumulate, const float* q_sumsq, int32_t q_ss_ld, int32_t q_ss_parts, int32_t q_dim,
+                                   float q_eps, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace svi;
-  SVI_REQUIRE(q_sumsq && q_ss_ld >= 1 && q_dim >= 1, "svi_attn_fwd_qscale: need q_sumsq, q_ss_ld >= 1, q_dim >= 1");
+  SVI_REQUIRE(q_sumsq && q_ss_ld >= 1 && q_dim >= 1 && q_ss_parts >= 0 && q_ss_parts <= q_ss_ld,
+              "svi_attn_fwd_qscale: need q_sumsq, q_ss_ld >= 1, q_dim >= 1, 0 <= q_ss_parts <= q_ss_ld");
   svi::attn::QScale qs;
   qs.sumsq = q_sumsq;
   qs.ld = q_ss_ld;
+  qs.parts = q_ss_parts > 0 ? q_ss_parts : 1;
   qs.dim = q_dim;
   qs.eps = q_eps;
   return svi::attn::launch_attn(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, num_heads, scale, accumulate, nullptr, 0, 1, 0,

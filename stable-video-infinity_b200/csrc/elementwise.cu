@@ -176,7 +176,7 @@ layernorm_modulate_warp_kernel(const float* __restrict__ x, int M, int D, float 
 // sumsq columns sumsq_col / sumsq_col + 1 and weights w / w2 — one launch instead of two.
 __global__ void __launch_bounds__(256)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D, int groups,
-                    const float* __restrict__ sumsq, int sumsq_ld, int sumsq_col, float eps,
+                    const float* __restrict__ sumsq, int sumsq_ld, int sumsq_col, int parts, float eps,
                     const float* __restrict__ w, const float* __restrict__ w2, const float* __restrict__ rope_cos,
                     const float* __restrict__ rope_sin, int row_offset) {
   const int vec_per_row = (D >> 3) * groups;
@@ -188,7 +188,11 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D, 
     const int cc = (int)(i % vec_per_row) * 8;      // column inside the row (both groups)
     const int grp = cc >= D ? 1 : 0;
     const int c0 = cc - grp * D;                     // column inside the group
-    const float rs = rsqrtf(sumsq[(long long)m * sumsq_ld + sumsq_col + grp] * inv_d + eps);
+    // the group's sum of squares: one value (atomically accumulated) or `parts` partials added in index order (reproducible)
+    const float* sp = sumsq + (long long)m * sumsq_ld + (long long)(sumsq_col + grp) * parts;
+    float ssum = sp[0];
+    for (int q = 1; q < parts; ++q) ssum += sp[q];
+    const float rs = rsqrtf(ssum * inv_d + eps);
     uint4* ptr = reinterpret_cast<uint4*>(t + (long long)m * ldt + cc);
     const uint4 raw = *ptr;
     const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
@@ -437,7 +441,7 @@ extern "C" int svi_layernorm_modulate_split(const float* x, int32_t M, int32_t D
 }
 
 extern "C" int svi_rmsnorm_rope(void* t_bf16, int64_t ldt, int32_t M, int32_t D, const float* sumsq,
-                                int32_t sumsq_ld, int32_t sumsq_col, float eps, const float* w,
+                                int32_t sumsq_ld, int32_t sumsq_col, int32_t sumsq_parts, float eps, const float* w,
                                 const float* rope_cos, const float* rope_sin, int32_t row_offset,
                                 void* stream) {
   SVI_REQUIRE(t_bf16 && sumsq && w, "svi_rmsnorm_rope: null pointer");
@@ -449,13 +453,14 @@ extern "C" int svi_rmsnorm_rope(void* t_bf16, int64_t ldt, int32_t M, int32_t D,
               "svi_rmsnorm_rope: alignment");
   const long long total = (long long)M * (D / 8);
   rmsnorm_rope_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(t_bf16), ldt, M, D, 1, sumsq, sumsq_ld, sumsq_col, eps, w, w, rope_cos,
+      reinterpret_cast<__nv_bfloat16*>(t_bf16), ldt, M, D, 1, sumsq, sumsq_ld, sumsq_col, sumsq_parts > 0 ? sumsq_parts : 1, eps, w, w, rope_cos,
       rope_sin, row_offset);
   SVI_CUDA_LAUNCH_CHECK("svi_rmsnorm_rope");
   return SVI_OK;
 }
 
 extern "C" int svi_qk_norm_rope(void* qk_bf16, int64_t ld, int32_t M, int32_t D, const float* sumsq, int32_t sumsq_ld,
+                                int32_t sumsq_parts,
                                 float eps, const float* wq, const float* wk, const float* rope_cos,
                                 const float* rope_sin, int32_t row_offset, void* stream) {
   SVI_REQUIRE(qk_bf16 && sumsq && wq && wk && rope_cos && rope_sin, "svi_qk_norm_rope: null pointer");
@@ -465,7 +470,7 @@ extern "C" int svi_qk_norm_rope(void* qk_bf16, int64_t ld, int32_t M, int32_t D,
               "svi_qk_norm_rope: alignment");
   const long long total = (long long)M * (D / 4);
   rmsnorm_rope_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(qk_bf16), ld, M, D, 2, sumsq, sumsq_ld, 0, eps, wq, wk, rope_cos, rope_sin,
+      reinterpret_cast<__nv_bfloat16*>(qk_bf16), ld, M, D, 2, sumsq, sumsq_ld, 0, sumsq_parts > 0 ? sumsq_parts : 1, eps, wq, wk, rope_cos, rope_sin,
       row_offset);
   SVI_CUDA_LAUNCH_CHECK("svi_qk_norm_rope");
   return SVI_OK;

@@ -581,10 +581,11 @@ extern "C" int svi_attn_fwd(const void* Q, int64_t ldq, const void* K, int64_t l
 
 extern "C" int svi_attn_fwd_qscale(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
                                    void* O, int64_t ldo, int32_t Lq, int32_t Lk, int32_t num_heads, float scale,
-                                   int32_t accumulate, const float* q_sumsq, int32_t q_ss_ld, int32_t q_dim, float q_eps,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+                                   int32_t accumulate, const float* q_sumsq, int32_t q_ss_ld, int32_t q_ss_parts, int32_t q_dim,
+                                   float q_eps, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace svi;
   SVI_REQUIRE(q_sumsq && q_ss_ld >= 1 && q_dim >= 1, "svi_attn_fwd_qscale: need q_sumsq, q_ss_ld >= 1, q_dim >= 1");
+  SVI_REQUIRE(q_ss_parts <= 1, "svi_attn_fwd_qscale (round-1 kernel, A/B build): partial row sums are not supported");
   svi::attn::QScale qs;
   qs.sumsq = q_sumsq;
   qs.ld = q_ss_ld;

@@ -50,6 +50,7 @@ struct Epi {
   float* sumsq;
   int sumsq_groups;
   int sumsq_group_cols;
+  int sumsq_parts;
   // LayerNorm folded into this GEMM (consumer side): A holds bf16(x * g) of the UN-normalised rows x; with the row statistics
   // (sum x, sum x^2) the epilogue reconstructs  LN(x)*g + t  times W^T  =  r_m (acc - mu_m u_n) + c_n,  u = W g, c = W t + b
   // (c arrives as `bias`)
@@ -392,15 +393,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tmem_ld32(t_base + c * 32, r);
         tmem_ld_wait();
         if (row_ok) {
-          if (ep.sumsq) {
-            const int g = n0 / ep.sumsq_group_cols;
-            if (g != ss_group) {
-              if (ss_group >= 0 && ss_group < ep.sumsq_groups)
-                atomicAdd(&ep.sumsq[(long long)row * ep.sumsq_groups + ss_group], ss);
-              ss = 0.f;
-              ss_group = g;
-            }
-          }
+          if (ep.sumsq) sumsq_step(ep, n0, row, ss, ss_group);
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             const int n = n0 + j8 * 8;
@@ -480,8 +473,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
       }
-      if (row_ok && ep.sumsq && ss_group >= 0 && ss_group < ep.sumsq_groups)
-        atomicAdd(&ep.sumsq[(long long)row * ep.sumsq_groups + ss_group], ss);
+      if (row_ok && ep.sumsq) sumsq_flush(ep, row, ss, ss_group);
       if (ep.a_next) {
         if (coal) {       // row sums of the coalesced phase: 8 lanes share a row
           const int row_w0 = m_blk * 2 * BM + (int)rank * BM + quad * 32;
@@ -530,7 +522,7 @@ int launch(const void* A, long long lda, const void* W, long long ldw, int M, in
   Epi ep;
   ep.out = e->out; ep.ldo = e->ldo; ep.out_is_f32 = e->out_is_f32; ep.act = e->act;
   ep.bias = e->bias; ep.gate = e->gate; ep.residual = e->residual; ep.ldr = e->ldr;
-  ep.sumsq = e->sumsq; ep.sumsq_groups = e->sumsq_groups; ep.sumsq_group_cols = e->sumsq_group_cols;
+  ep.sumsq = e->sumsq; ep.sumsq_groups = e->sumsq_groups; ep.sumsq_group_cols = e->sumsq_group_cols; ep.sumsq_parts = e->sumsq_parts;
   ep.ln_stats = e->ln_stats; ep.ln_u = e->ln_u; ep.ln_inv_d = e->ln_dim > 0 ? 1.0f / (float)e->ln_dim : 0.f; ep.ln_eps = e->ln_eps;
   ep.a_next = reinterpret_cast<__nv_bfloat16*>(e->a_next); ep.ld_an = e->ld_an; ep.g_next = e->g_next; ep.row_stats = e->row_stats;
   static bool attr_set = false;

@@ -38,6 +38,7 @@ struct Epi {
   float* sumsq;
   int sumsq_groups;
   int sumsq_group_cols;
+  int sumsq_parts;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -160,15 +161,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tmem_ld32(t_base + c * 32, r);
         tmem_ld_wait();
         if (row_ok) {
-          if (ep.sumsq) {
-            const int g = n0 / ep.sumsq_group_cols;
-            if (g != ss_group) {
-              if (ss_group >= 0 && ss_group < ep.sumsq_groups)
-                atomicAdd(&ep.sumsq[(long long)row * ep.sumsq_groups + ss_group], ss);
-              ss = 0.f;
-              ss_group = g;
-            }
-          }
+          if (ep.sumsq) sumsq_step(ep, n0, row, ss, ss_group);
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {  // 8 columns at a time
             const int n = n0 + j8 * 8;
@@ -220,8 +213,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       }
-      if (row_ok && ep.sumsq && ss_group >= 0 && ss_group < ep.sumsq_groups)
-        atomicAdd(&ep.sumsq[(long long)row * ep.sumsq_groups + ss_group], ss);
+      if (row_ok && ep.sumsq) sumsq_flush(ep, row, ss, ss_group);
       // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator back
       tc_fence_before();
       __syncwarp();
@@ -269,6 +261,9 @@ extern "C" int svi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   if (e->sumsq)
     SVI_REQUIRE(e->sumsq_groups > 0 && e->sumsq_group_cols > 0 && e->sumsq_group_cols % 32 == 0,
                 "svi_gemm_bf16: sumsq_group_cols must be a positive multiple of 32");
+  if (e->sumsq && e->sumsq_parts)
+    SVI_REQUIRE(e->sumsq_group_cols % 128 == 0 && e->sumsq_parts == e->sumsq_group_cols / 128,
+                "svi_gemm_bf16: sumsq_parts must be 0 (atomic accumulation) or sumsq_group_cols / 128 with sumsq_group_cols %% 128 == 0");
 
   if (e->ln_stats || e->a_next) {
     SVI_REQUIRE(M > BM, "svi_gemm_bf16: the LayerNorm fold (ln_stats / a_next) runs in the CTA-pair kernel: needs M > 128");
@@ -295,7 +290,7 @@ extern "C" int svi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   Epi ep;
   ep.out = e->out; ep.ldo = e->ldo; ep.out_is_f32 = e->out_is_f32; ep.act = e->act;
   ep.bias = e->bias; ep.gate = e->gate; ep.residual = e->residual; ep.ldr = e->ldr;
-  ep.sumsq = e->sumsq; ep.sumsq_groups = e->sumsq_groups; ep.sumsq_group_cols = e->sumsq_group_cols;
+  ep.sumsq = e->sumsq; ep.sumsq_groups = e->sumsq_groups; ep.sumsq_group_cols = e->sumsq_group_cols; ep.sumsq_parts = e->sumsq_parts;
 
   static bool attr_set = false;
   if (!attr_set) {

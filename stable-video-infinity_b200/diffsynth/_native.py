@@ -26,6 +26,7 @@ class GemmEpilogue(_c.Structure):
         ("sumsq", _vp), ("sumsq_groups", _i32), ("sumsq_group_cols", _i32),
         ("ln_stats", _vp), ("ln_u", _vp), ("ln_dim", _i32), ("ln_eps", _f32),
         ("a_next", _vp), ("ld_an", _i64), ("g_next", _vp), ("row_stats", _vp),
+        ("sumsq_parts", _i32),
     ]
 
 
@@ -56,7 +57,7 @@ SIGNATURES = {
     "svi_gemm_bf16": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _c.POINTER(GemmEpilogue), _vp]),
     "svi_attn_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp, _c.c_size_t, _vp]),
     "svi_attn_workspace_bytes": (_c.c_size_t, [_i32, _i32, _i32]),
-    "svi_attn_fwd_qscale": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp, _i32, _i32, _f32,
+    "svi_attn_fwd_qscale": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp, _i32, _i32, _i32, _f32,
                                    _vp, _c.c_size_t, _vp]),
     "svi_attn_plan": (None, [_i32, _i32, _i32, _c.c_size_t, _c.POINTER(_i32), _c.POINTER(_i32)]),
     "svi_attn_fwd_sp": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _c.c_uint32, _i32, _i32, _vp, _c.c_size_t, _vp]),
@@ -67,8 +68,8 @@ SIGNATURES = {
     "svi_sp_push": (_i32, [_vp, _c.POINTER(_vp), _c.POINTER(_vp), _i32, _c.c_size_t, _vp, _vp]),
     "svi_layernorm_modulate": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "svi_layernorm_modulate_split": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "svi_rmsnorm_rope": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _i32, _vp]),
-    "svi_qk_norm_rope": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "svi_rmsnorm_rope": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _i32, _vp]),
+    "svi_qk_norm_rope": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "svi_patchify_gather_split": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "svi_split_f32_to_bf16x2": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _vp]),
     "svi_zero": (_i32, [_vp, _c.c_size_t, _vp]),
@@ -186,9 +187,15 @@ def gemm(a, w, out, bias=None, act=ACT_NONE, gate=None, residual=None, sumsq=Non
         ep.residual = _ptr(residual, torch.float32, "residual")
         ep.ldr = _rowmajor(residual, "residual")
     if sumsq is not None:
+        # [M, groups]: atomicAdd per group (the buffer must be zero);  [M, groups, parts] contiguous, parts = group_cols / 128:
+        # every 128-column segment stores its partial sum (reproducible, no zeroing) — see svi_gemm_epilogue.sumsq_parts
         ep.sumsq = _ptr(sumsq, torch.float32, "sumsq")
         ep.sumsq_groups = sumsq.shape[1]
         ep.sumsq_group_cols = sumsq_group_cols
+        if sumsq.dim() == 3:
+            if not sumsq.is_contiguous() or sumsq.shape[2] * 128 != sumsq_group_cols:
+                raise RuntimeError("svi_b200.gemm: partial sumsq must be contiguous [M, groups, sumsq_group_cols / 128]")
+            ep.sumsq_parts = sumsq.shape[2]
     if ln is not None or emit is not None:
         if M <= 128:
             raise RuntimeError("svi_b200.gemm: the LayerNorm fold runs in the CTA-pair kernel (M > 128)")
@@ -226,7 +233,7 @@ def attention(q, k, v, out, num_heads, scale=None, accumulate=False, workspace=N
 
 def attention_qscale(q, k, v, out, num_heads, q_sumsq, q_dim, q_eps, scale=None, accumulate=False, workspace=None):
     """attention() on an UN-normalised q whose full-width RMSNorm factor rsqrt(q_sumsq[r] / q_dim + q_eps) is applied inside
-    the softmax (svi_attn_fwd_qscale); q_sumsq f32 [Lq, n] (column 0 is used)."""
+    the softmax (svi_attn_fwd_qscale); q_sumsq f32 [Lq, n] (column 0 is used) or [Lq, n, parts] (the partials of group 0)."""
     ldq, ldk, ldv, ldo = (_rowmajor(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")))
     if scale is None:
         scale = 128 ** -0.5
@@ -235,10 +242,19 @@ def attention_qscale(q, k, v, out, num_heads, q_sumsq, q_dim, q_eps, scale=None,
     rc = load().svi_attn_fwd_qscale(_ptr(q, torch.bfloat16, "q"), ldq, _ptr(k, torch.bfloat16, "k"), ldk,
                                     _ptr(v, torch.bfloat16, "v"), ldv, _ptr(out, torch.bfloat16, "out"), ldo,
                                     q.shape[0], k.shape[0], num_heads, float(scale), int(bool(accumulate)),
-                                    _ptr(q_sumsq, torch.float32, "q_sumsq"), _rowmajor(q_sumsq, "q_sumsq"), int(q_dim),
+                                    _ptr(q_sumsq, torch.float32, "q_sumsq"), *_sumsq_layout(q_sumsq), int(q_dim),
                                     float(q_eps), *_workspace(workspace), _stream())
     _check(rc, "svi_attn_fwd_qscale")
     return out
+
+
+def _sumsq_layout(ss):
+    """(floats per row, partials per group) of a row-sum-of-squares buffer: [M, groups] or contiguous [M, groups, parts]."""
+    if ss.dim() == 3:
+        if not ss.is_contiguous():
+            raise RuntimeError("svi_b200: a partial sumsq buffer [M, groups, parts] must be contiguous")
+        return ss.shape[1] * ss.shape[2], ss.shape[2]
+    return _rowmajor(ss, "sumsq"), 0
 
 
 def _workspace(ws):
@@ -346,7 +362,7 @@ def qk_norm_rope(qk, sumsq, eps, wq, wk, rope_cos, rope_sin, row_offset=0):
     ld = _rowmajor(qk, "qk")
     M, D2 = qk.shape
     rc = load().svi_qk_norm_rope(_ptr(qk, torch.bfloat16, "qk"), ld, M, D2 // 2, _ptr(sumsq, torch.float32, "sumsq"),
-                                 _rowmajor(sumsq, "sumsq"), float(eps), _ptr(wq, torch.float32, "wq"),
+                                 *_sumsq_layout(sumsq), float(eps), _ptr(wq, torch.float32, "wq"),
                                  _ptr(wk, torch.float32, "wk"), _ptr(rope_cos, torch.float32, "rope_cos"),
                                  _ptr(rope_sin, torch.float32, "rope_sin"), row_offset, _stream())
     _check(rc, "svi_qk_norm_rope")
@@ -395,8 +411,9 @@ def rmsnorm_rope(t, sumsq, sumsq_col, eps, weight, rope_cos=None, rope_sin=None,
     """In place on bf16 t[M, D] (row-strided view allowed): full-width RMSNorm + optional RoPE."""
     ldt = _rowmajor(t, "t")
     M, D = t.shape
+    ss_ld, ss_parts = _sumsq_layout(sumsq)
     rc = load().svi_rmsnorm_rope(_ptr(t, torch.bfloat16, "t"), ldt, M, D, _ptr(sumsq, torch.float32, "sumsq"),
-                                 sumsq.shape[1], sumsq_col, float(eps), _ptr(weight, torch.float32, "weight"),
+                                 ss_ld, sumsq_col, ss_parts, float(eps), _ptr(weight, torch.float32, "weight"),
                                  _ptr(rope_cos, torch.float32, "rope_cos"), _ptr(rope_sin, torch.float32, "rope_sin"),
                                  row_offset, _stream())
     _check(rc, "svi_rmsnorm_rope")

@@ -489,16 +489,17 @@ class WanDiTEngine:
         d, dev = self.dim, self.device
         n_txt = emb.shape[0] - n_img
         st = ContextState(n_img, n_txt, len(self.blocks), d, dev)
-        ss = torch.empty(len(self.blocks), 2, max(n_txt, 257), device=dev, dtype=torch.float32)
-        self.k.zero_(ss)
+        # row sums of squares of k as d/128 partials per row (stored, not accumulated: reproducible, nothing to zero)
+        P = d // 128
+        ss = torch.empty(2, max(n_txt, 257), 1, P, device=dev, dtype=torch.float32)
         for li, bw in enumerate(self.blocks):
             kv = st.kv_txt[li]
-            sl = ss[li, 0, :n_txt].unsqueeze(1)
+            sl = ss[0, :n_txt]
             self.k.gemm(emb[n_img:], bw.w_ckv, kv, bias=bw.b_ckv, sumsq=sl, sumsq_group_cols=d)
             self.k.rmsnorm_rope(kv[:, :d], sl, 0, bw.eps_qk, bw.cnk_q)       # K * rms * (w_k * w_q): see _BlockWeights
             if n_img:
                 kvi = st.kv_img[li]
-                si = ss[li, 1, :257].unsqueeze(1)
+                si = ss[1, :257]
                 self.k.gemm(emb[:257], bw.w_ckv_img, kvi, bias=bw.b_ckv_img, sumsq=si, sumsq_group_cols=d)
                 self.k.rmsnorm_rope(kvi[:, :d], si, 0, bw.eps_qk, bw.cnk_img_q)
         return st
@@ -538,15 +539,18 @@ class WanDiTEngine:
 
     # ------------------------------------------------------------------ block stack
     def _row_sums(self, L):
-        """f32 [layers, 3*L] accumulators of the GEMM epilogues' row sums of squares for one forward (per layer: q | k of
-        self-attention, q of cross-attention), zeroed by ONE memset node at the start of the forward."""
-        return self._buf("row_sums", (len(self.blocks), 3 * L), torch.float32)
+        """f32 [3 * L * d/128]: the GEMM epilogues' row sums of squares of one block (q | k of self-attention, q of
+        cross-attention) as d/128 partial sums per row — one per 128-column segment, STORED by the epilogue and added in
+        index order by the consumers, so a forward is bit-identical from run to run (with one atomically accumulated float
+        per row the order of the adds, and with it the last bit, changed between runs).  Reused by every block; never
+        zeroed."""
+        return self._buf("row_sums", (3 * L * (self.dim // 128),), torch.float32)
 
     def run_block(self, i, x, mods, ctx: ContextState, cos, sin, sp=None, audio: Optional[AudioState] = None, row_sums=None,
                   fold=None):
         """x f32 [L,d] updated in place.  Reference DiTBlock.forward wan_video_dit.py:354-374.  `mods`: TimeState.mods (or
-        any f32 [>= 6*(i+1), d] table whose rows 6i..6i+5 are this block's shift/scale/gate rows); `row_sums`: this
-        forward's zeroed _row_sums buffer (None: a private one is zeroed here — single-block callers).
+        any f32 [>= 6*(i+1), d] table whose rows 6i..6i+5 are this block's shift/scale/gate rows); `row_sums`: the
+        _row_sums scratch buffer (None: fetched here).
         `fold` (a _FoldRun): the three LayerNorms of the block are folded into the GEMMs around them — the buffer `h` then
         already holds bf16(x * g) written by the previous residual GEMM's epilogue (or the patch embedding), every residual
         GEMM of this block emits the next one, and no LayerNorm kernel runs."""
@@ -557,10 +561,8 @@ class WanDiTEngine:
         qkv = self._buf("qkv", (L, 3 * d), torch.bfloat16)
         att = self._buf("att", (L, d), torch.bfloat16)
         ffn = self._buf("ffn", (L, bw.w_f0.shape[0]), torch.bfloat16)
-        if row_sums is None:
-            row_sums = self._row_sums(L)
-            self.k.zero_(row_sums[i])
-        rs = row_sums[i]
+        rs = self._row_sums(L) if row_sums is None else row_sums
+        P = d // 128
         # --- self attention
         if fold is None:
             self.k.layernorm_modulate(x, h, bw.eps, scale=mod[1], shift=mod[0])
@@ -569,7 +571,7 @@ class WanDiTEngine:
             b_qkv, ln1 = fold.v.c1[i], (fold.stats[i, 0], fold.v.u1[i], d, bw.eps)
         ev = self.attn_events
         if sp is None:
-            ss = rs[:2 * L].view(L, 2)
+            ss = rs[:2 * L * P].view(L, 2, P)
             self.k.gemm(h, bw.w_qkv, qkv, bias=b_qkv, sumsq=ss, sumsq_group_cols=d, ln=ln1)
             self.k.qk_norm_rope(qkv[:, :2 * d], ss, bw.eps_qk, bw.nq, bw.nk, cos, sin, 0)
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
@@ -586,7 +588,7 @@ class WanDiTEngine:
             else:
                 kvf = self._buf("kv_full", (L * sp.sp_size, 2 * d), torch.bfloat16)
                 kvl = kvf[sp.sp_rank * L:(sp.sp_rank + 1) * L]
-            ssq, ssk = rs[:L].view(L, 1), rs[L:2 * L].view(L, 1)
+            ssq, ssk = rs[:L * P].view(L, 1, P), rs[L * P:2 * L * P].view(L, 1, P)
             self.k.gemm(h, bw.w_kv, kvl, bias=b_qkv[d:], sumsq=ssk, sumsq_group_cols=d,
                         ln=None if ln1 is None else (ln1[0], ln1[1][d:], d, bw.eps))
             self.k.rmsnorm_rope(kvl[:, :d], ssk, 0, bw.eps_qk, bw.nk, cos, sin, sp.sp_rank * L)
@@ -615,7 +617,7 @@ class WanDiTEngine:
         # --- cross attention: q stays un-normalised in memory; its RMS factor is applied inside the softmax and norm_q's
         #     weight already sits in the context K (context_state)
         cq = qkv[:, :d]
-        ss1 = rs[2 * L:].view(L, 1)
+        ss1 = rs[2 * L * P:].view(L, 1, P)
         if fold is None:
             self.k.layernorm_modulate(x, h, bw.eps, gamma=bw.n3w, beta=bw.n3b)
             self.k.gemm(h, bw.w_cq, cq, bias=bw.b_cq, sumsq=ss1, sumsq_group_cols=d)
@@ -777,7 +779,6 @@ class WanDiTEngine:
             tea_cache.update(xr)                      # skipped step: tokens + residual of the last computed step
         else:
             row_sums = self._row_sums(Ll)
-            self.k.zero_(row_sums)
             for i in range(nl):
                 self.run_block(i, xr, ts.mods, ctx, cos, sin, sp, audio, row_sums, fold)
             if tea_cache is not None:

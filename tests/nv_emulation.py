@@ -33,7 +33,14 @@ def gemm(a, w, out, bias=None, act=0, gate=None, residual=None, sumsq=None, sums
     if bias is not None:
         v = v + bias
     v = _act(v, act)
-    if sumsq is not None:                          # atomicAdd of the row sum of squares per column group
+    if sumsq is not None and sumsq.dim() == 3:     # [M, groups, parts]: one STORED partial per 128-column segment
+        assert sumsq.shape[2] * 128 == sumsq_group_cols
+        for g in range(sumsq.shape[1]):
+            for part in range(sumsq.shape[2]):
+                c0 = g * sumsq_group_cols + part * 128
+                cols = v[:, c0:c0 + 128]
+                sumsq[:, g, part] = (cols * cols).sum(dim=1)
+    elif sumsq is not None:                        # atomicAdd of the row sum of squares per column group
         for g in range(sumsq.shape[1]):
             cols = v[:, g * sumsq_group_cols:(g + 1) * sumsq_group_cols]
             if cols.numel():
@@ -84,10 +91,15 @@ def attention_workspace_bytes(Lq, Lk, num_heads):
     return 0
 
 
+def _group_sum(ss, g):
+    """row sums of squares of group g: [M, groups] or partials [M, groups, parts] added in index order"""
+    return ss[:, g] if ss.dim() == 2 else ss[:, g].sum(dim=1)
+
+
 def attention_qscale(q, k, v, out, num_heads, q_sumsq, q_dim, q_eps, scale=None, accumulate=False, workspace=None):
     hd = q.shape[1] // num_heads
     scale = hd ** -0.5 if scale is None else scale
-    rs = torch.rsqrt(q_sumsq[:, 0] / q_dim + q_eps).unsqueeze(1)
+    rs = torch.rsqrt(_group_sum(q_sumsq, 0) / q_dim + q_eps).unsqueeze(1)
     return attention((q.float() * rs), k, v, out, num_heads, scale, accumulate)     # the factor rides in fp32, q stays bf16
 
 
@@ -135,7 +147,7 @@ def layernorm_modulate(x, out, eps, gamma=None, beta=None, scale=None, shift=Non
 
 def rmsnorm_rope(t, sumsq, sumsq_col, eps, weight, rope_cos=None, rope_sin=None, row_offset=0):
     M, D = t.shape
-    rs = torch.rsqrt(sumsq[:, sumsq_col] / D + eps).unsqueeze(1)
+    rs = torch.rsqrt(_group_sum(sumsq, sumsq_col) / D + eps).unsqueeze(1)
     v = t.float() * rs * weight
     if rope_cos is not None:
         rows = torch.arange(M) + row_offset

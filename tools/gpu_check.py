@@ -285,6 +285,42 @@ def sec_abi3():
         report(f"attention_qscale vs attention(normalised q) Lq={Lq} Lk={Lk} H={Hh_}", out, out2, 2e-2)
         nv.attention_qscale(q, k, v, out, Hh_, ssq, Dq, 1e-6, scale, accumulate=True)
         report(f"attention_qscale accumulate Lq={Lq} Lk={Lk} H={Hh_}", out, ref.bfloat16().float() + ref, 3e-2)
+    # reproducible row sums of squares: the GEMM epilogue STORES one partial per 128-column segment ([M, groups, parts]); both GEMM
+    # kernels (M <= 128 single CTA, M > 128 CTA pairs); consumers add the partials in index order
+    for Mg in (100, 700):
+        Kk, gc, Ng = 256, 512, 3
+        a_ = torch.randn(Mg, Kk, generator=g).to(dev, torch.bfloat16)
+        w_ = (torch.randn(Ng * gc, Kk, generator=g) / 16).to(dev, torch.bfloat16)
+        b_ = torch.randn(Ng * gc, generator=g).to(dev) * 0.1
+        o_ = torch.empty(Mg, Ng * gc, device=dev, dtype=torch.bfloat16)
+        parts = torch.full((Mg, 2, gc // 128), float("nan"), device=dev)          # 2 of the 3 groups; garbage in: nothing is accumulated
+        nv.gemm(a_, w_, o_, bias=b_, sumsq=parts, sumsq_group_cols=gc)
+        vref = a_.float() @ w_.float().t() + b_
+        want = torch.stack([(vref[:, :gc] ** 2).sum(1), (vref[:, gc:2 * gc] ** 2).sum(1)], 1)
+        report(f"gemm sumsq partials M={Mg}: sum of the {gc // 128} partials per group", parts.sum(2), want, 2e-3)
+        first = parts.clone()
+        nv.gemm(a_, w_, o_, bias=b_, sumsq=parts, sumsq_group_cols=gc)
+        report(f"gemm sumsq partials M={Mg}: second run bit-identical", parts, first, 0.0)
+    # consumers on partials == consumers on the summed value
+    P = D // 128
+    ssp = (tf[:, :2 * D].reshape(t.shape[0], 2, P, 128) ** 2).sum(3).contiguous()
+    a2 = t.clone()
+    nv.qk_norm_rope(a2[:, :2 * D], ssp, 1e-6, wq, wk, cos, sin, row_offset=7)
+    report("qk_norm_rope on partial sums == on sums", a2, a, 1e-2)
+    a3 = t.clone()
+    nv.rmsnorm_rope(a3[:, D:2 * D], ssp, 1, 1e-6, wk, cos, sin, row_offset=7)
+    report("rmsnorm_rope on partial sums (group 1) == on sums", a3[:, D:2 * D], a[:, D:2 * D], 1e-2)
+    Lq, Lk, Hh_ = 700, 512, 2
+    Dq = Hh_ * 128
+    q = (torch.randn(Lq, Dq, generator=g) * 2.5).to(dev, torch.bfloat16)
+    k = torch.randn(Lk, Dq, generator=g).to(dev, torch.bfloat16)
+    v = torch.randn(Lk, Dq, generator=g).to(dev, torch.bfloat16)
+    qp = (q.float().view(Lq, 1, Hh_, 128) ** 2).sum(3).contiguous()
+    o_a = torch.empty(Lq, Dq, device=dev, dtype=torch.bfloat16)
+    o_b = torch.empty_like(o_a)
+    nv.attention_qscale(q, k, v, o_a, Hh_, qp, Dq, 1e-6, scale)
+    nv.attention_qscale(q, k, v, o_b, Hh_, qp.sum(2).contiguous(), Dq, 1e-6, scale)
+    report("attention_qscale on partial sums == on sums", o_a, o_b, 1e-2)
     # clip-boundary conversion: planar f32 video -> uint8 frames, bit-identical to the reference's numpy formula
     vid = (torch.rand(3, 5, 24, 40, generator=g) * 2.4 - 1.2).to(dev)
     u8 = torch.empty(5, 24, 40, 3, device=dev, dtype=torch.uint8)
