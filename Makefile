@@ -9,7 +9,7 @@ OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 
 all: $(LIB)
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/conv3d_common.cuh include/svi_b200.h
+build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/conv3d_common.cuh $(CSRC)/gemm_epilogue.cuh include/svi_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

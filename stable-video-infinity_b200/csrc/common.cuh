@@ -447,31 +447,6 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
          | (a_major << 15) | (b_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-// Row sums of squares of the epilogue value per column group (the full-width q / k RMS norms, wan_video_dit.py:150-151).
-// sumsq_parts == 0: atomicAdd into [M, groups] — the order of the adds varies from run to run, and with it the last bit of
-// the sums.  sumsq_parts == P > 0 (P = group_cols / 128): every 128-column segment STORES its partial sum into
-// [M, groups * P]; the consumers add a group's P partials in index order, so the result is bit-reproducible and the buffer
-// needs no zeroing.  `key` = the segment (or group) the running sum `ss` belongs to.
-template <class E>
-__device__ __forceinline__ void sumsq_flush(const E& ep, long long row, float ss, int key) {
-  if (key < 0) return;
-  if (ep.sumsq_parts) {
-    const int segs = ep.sumsq_groups * ep.sumsq_parts;
-    if (key < segs) ep.sumsq[row * segs + key] = ss;
-  } else if (key < ep.sumsq_groups) {
-    atomicAdd(&ep.sumsq[row * ep.sumsq_groups + key], ss);
-  }
-}
-template <class E>
-__device__ __forceinline__ void sumsq_step(const E& ep, int n0, long long row, float& ss, int& key) {
-  const int k = ep.sumsq_parts ? (n0 >> 7) : n0 / ep.sumsq_group_cols;
-  if (k != key) {
-    sumsq_flush(ep, row, ss, key);
-    ss = 0.f;
-    key = k;
-  }
-}
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -132,6 +132,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t targe
       "r"(target_rank)
       : "memory");
 }
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -143,11 +144,11 @@ struct Params {
   int nk_last;                  // K = 16 steps of the last channel chunk that hold real channels
 };
 
-// Register budget: 384 threads start with 168 registers; once the roles are fixed the TMA / MMA / idle warpgroup drops to 72
-// and the two epilogue warpgroups take 216 (2 * 216 + 72 = 3 * 168: setmaxnreg only redistributes what the CTA owns).  The
+// Register budget: 384 threads start with 168 registers; once the roles are fixed the TMA / MMA / idle warpgroup drops to 88
+// and the two epilogue warpgroups take 208 (2 * 208 + 88 = 3 * 168: setmaxnreg only redistributes what the CTA owns).  The
 // epilogue needs them to hold a pixel's whole fp32 residual (up to 128 channels per warp) from before the accumulator is
 // ready until the second pass.
-constexpr int EPI_REGS = 216, OTHER_REGS = 72;
+constexpr int EPI_REGS = 208, OTHER_REGS = 88;
 static_assert(2 * EPI_REGS + OTHER_REGS <= 3 * 168 && EPI_REGS % 8 == 0 && OTHER_REGS % 8 == 0, "register split");
 
 enum : uint32_t { FULL = 0, EMPTY = MAX_STAGES, TMEM_FULL = 2 * MAX_STAGES, TMEM_EMPTY = 2 * MAX_STAGES + 2, NUM_BARS = 2 * MAX_STAGES + 4 };
@@ -206,7 +207,10 @@ __device__ __forceinline__ void producer_role(const CUtensorMap* tmap_x, const C
 __device__ __forceinline__ void mma_role(const Params& pp, uint32_t sbase, uint32_t tmem_base, int pair, int num_pairs) {
   const svi::conv::Params& p = pp.c;
   const TileWalk tw(p);
-  const uint32_t idesc = make_idesc_bf16(2 * BM, p.BN, 0, 0);
+  // operands of the MMA asm block as provably warp-uniform values (a shuffle from lane 0): the descriptor arithmetic then runs
+  // in the uniform datapath and UTCHMMA takes its uniform registers directly instead of through R2UR moves
+  const uint32_t idesc = uniform(make_idesc_bf16(2 * BM, p.BN, 0, 0));
+  const uint32_t b_step = uniform((uint32_t)pp.b_bytes >> 4);
   constexpr uint32_t hi_kmaj = smem_desc_hi(1024, 2);  // SBO 1024 B, 128B swizzle, K-major
   int stage = 0;
   uint32_t phase = 0;
@@ -216,7 +220,7 @@ __device__ __forceinline__ void mma_role(const Params& pp, uint32_t sbase, uint3
   for (int tile = pair; tile < tw.num_tiles; tile += num_pairs) {
     mbar_wait_a(bar_addr(sbase, TMEM_EMPTY + acc), acc_phase ^ 1);
     tc_fence_after();
-    const uint32_t d_tmem = tmem_base + acc * MAX_BN;
+    const uint32_t d_tmem = uniform(tmem_base + acc * MAX_BN);
     uint32_t accumulate = 0;
     for (int g = 0; g < groups; ++g) {
       for (int cc = 0; cc < p.cin_chunks; ++cc) {
@@ -228,7 +232,7 @@ __device__ __forceinline__ void mma_role(const Params& pp, uint32_t sbase, uint3
         // absolute shared-memory address (TMA wrote the box into a 1024-byte aligned stage), so a start address that is not a
         // multiple of 8 rows needs nothing else: the descriptor's base-offset field stays 0 (measured on B200: with the row
         // phase in that field the results are wrong, profiles/r02_c6_pair_probe.log).  k_w == 3 (launch side).
-        mma2_stage(nk, d_tmem, smem_desc_lo(sa, 16), hi_kmaj, smem_desc_lo(sa + A_BYTES, 16), hi_kmaj, (uint32_t)pp.b_bytes >> 4,
+        mma2_stage(nk, d_tmem, uniform(smem_desc_lo(sa, 16)), hi_kmaj, uniform(smem_desc_lo(sa + A_BYTES, 16)), hi_kmaj, b_step,
                    idesc, accumulate);
         accumulate = 1;
         commit2_multicast(bar_addr(sbase, EMPTY + stage));
@@ -274,7 +278,7 @@ __device__ __forceinline__ void epilogue_role(const Params& pp, uint32_t sbase, 
     mbar_wait_a(bar_addr(sbase, TMEM_FULL + acc), acc_phase);
     tc_fence_after();
     const uint32_t t_base = tmem_base + acc * MAX_BN + half * cols_half + (static_cast<uint32_t>(quad * 32) << 16);
-    // pass 1: v = acc + bias + residual -> fp32 out, sum of squares
+    // pass 1: v = acc + bias + residual -> fp32 out, sum of squares; v replaces the residual in the registers
     float ssq = 0.f;
 #pragma unroll
     for (int c = 0; c < MAX_Q / 4; ++c) {           // 16 columns per step
@@ -288,29 +292,32 @@ __device__ __forceinline__ void epilogue_role(const Params& pp, uint32_t sbase, 
           for (int j4 = 0; j4 < 4; ++j4) {
             const int n = n0 + j4 * 4;
             if (n < p.C_out) {
-              float v[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j4 * 4 + j]);
+              float4 v = q[c * 4 + j4];
+              v.x += __uint_as_float(r[j4 * 4 + 0]); v.y += __uint_as_float(r[j4 * 4 + 1]);
+              v.z += __uint_as_float(r[j4 * 4 + 2]); v.w += __uint_as_float(r[j4 * 4 + 3]);
               if (p.bias) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
               }
-              const float4 qq = q[c * 4 + j4];
-              v[0] += qq.x; v[1] += qq.y; v[2] += qq.z; v[3] += qq.w;
-              ssq += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+              ssq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+              q[c * 4 + j4] = v;
               if (p.write_f32) {
                 float* dst;
                 if (p.n_split > 0 && n >= p.n_split)
                   dst = p.out + p.split_offset + (long long)t * p.out_frame_stride + pix * p.out_ld + (n - p.n_split);
                 else
                   dst = p.out + (long long)t * p.out_frame_stride + pix * p.out_ld + n;
-                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dst) = v;
               }
             }
           }
         }
       }
     }
+    // the accumulator is free from here on: the second pass works on the registers
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(bar_addr(sbase, TMEM_EMPTY + acc), 0);
     if (p.next_ring) {
       if (p.next_gamma) {       // the other half of the pixel's channel vector belongs to the partner warp of this quadrant
         float* sx = ssq_x + acc * 2 * BM;
@@ -318,51 +325,28 @@ __device__ __forceinline__ void epilogue_role(const Params& pp, uint32_t sbase, 
         named_bar_sync(1 + quad, 64);
         ssq = sx[row_in_tile] + sx[BM + row_in_tile];
       }
-      // pass 2 (accumulator still in TMEM, residual still in registers): RMS norm + SiLU -> bf16 into the next conv's ring
+      // pass 2: RMS norm + SiLU of v -> bf16 into the next conv's ring
       const float mul = p.next_gamma ? sqrtf((float)p.C_out) / fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
       __nv_bfloat16* nrow = p.next_ring + (long long)p.next_slot[t] * p.next_frame_stride + pix * p.next_ld;
+      if (ok) {
 #pragma unroll
-      for (int c = 0; c < MAX_Q / 4; ++c) {
-        const int n0 = col0 + c * 16;
-        if (c * 16 < cols_half && n0 < p.C_out) {
-          uint32_t r[16];
-          tmem_ld16(t_base + c * 16, r);
-          tmem_ld_wait();
-          if (ok) {
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const int n = n0 + j4 * 4;
-              if (n < p.C_out) {
-                float v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j4 * 4 + j]);
-                if (p.bias) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                  v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-                }
-                const float4 qq = q[c * 4 + j4];
-                v[0] += qq.x; v[1] += qq.y; v[2] += qq.z; v[3] += qq.w;
-                if (p.next_gamma) {
-                  const float4 g = __ldg(reinterpret_cast<const float4*>(p.next_gamma + n));
-                  v[0] *= mul * g.x; v[1] *= mul * g.y; v[2] *= mul * g.z; v[3] *= mul * g.w;
-                }
-                if (p.next_silu) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) v[j] = silu(v[j]);
-                }
-                uint2 pk;
-                pk.x = pack_bf16x2(v[0], v[1]);
-                pk.y = pack_bf16x2(v[2], v[3]);
-                *reinterpret_cast<uint2*>(nrow + n) = pk;
-              }
+        for (int j = 0; j < MAX_Q; ++j) {
+          const int n = col0 + j * 4;
+          if (j < n4 && n < p.C_out) {
+            float4 v = q[j];
+            if (p.next_gamma) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.next_gamma + n));
+              v.x *= mul * g.x; v.y *= mul * g.y; v.z *= mul * g.z; v.w *= mul * g.w;
             }
+            if (p.next_silu) { v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w); }
+            uint2 pk;
+            pk.x = pack_bf16x2(v.x, v.y);
+            pk.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(nrow + n) = pk;
           }
         }
       }
     }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_cluster(bar_addr(sbase, TMEM_EMPTY + acc), 0);
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
 }

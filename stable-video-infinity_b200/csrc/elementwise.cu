@@ -190,8 +190,18 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D, 
     const int c0 = cc - grp * D;                     // column inside the group
     // the group's sum of squares: one value (atomically accumulated) or `parts` partials added in index order (reproducible)
     const float* sp = sumsq + (long long)m * sumsq_ld + (long long)(sumsq_col + grp) * parts;
-    float ssum = sp[0];
-    for (int q = 1; q < parts; ++q) ssum += sp[q];
+    float ssum;
+    if ((parts & 3) == 0 && (sumsq_ld & 3) == 0) {      // 16-byte loads (d = 1536: 12 partials = 3 loads), same add order
+      float4 a = __ldg(reinterpret_cast<const float4*>(sp));
+      ssum = ((a.x + a.y) + a.z) + a.w;
+      for (int q = 4; q < parts; q += 4) {
+        a = __ldg(reinterpret_cast<const float4*>(sp + q));
+        ssum = (((ssum + a.x) + a.y) + a.z) + a.w;
+      }
+    } else {
+      ssum = sp[0];
+      for (int q = 1; q < parts; ++q) ssum += sp[q];
+    }
     const float rs = rsqrtf(ssum * inv_d + eps);
     uint4* ptr = reinterpret_cast<uint4*>(t + (long long)m * ldt + cc);
     const uint4 raw = *ptr;

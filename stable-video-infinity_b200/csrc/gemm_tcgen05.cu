@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "../../include/svi_b200.h"
+#include "gemm_epilogue.cuh"
 
 namespace svi {
 namespace gemm {
@@ -41,13 +42,6 @@ struct Epi {
   int sumsq_parts;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == SVI_ACT_GELU_TANH) return gelu_tanh(v);
-  if (act == SVI_ACT_SILU) return silu(v);
-  if (act == SVI_ACT_GELU_ERF) return gelu_erf(v);
-  if (act == SVI_ACT_RELU) return fmaxf(v, 0.f);
-  return v;
-}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -175,10 +169,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
               v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
-            if (ep.act != SVI_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
-            }
+            if (ep.act != SVI_ACT_NONE) apply_act8(v, ep.act);
             if (ep.sumsq) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
