@@ -46,3 +46,13 @@ attn_r1:
 clean:
 	rm -rf build $(LIB) $(EXP_LIB)
 .PHONY: all clean exp fastmath attn_variants attn_r1
+
+# A/B builds of the pair convolution kernel (SVI_B200_LIB=<lib> python tools/gpu_check.py perf_conv): u = uniform MMA operands,
+# e = epilogue that keeps the result in registers and frees the accumulator after the first pass
+CONV_OTHER := $(filter-out build/conv3d2_tcgen05.o,$(OBJS))
+conv_variants: $(OBJS)
+	for v in u0e1 u1e0 u0e0; do \
+	  u=$$(echo $$v | cut -c2); e=$$(echo $$v | cut -c4); \
+	  $(NVCC) $(NVFLAGS) -DSVI_CONV2_UNIFORM=$$u -DSVI_CONV2_EPI=$$e -c $(CSRC)/conv3d2_tcgen05.cu -o build/conv3d2_$$v.o && \
+	  $(NVCC) -shared -o $(PKG)/lib/libsvi_b200_conv_$$v.so $(CONV_OTHER) build/conv3d2_$$v.o -cudart shared || exit 1; \
+	done

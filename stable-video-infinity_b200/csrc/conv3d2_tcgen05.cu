@@ -132,7 +132,22 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t targe
       "r"(target_rank)
       : "memory");
 }
-__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+#ifndef SVI_CONV2_UNIFORM
+#define SVI_CONV2_UNIFORM 1     // MMA operands as shuffle-from-lane-0 values (uniform datapath); 0: plain registers (A/B: +1 % with 1)
+#endif
+#ifndef SVI_CONV2_EPI
+#define SVI_CONV2_EPI 0         // 0: the residual waits in registers, both epilogue passes read the accumulator; 1: the first pass leaves
+                                // the result in registers and frees the accumulator, the second works from registers.  Measured
+                                // (profiles/r02_c11_conv_variants.log, TF/s 0 / 1): C = 96 'mid' 881 / 793, 'end' 603 / 546; C = 192 'mid'
+                                // 1284 / 1330, 'end' 898 / 922; whole VAE decode 382.4 / 384.0 ms -> 0
+#endif
+__device__ __forceinline__ uint32_t uniform(uint32_t v) {
+#if SVI_CONV2_UNIFORM
+  return __shfl_sync(0xffffffffu, v, 0);
+#else
+  return v;
+#endif
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -278,6 +293,7 @@ __device__ __forceinline__ void epilogue_role(const Params& pp, uint32_t sbase, 
     mbar_wait_a(bar_addr(sbase, TMEM_FULL + acc), acc_phase);
     tc_fence_after();
     const uint32_t t_base = tmem_base + acc * MAX_BN + half * cols_half + (static_cast<uint32_t>(quad * 32) << 16);
+#if SVI_CONV2_EPI == 1
     // pass 1: v = acc + bias + residual -> fp32 out, sum of squares; v replaces the residual in the registers
     float ssq = 0.f;
 #pragma unroll
@@ -347,6 +363,97 @@ __device__ __forceinline__ void epilogue_role(const Params& pp, uint32_t sbase, 
         }
       }
     }
+#else   // A/B: residual in registers, both passes read the accumulator, released at the end of the tile
+    // pass 1: v = acc + bias + residual -> fp32 out, sum of squares
+    float ssq = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAX_Q / 4; ++c) {           // 16 columns per step
+      const int n0 = col0 + c * 16;
+      if (c * 16 < cols_half && n0 < p.C_out) {      // warp-uniform
+        uint32_t r[16];
+        tmem_ld16(t_base + c * 16, r);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int n = n0 + j4 * 4;
+            if (n < p.C_out) {
+              float v[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j4 * 4 + j]);
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+              }
+              const float4 qq = q[c * 4 + j4];
+              v[0] += qq.x; v[1] += qq.y; v[2] += qq.z; v[3] += qq.w;
+              ssq += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+              if (p.write_f32) {
+                float* dst;
+                if (p.n_split > 0 && n >= p.n_split)
+                  dst = p.out + p.split_offset + (long long)t * p.out_frame_stride + pix * p.out_ld + (n - p.n_split);
+                else
+                  dst = p.out + (long long)t * p.out_frame_stride + pix * p.out_ld + n;
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (p.next_ring) {
+      if (p.next_gamma) {       // the other half of the pixel's channel vector belongs to the partner warp of this quadrant
+        float* sx = ssq_x + acc * 2 * BM;
+        sx[half * BM + row_in_tile] = ssq;
+        named_bar_sync(1 + quad, 64);
+        ssq = sx[row_in_tile] + sx[BM + row_in_tile];
+      }
+      // pass 2 (accumulator still in TMEM, residual still in registers): RMS norm + SiLU -> bf16 into the next conv's ring
+      const float mul = p.next_gamma ? sqrtf((float)p.C_out) / fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+      __nv_bfloat16* nrow = p.next_ring + (long long)p.next_slot[t] * p.next_frame_stride + pix * p.next_ld;
+#pragma unroll
+      for (int c = 0; c < MAX_Q / 4; ++c) {
+        const int n0 = col0 + c * 16;
+        if (c * 16 < cols_half && n0 < p.C_out) {
+          uint32_t r[16];
+          tmem_ld16(t_base + c * 16, r);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const int n = n0 + j4 * 4;
+              if (n < p.C_out) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j4 * 4 + j]);
+                if (p.bias) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                  v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                }
+                const float4 qq = q[c * 4 + j4];
+                v[0] += qq.x; v[1] += qq.y; v[2] += qq.z; v[3] += qq.w;
+                if (p.next_gamma) {
+                  const float4 g = __ldg(reinterpret_cast<const float4*>(p.next_gamma + n));
+                  v[0] *= mul * g.x; v[1] *= mul * g.y; v[2] *= mul * g.z; v[3] *= mul * g.w;
+                }
+                if (p.next_silu) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) v[j] = silu(v[j]);
+                }
+                uint2 pk;
+                pk.x = pack_bf16x2(v[0], v[1]);
+                pk.y = pack_bf16x2(v[2], v[3]);
+                *reinterpret_cast<uint2*>(nrow + n) = pk;
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(bar_addr(sbase, TMEM_EMPTY + acc), 0);
+#endif
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
 }
