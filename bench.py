@@ -400,14 +400,16 @@ def main():
         out_host = torch.empty_like(lat_host).pin_memory()
         lat_h = lat_host.clone().pin_memory()
 
+        hbuf = [lat_h, out_host]      # this step's input / output host buffers; the output is the next step's input
+
         def e2e_step(i):
-            x = lat_h.to(dev, non_blocking=True)
+            x = hbuf[0].to(dev, non_blocking=True)
             cpx = eng.context_state(ctx_pos_host.to(dev, non_blocking=True), clip_dev) if own0 else None
             cnx = eng.context_state(ctx_neg_host.to(dev, non_blocking=True), clip_dev) if own1 else pipe.OTHER_RANK
             step(i, x=x, cpx=cpx, cnx=cnx)
-            out_host.copy_(x, non_blocking=True)
+            hbuf[1].copy_(x, non_blocking=True)
             torch.cuda.current_stream().synchronize()     # the caller consumes the host result every step
-            lat_h.copy_(out_host)
+            hbuf.reverse()
 
         # warm-up: every e2e step builds two fresh ContextStates (94 MB of K|V each); the engine keeps the last 8 alive, so the
         # caching allocator only stops calling cudaMalloc (~20 ms per block) once 9 have been built — 5 steps where a rank
@@ -418,11 +420,16 @@ def main():
         sync()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        step_wall = []
         for i in range(args.steps):
+            t_w = time.perf_counter()
             e2e_step(i)
+            step_wall.append(1e3 * (time.perf_counter() - t_w))
         b.record()
         sync()
         e2e_ms = a.elapsed_time(b) / args.steps
+        if rank == 0:
+            print("e2e step wall times (ms): " + " ".join(f"{t:.1f}" for t in step_wall), file=sys.stderr, flush=True)
         if world > 1:
             tt = torch.tensor([e2e_ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -439,7 +446,7 @@ def main():
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         t_h0 = time.perf_counter()
         evs[0].record()
-        xx = lat_h.to(dev, non_blocking=True)
+        xx = hbuf[0].to(dev, non_blocking=True)
         evs[1].record()
         prof = None
         if os.environ.get("SVI_BENCH_PROFILE") == "1":
@@ -456,7 +463,7 @@ def main():
         evs[2].record()
         step(0, x=xx, cpx=cpx, cnx=cnx)
         evs[3].record()
-        out_host.copy_(xx, non_blocking=True)
+        hbuf[1].copy_(xx, non_blocking=True)
         evs[4].record()
         torch.cuda.synchronize()
         if rank == 0:

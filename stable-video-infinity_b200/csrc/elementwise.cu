@@ -182,6 +182,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D, 
   const int vec_per_row = (D >> 3) * groups;
   const long long total = (long long)M * vec_per_row;
   const float inv_d = 1.0f / (float)D;
+  const bool warp_row = ((D >> 3) & 31) == 0;       // a warp's 32 x 8 columns never straddle a row or a group (D % 256 == 0)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / vec_per_row);
@@ -191,7 +192,16 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D, 
     // the group's sum of squares: one value (atomically accumulated) or `parts` partials added in index order (reproducible)
     const float* sp = sumsq + (long long)m * sumsq_ld + (long long)(sumsq_col + grp) * parts;
     float ssum;
-    if ((parts & 3) == 0 && (sumsq_ld & 3) == 0) {      // 16-byte loads (d = 1536: 12 partials = 3 loads), same add order
+    if (parts > 1 && warp_row) {
+      // every lane of this warp works on the same (row, group): the partials are read once per warp (lane q takes partials q,
+      // q + 32, ...) and added by a butterfly — commutative at every level, so all lanes hold the same bits, and the tree is
+      // fixed, so the sum is reproducible.  (Every thread summing all partials itself made the pass L1-bound: 101 -> 133 us.)
+      float a = 0.f;
+      for (int q = threadIdx.x & 31; q < parts; q += 32) a += __ldg(sp + q);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      ssum = a;
+    } else if ((parts & 3) == 0 && (sumsq_ld & 3) == 0) {      // 16-byte loads, index order
       float4 a = __ldg(reinterpret_cast<const float4*>(sp));
       ssum = ((a.x + a.y) + a.z) + a.w;
       for (int q = 4; q < parts; q += 4) {

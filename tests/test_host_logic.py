@@ -412,3 +412,32 @@ def test_streaming_video_writer_appends_clips(tmp_path):
     if os.path.isdir(out):
         vals = [int(np.array(Image.open(os.path.join(out, f"{i}.png")))[0, 0, 0]) for i in range(5)]
         assert vals == [1, 2, 3, 4, 5]
+
+
+def test_ctypes_mirrors_match_the_c_struct_layouts(tmp_path):
+    """The two descriptor structs of the C ABI (svi_gemm_epilogue, svi_conv_desc) are mirrored by hand in _native.py: compile a
+    probe against include/svi_b200.h with the C compiler and compare sizeof / offsetof of every field with ctypes."""
+    import ctypes
+    import subprocess
+    from diffsynth import _native as nv
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"svi_gemm_epilogue": nv.GemmEpilogue, "svi_conv_desc": nv.ConvDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "svi_b200.h"', 'int main(void) {']
+    for cname, mirror in structs.items():
+        lines.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for line in filter(None, out):
+        cname, fname, val = line.split()
+        mirror = structs[cname]
+        want = ctypes.sizeof(mirror) if fname == "sizeof" else getattr(mirror, fname).offset
+        assert int(val) == want, (cname, fname, int(val), want)
+        seen += 1
+    assert seen == sum(len(m._fields_) + 1 for m in structs.values())

@@ -310,6 +310,24 @@ def sec_abi3():
     a3 = t.clone()
     nv.rmsnorm_rope(a3[:, D:2 * D], ssp, 1, 1e-6, wk, cos, sin, row_offset=7)
     report("rmsnorm_rope on partial sums (group 1) == on sums", a3[:, D:2 * D], a[:, D:2 * D], 1e-2)
+    # D % 256 == 0: the kernel's warp-cooperative reduction of the partials (a warp's 256 columns lie in one row and group)
+    for Hw in (2, 12, 40):
+        Dw = Hw * 128
+        tw_ = torch.randn(301, 3 * Dw, generator=g).to(dev, torch.bfloat16)
+        sw = (tw_.float()[:, :2 * Dw].reshape(301, 2, Hw, 128) ** 2).sum(3).contiguous()
+        wqw = (torch.randn(Dw, generator=g) * 0.2 + 1).to(dev)
+        wkw = (torch.randn(Dw, generator=g) * 0.2 + 1).to(dev)
+        angw = torch.rand(301 + 5, 64, generator=g, dtype=torch.float64) * 6.28
+        cw, sn_ = angw.cos().float().to(dev), angw.sin().float().to(dev)
+        x1, x2, x3 = tw_.clone(), tw_.clone(), tw_.clone()
+        nv.qk_norm_rope(x1[:, :2 * Dw], sw, 1e-6, wqw, wkw, cw, sn_, row_offset=5)
+        nv.qk_norm_rope(x2[:, :2 * Dw], sw.sum(2).contiguous(), 1e-6, wqw, wkw, cw, sn_, row_offset=5)
+        report(f"qk_norm_rope D={Dw}: partial sums (warp reduction) == sums", x1, x2, 1e-2)
+        nv.rmsnorm_rope(x3[:, Dw:2 * Dw], sw, 1, 1e-6, wkw, cw, sn_, row_offset=5)
+        report(f"rmsnorm_rope D={Dw}: group 1 of the partials == qk_norm_rope's k", x3[:, Dw:2 * Dw], x1[:, Dw:2 * Dw], 0.0)
+        x4 = tw_.clone()
+        nv.qk_norm_rope(x4[:, :2 * Dw], sw, 1e-6, wqw, wkw, cw, sn_, row_offset=5)
+        report(f"qk_norm_rope D={Dw}: second run bit-identical", x4, x1, 0.0)
     Lq, Lk, Hh_ = 700, 512, 2
     Dq = Hh_ * 128
     q = (torch.randn(Lq, Dq, generator=g) * 2.5).to(dev, torch.bfloat16)
