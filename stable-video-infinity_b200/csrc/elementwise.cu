@@ -189,6 +189,13 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D, 
     const int cc = (int)(i % vec_per_row) * 8;      // column inside the row (both groups)
     const int grp = cc >= D ? 1 : 0;
     const int c0 = cc - grp * D;                     // column inside the group
+    // this thread's 8 values and weights first: the loads below them in program order would otherwise wait behind the
+    // partial-sum loads and the shuffles (two serialized memory latencies per thread: 101 -> 131 us at L = 32760)
+    uint4* ptr = reinterpret_cast<uint4*>(t + (long long)m * ldt + cc);
+    const uint4 raw = *ptr;
+    const float* wg = grp ? w2 : w;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wg + c0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wg + c0 + 4));
     // the group's sum of squares: one value (atomically accumulated) or `parts` partials added in index order (reproducible)
     const float* sp = sumsq + (long long)m * sumsq_ld + (long long)(sumsq_col + grp) * parts;
     float ssum;
@@ -213,12 +220,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ t, long long ldt, int M, int D, 
       for (int q = 1; q < parts; ++q) ssum += sp[q];
     }
     const float rs = rsqrtf(ssum * inv_d + eps);
-    uint4* ptr = reinterpret_cast<uint4*>(t + (long long)m * ldt + cc);
-    const uint4 raw = *ptr;
     const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-    const float* wg = grp ? w2 : w;
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wg + c0));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wg + c0 + 4));
     float v[8];
     {
       const float2 a = __bfloat1622float2(b2[0]), b = __bfloat1622float2(b2[1]),

@@ -583,6 +583,11 @@ def sec_perf_ew():
     sin = torch.randn(L, 64, generator=g).to(dev)
     for cold in (False, True):
         timed(lambda: nv.rmsnorm_rope(qkv[:, :d], ss, 0, 1e-6, w, cos, sin, 0), L * d * 4, "rmsnorm_rope (q slice of qkv)", cold)
+    ssp = (torch.rand(L, 2, d // 128, generator=g) * 128).to(dev)
+    w2 = torch.randn(d, generator=g).to(dev)
+    for cold in (False, True):
+        timed(lambda: nv.qk_norm_rope(qkv[:, :2 * d], ss, 1e-6, w, w2, cos, sin, 0), L * d * 8, "qk_norm_rope, one sum per row and group", cold)
+        timed(lambda: nv.qk_norm_rope(qkv[:, :2 * d], ssp, 1e-6, w, w2, cos, sin, 0), L * d * 8, "qk_norm_rope, 12 partial sums per row and group", cold)
 
 
 def sec_perf_attn_quick():
