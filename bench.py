@@ -358,6 +358,13 @@ def main():
             del xb, c0, c1
         sync()
 
+    # the models are built: move every live Python object to the permanent generation so that a cyclic-GC pass triggered inside a
+    # timed loop has (almost) nothing to traverse.  A full collection over the module trees is a host stall of tens of ms that the
+    # e2e leg (one synchronisation per step) cannot hide; whether that is what made one e2e step in three 22 ms longer
+    # (profiles/r02_f2_e2e_steps.txt) was not measured — this is hygiene, the per-step wall times stay on stderr
+    import gc
+    gc.collect()
+    gc.freeze()
     for i in range(args.warmup):
         step(i)
     sync()

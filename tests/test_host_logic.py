@@ -441,3 +441,30 @@ def test_ctypes_mirrors_match_the_c_struct_layouts(tmp_path):
         assert int(val) == want, (cname, fname, int(val), want)
         seen += 1
     assert seen == sum(len(m._fields_) + 1 for m in structs.values())
+
+
+def test_conv_kernel_choice_is_validated_before_anything_touches_the_gpu():
+    """svi_conv_desc.variant (include/svi_b200.h): 2 = the CTA-pair kernel, which needs k_w = 3 and pad_w = 1; anything outside 0..2 is
+    refused.  The checks run before any tensor map / launch, so the error path is testable without a GPU."""
+    from diffsynth import _native as nv
+    lib = nv.load()
+
+    def desc(kw, pad, variant):
+        d = nv.ConvDesc()
+        d.x_ring, d.w_packed, d.out = 0x1000, 0x2000, 0x3000          # never dereferenced: validation fails first
+        d.ring_slots, d.in_H, d.in_W, d.C_in = 4, 8, 256, 64
+        d.w_rows, d.w_ld = 96, 3 * 3 * kw * 64
+        d.kt, d.kh, d.kw, d.pad_h, d.pad_w = 3, 3, kw, 1, pad
+        d.H, d.W, d.T = 8, 256, 1
+        for a in range(3):
+            d.slot[a] = a
+        d.C_out, d.tile_w, d.out_ld, d.out_frame_stride = 96, 16, 96, 8 * 256 * 96
+        d.variant = variant
+        return d
+
+    import ctypes
+    for kw, pad, variant, needle in [(1, 0, 2, "variant 2 needs"), (3, 1, 7, "variant must be"), (3, 0, 2, "variant 2 needs")]:
+        d = desc(kw, pad, variant)
+        rc = lib.svi_conv3d_causal(ctypes.byref(d), None)
+        assert rc != 0
+        assert needle in lib.svi_last_error().decode(), lib.svi_last_error().decode()
