@@ -657,7 +657,7 @@ class SpatialShard:
         pad = torch.zeros(mx, C, device=local.device, dtype=local.dtype)
         pad[:local.shape[0]] = local
         parts = torch.empty(self.world, mx, C, device=local.device, dtype=local.dtype)
-        dist.all_gather_into_tensor(parts, pad, group=self.group)
+        dist.all_gather_into_tensor(parts.view(self.world * mx, C), pad, group=self.group)     # concatenated form: NCCL and gloo
         off = 0
         for r in range(self.world):
             full[off:off + counts[r]] = parts[r, :counts[r]]
@@ -674,7 +674,7 @@ class SpatialShard:
         pad = torch.zeros(shape, device=t.device, dtype=t.dtype)
         pad.narrow(dim, 0, t.shape[dim]).copy_(t)
         parts = torch.empty([self.world] + shape, device=t.device, dtype=t.dtype)
-        dist.all_gather_into_tensor(parts, pad.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(parts.view([self.world * shape[0]] + shape[1:]), pad.contiguous(), group=self.group)
         return torch.cat([parts[r].narrow(dim, 0, rows[r]) for r in range(self.world)], dim=dim)
 
 

@@ -24,7 +24,7 @@ def _act(v, act):
 
 
 def gemm(a, w, out, bias=None, act=0, gate=None, residual=None, sumsq=None, sumsq_group_cols=0, ln=None, emit=None):
-    v = a.float() @ w.float().T
+    v = (a.double() @ w.double().T).float()      # fp64 accumulation, rounded once: independent of the row count / blocking
     if ln is not None:                             # LayerNorm folded into the GEMM: r (acc - mu u), then + c (= bias)
         stats, u, dim, eps = ln
         mean = stats[:, 0:1] / dim
@@ -205,9 +205,124 @@ def axpby(a, alpha, b, beta, out):
     return out
 
 
+# ---------------------------------------------------------------------------------------------- VAE kernels
+def vae_norm_act(x, n_pix, C, ldx, gamma, silu, out, Cpad):
+    v = torch.as_strided(x, (n_pix, C), (ldx, 1)).float()
+    if gamma is not None:
+        v = v / v.norm(dim=1, keepdim=True).clamp_min(1e-12) * (C ** 0.5) * gamma
+    if silu:
+        v = F.silu(v)
+    o = out.reshape(-1, Cpad)[:n_pix]            # `out` is contiguous and may have more rows than n_pix (padded work buffers)
+    o[:, :C] = v.to(o.dtype)
+    o[:, C:] = 0
+    return out
+
+
+def vae_upsample2x(x, H, W, C, out):
+    out.copy_(x.repeat_interleave(2, 0).repeat_interleave(2, 1).to(out.dtype))
+    return out
+
+
+def vae_space_to_depth(x, H, W, C, out):
+    # y[h, w, (dy*2 + dx)*C + c] = x[2h+dy, 2w+dx, c]
+    out.copy_(x.view(H // 2, 2, W // 2, 2, C).permute(0, 2, 1, 3, 4).reshape(H // 2, W // 2, 4 * C).to(out.dtype))
+    return out
+
+
+def vae_from_planar(x, C, n_pix, scale, shift, out, ldo, out_is_bf16, ldc=None):
+    v = x.reshape(C, n_pix).t().float()
+    if scale is not None:
+        v = v * scale
+    if shift is not None:
+        v = v + shift
+    o = out.view(n_pix, ldo)
+    o[:, :C] = v.to(o.dtype)
+    o[:, C:] = 0
+    return out
+
+
+def vae_to_planar(x, ldx, C, n_pix, pre_shift, scale, clamp, out, ldc=None):
+    v = x[:, :C].float()
+    if pre_shift is not None:
+        v = v + pre_shift
+    if scale is not None:
+        v = v * scale
+    if clamp:
+        v = v.clamp(-1, 1)
+    out.view(C, n_pix).copy_(v.t())
+    return out
+
+
+def softmax_rows(s, N, scale, p):
+    p.zero_()
+    p[:, :N] = torch.softmax(s[:, :N].float() * scale, dim=1).to(p.dtype)
+    return p
+
+
+def _mem(ptr, n, dtype):
+    """n elements of `dtype` at the raw (host) address `ptr` as a tensor sharing that memory: the conv descriptor carries
+    pointers, exactly as the C ABI receives them."""
+    import ctypes
+    size = {torch.float32: 4, torch.bfloat16: 2}[dtype]
+    buf = (ctypes.c_char * (n * size)).from_address(ptr)
+    return torch.frombuffer(buf, dtype=dtype)
+
+
+def conv3d_causal(d):
+    """svi_conv3d_causal on host memory (include/svi_b200.h): implicit GEMM over the frame ring with the (output frame, k_t) ->
+    slot table, zero fill outside the ring frame (TMA out-of-bounds), bias / residual / channel->frame split, and the fused
+    producer of the next conv's input (RMS norm + SiLU -> bf16 ring)."""
+    kt, kh, kw, H, W, T = d.kt, d.kh, d.kw, d.H, d.W, d.T
+    Ci, Co = d.C_in, d.C_out
+    cpad = (Ci + 63) // 64 * 64
+    ring = _mem(d.x_ring, d.ring_slots * d.in_H * d.in_W * Ci, torch.bfloat16).view(d.ring_slots, d.in_H, d.in_W, Ci)
+    wp = _mem(d.w_packed, d.w_rows * d.w_ld, torch.bfloat16).view(d.w_rows, d.w_ld)[:Co, :kt * kh * kw * cpad]
+    w = wp.float().view(Co, kt, kh, kw, cpad)[..., :Ci].permute(0, 4, 1, 2, 3).contiguous()       # [Co, Ci, kt, kh, kw]
+    bias = _mem(d.bias, Co, torch.float32) if d.bias else None
+    gamma = _mem(d.next_gamma, Co, torch.float32) if d.next_gamma else None
+    write_f32 = d.write_f32 if d.next_ring else 1
+    for t in range(T):
+        # input window: rows h + b - pad_h, columns w + c - pad_w; zero where that leaves the ring frame
+        x = torch.zeros(kt, H + kh - 1, W + kw - 1, Ci)
+        for a in range(kt):
+            fr = ring[d.slot[t * 3 + a]].float()
+            for i in range(H + kh - 1):
+                si = i - d.pad_h
+                if 0 <= si < d.in_H:
+                    j0, j1 = max(0, d.pad_w), min(W + kw - 1, d.in_W + d.pad_w)
+                    x[a, i, j0:j1] = fr[si, j0 - d.pad_w:j1 - d.pad_w]
+        # fp64 accumulation, rounded once: the value of a pixel must not depend on how the CPU library blocks a frame of this size
+        # (a band of rows vs the whole frame under spatial sharding), as it does not on the GPU
+        v = F.conv3d(x.double().permute(3, 0, 1, 2).unsqueeze(0), w.double())[0, :, 0].permute(1, 2, 0).float()   # [H, W, Co]
+        if bias is not None:
+            v = v + bias
+        if d.residual:
+            res = _mem(d.residual + 4 * t * d.res_frame_stride, H * W * d.res_ld, torch.float32).view(H, W, d.res_ld)
+            v = v + res[..., :Co]
+        if write_f32:
+            if d.n_split > 0:
+                o0 = _mem(d.out + 4 * t * d.out_frame_stride, H * W * d.out_ld, torch.float32).view(H, W, d.out_ld)
+                o1 = _mem(d.out + 4 * (d.split_offset + t * d.out_frame_stride), H * W * d.out_ld, torch.float32).view(H, W, d.out_ld)
+                o0[..., :d.n_split] = v[..., :d.n_split]
+                o1[..., :Co - d.n_split] = v[..., d.n_split:]
+            else:
+                o = _mem(d.out + 4 * t * d.out_frame_stride, H * W * d.out_ld, torch.float32).view(H, W, d.out_ld)
+                o[..., :Co] = v
+        if d.next_ring:
+            y = v
+            if gamma is not None:
+                y = y / y.norm(dim=2, keepdim=True).clamp_min(1e-12) * (Co ** 0.5) * gamma
+            if d.next_silu:
+                y = F.silu(y)
+            nr = _mem(d.next_ring + 2 * d.next_slot[t] * d.next_frame_stride, H * W * d.next_ld, torch.bfloat16).view(H, W, d.next_ld)
+            nr[..., :Co] = y.to(torch.bfloat16)
+    return 0
+
+
 _NAMES = ("gemm", "attention", "attention_workspace_bytes", "attention_qscale", "layernorm_modulate", "layernorm_modulate_split",
           "rmsnorm_rope", "qk_norm_rope", "patchify_gather", "unpatchify", "cfg_euler_step", "cast_f32_to_bf16",
-          "cast_bf16_to_f32", "split_f32_to_bf16x2", "zero_", "add_rows", "axpby", "ln_fold_prepare", "ln_fold_combine")
+          "cast_bf16_to_f32", "split_f32_to_bf16x2", "zero_", "add_rows", "axpby", "ln_fold_prepare", "ln_fold_combine",
+          "vae_norm_act", "vae_upsample2x", "vae_space_to_depth", "vae_from_planar", "vae_to_planar", "softmax_rows", "conv3d_causal")
 
 
 def install(monkeypatch=None):
