@@ -147,3 +147,24 @@ def test_sequence_and_cfg_parallel_plan_two_ranks():
         assert len(res) == 7, res                     # 2 models x (sp2 forward, sp2 step, cfg2 step) + talk sp2 forward
         for name, err in res.items():
             assert err < 2e-2, (rank, name, err)
+
+
+def test_sequence_and_cfg_parallel_plan_four_ranks():
+    """world_size 4 over gloo: the plan the public pipeline installs on 4 GPUs — two guidance branches x 2-way token split
+    (cfg2 x sp2: two K|V groups, velocity exchange between the branch groups) — and the pure 4-way token split, against the
+    single-process result on every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 150)
+    procs = [ctx.Process(target=_sp_worker, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in range(4)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in got:
+        # 2 models x (sp4 forward, sp4 step, cfg2xsp2 forward, cfg2xsp2 step) + talk sp4 forward
+        assert len(res) == 9, res
+        for name, err in res.items():
+            assert err < 2e-2, (rank, name, err)

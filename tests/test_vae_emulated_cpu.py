@@ -66,7 +66,8 @@ def _shard_worker(rank, world, port, q):
     try:
         res = {}
         m, _ = _vae()
-        # (frames, H, W): 6 latent rows = 3 + 3, and 5 latent rows = 2 + 3 (uneven bands; odd band heights at every level)
+        # (frames, H, W): 6 latent rows = 3 + 3 (or 1 + 2 + 1 + 2 over 4 ranks), 5 latent rows = 2 + 3 (or 1 + 1 + 1 + 2): uneven bands,
+        # odd band heights at every level
         for T, H, W in ((5, 48, 32), (5, 40, 48)):
             g = torch.Generator().manual_seed(T + H)
             video = torch.rand(3, T, H, W, generator=g) * 2 - 1
@@ -88,18 +89,19 @@ def _shard_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_spatially_sharded_vae_two_ranks():
-    """world_size 2 over gloo: every rank encodes / decodes its band of image rows — one border row exchanged with the neighbour
+@pytest.mark.parametrize("world", [2, 4])
+def test_spatially_sharded_vae(world):
+    """world_size 2 and 4 over gloo (4: bands of ONE latent row, whose 3x3 convolutions read nothing but halo rows above and below): every rank encodes / decodes its band of image rows — one border row exchanged with the neighbour
     per convolution input, the attention block's tokens gathered, the result bands gathered on every rank — and must reproduce
     the single-process result exactly, as the GPU kernels do (tools/vae_shard_check.py): the stand-in kernels accumulate in fp64
     and round once, so a pixel's value does not depend on how the CPU library blocks a band vs a whole frame."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29900 + (os.getpid() % 90)
-    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29900 + (os.getpid() % 90) + world
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=600) for _ in range(2)]
+    got = [q.get(timeout=900) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
