@@ -229,6 +229,10 @@ def vae_space_to_depth(x, H, W, C, out):
     return out
 
 
+def vae_space_to_depth_act(x, H, W, C, act, out):
+    return vae_space_to_depth(_act(x.float(), act), H, W, C, out)
+
+
 def vae_from_planar(x, C, n_pix, scale, shift, out, ldo, out_is_bf16, ldc=None):
     v = x.reshape(C, n_pix).t().float()
     if scale is not None:
@@ -322,7 +326,7 @@ def conv3d_causal(d):
 _NAMES = ("gemm", "attention", "attention_workspace_bytes", "attention_qscale", "layernorm_modulate", "layernorm_modulate_split",
           "rmsnorm_rope", "qk_norm_rope", "patchify_gather", "unpatchify", "cfg_euler_step", "cast_f32_to_bf16",
           "cast_bf16_to_f32", "split_f32_to_bf16x2", "zero_", "add_rows", "axpby", "ln_fold_prepare", "ln_fold_combine",
-          "vae_norm_act", "vae_upsample2x", "vae_space_to_depth", "vae_from_planar", "vae_to_planar", "softmax_rows", "conv3d_causal")
+          "vae_norm_act", "vae_upsample2x", "vae_space_to_depth", "vae_space_to_depth_act", "vae_from_planar", "vae_to_planar", "softmax_rows", "conv3d_causal")
 
 
 def install(monkeypatch=None):

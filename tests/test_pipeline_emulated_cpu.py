@@ -38,6 +38,35 @@ def _build(device="cpu", use_usp=False):
     return pipe, cfg, dit_sd, vae_sd
 
 
+def _build_dance(use_usp=False):
+    import test_dance_gpu as D
+    import test_pipeline_gpu as P
+    from diffsynth import ModelManager, SVIDanceVideoPipeline
+    from diffsynth.models.wan_video_dit import WanModel
+    from diffsynth.models.wan_video_vae import WanVideoVAE
+    cfg = synth.CFG_TINY_I2V
+    dit = WanModel(**cfg).eval()
+    dit.load_state_dict({k: v.to(torch.bfloat16).float() for k, v in synth.make_dit_state_dict(cfg, seed=2).items()})
+    vae = WanVideoVAE().eval()
+    vae.load_state_dict({k: v.to(torch.bfloat16).float() for k, v in synth_vae.make_vae_state_dict(seed=0).items()})
+    mm = ModelManager(torch_dtype=torch.bfloat16, device="cpu")
+    mm.add_model("wan_video_dit", dit)
+    mm.add_model("wan_video_vae", vae)
+    mm.state_dict_new_module = {"pipe.dwpose_embedding." + k: v for k, v in D._stem_sd(cfg["dim"], seed=7).items()}
+    pipe = SVIDanceVideoPipeline.from_model_manager(mm, torch_dtype=torch.bfloat16, device="cpu", is_test=True, use_usp=use_usp)
+    pipe.prompter = P._prompter
+    pipe.image_encoder = P._ClipStub()
+    return pipe
+
+
+def _call_dance(pipe, img, seed):
+    import test_dance_gpu as D
+    args = types.SimpleNamespace(ref_pad_cfg=False, ref_pad_num=-1, sequential_cfg="none")
+    return pipe(prompt="p", negative_prompt="n", input_image=img, num_inference_steps=STEPS, cfg_scale={"text": 5.0}, seed=seed,
+                tiled=False, random_ref_frame=torch.from_numpy(np.array(img)), height=H, width=W, num_frames=FRAMES,
+                humanpose_data=D._pose(FRAMES, H, W, seed=3), cond_wo_pose=False, args=args, progress_bar_cmd=lambda x: x)
+
+
 def _call(pipe, img, seed):
     args = types.SimpleNamespace(ref_pad_cfg=False, ref_pad_num=-1, sequential_cfg="none")
     return pipe(prompt="p", negative_prompt="n", input_image=img, num_inference_steps=STEPS, cfg_scale={"text": 5.0}, seed=seed,
@@ -84,7 +113,13 @@ def _usp_worker(rank, world, port, q):
         plan = pipe.sp_group().describe() if hasattr(pipe, "sp_group") and pipe.sp_group() is not None else "none"
         got = np.stack([np.array(f) for f in _call(pipe, img, seed=7)]).astype(np.int32)
         eng = pipe.vae.engine("cpu")
-        q.put((rank, {"plan": plan, "max_diff": int(np.abs(got - ref).max()), "halo_exchanges": eng.halo_exchanges}))
+        res = {"plan": plan, "max_diff": int(np.abs(got - ref).max()), "halo_exchanges": eng.halo_exchanges}
+        # SVI-Dance: the pose condition (add_condition rows) must follow the token split of the plan
+        dref = np.stack([np.array(f) for f in _call_dance(_build_dance(), img, seed=9)]).astype(np.int32)
+        dgot = np.stack([np.array(f) for f in _call_dance(_build_dance(use_usp=True), img, seed=9)]).astype(np.int32)
+        res["dance_max_diff"] = int(np.abs(dgot - dref).max())
+        res["dance_differs_from_svi"] = bool(np.abs(dref - ref).max() > 0)
+        q.put((rank, res))
     except Exception as ex:  # noqa: BLE001
         import traceback
         q.put((rank, {"error": traceback.format_exc()[-2500:] + repr(ex)}))
@@ -112,3 +147,4 @@ def test_pipeline_call_with_use_usp(world):
         assert res["plan"].startswith("cfg2"), res
         assert res["halo_exchanges"] > 0, res                 # the VAE really ran on row bands
         assert res["max_diff"] <= 1, res                      # bf16 re-rounding of a token-split forward may flip a grey level
+        assert res["dance_max_diff"] <= 1 and res["dance_differs_from_svi"], res
