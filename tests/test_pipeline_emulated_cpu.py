@@ -67,11 +67,11 @@ def _call_dance(pipe, img, seed):
                 humanpose_data=D._pose(FRAMES, H, W, seed=3), cond_wo_pose=False, args=args, progress_bar_cmd=lambda x: x)
 
 
-def _call(pipe, img, seed):
+def _call(pipe, img, seed, steps=STEPS, **extra):
     args = types.SimpleNamespace(ref_pad_cfg=False, ref_pad_num=-1, sequential_cfg="none")
-    return pipe(prompt="p", negative_prompt="n", input_image=img, num_inference_steps=STEPS, cfg_scale={"text": 5.0}, seed=seed,
+    return pipe(prompt="p", negative_prompt="n", input_image=img, num_inference_steps=steps, cfg_scale={"text": 5.0}, seed=seed,
                 tiled=False, random_ref_frame=torch.from_numpy(np.array(img)), height=H, width=W, num_frames=FRAMES,
-                args=args, progress_bar_cmd=lambda x: x)
+                args=args, progress_bar_cmd=lambda x: x, **extra)
 
 
 def _image():
@@ -119,6 +119,15 @@ def _usp_worker(rank, world, port, q):
         dgot = np.stack([np.array(f) for f in _call_dance(_build_dance(use_usp=True), img, seed=9)]).astype(np.int32)
         res["dance_max_diff"] = int(np.abs(dgot - dref).max())
         res["dance_differs_from_svi"] = bool(np.abs(dref - ref).max() > 0)
+        # TeaCache under the plan: every rank must take the same skip decisions (they depend on the timestep embedding only) and
+        # keep its own rows' residual
+        tea = dict(steps=8, tea_cache_l1_thresh=22000.0, tea_cache_model_id="Wan2.1-I2V-14B-720P")   # random weights: a threshold that skips
+        single = _build()[0]
+        tref = np.stack([np.array(f) for f in _call(single, img, seed=11, **tea)]).astype(np.int32)
+        tgot = np.stack([np.array(f) for f in _call(pipe, img, seed=11, **tea)]).astype(np.int32)
+        plain = np.stack([np.array(f) for f in _call(single, img, seed=11, steps=8)]).astype(np.int32)
+        res["tea_max_diff"] = int(np.abs(tgot - tref).max())
+        res["tea_skips_steps"] = bool(np.abs(tref - plain).max() > 0)
         q.put((rank, res))
     except Exception as ex:  # noqa: BLE001
         import traceback
@@ -148,3 +157,4 @@ def test_pipeline_call_with_use_usp(world):
         assert res["halo_exchanges"] > 0, res                 # the VAE really ran on row bands
         assert res["max_diff"] <= 1, res                      # bf16 re-rounding of a token-split forward may flip a grey level
         assert res["dance_max_diff"] <= 1 and res["dance_differs_from_svi"], res
+        assert res["tea_max_diff"] <= 1 and res["tea_skips_steps"], res
