@@ -168,13 +168,19 @@ class SVIVideoPipeline(BasePipeline):
         torch_dtype = model_manager.torch_dtype if torch_dtype is None else torch_dtype
         pipe = SVIVideoPipeline(device=device, torch_dtype=torch_dtype, is_test=is_test, num_train_timesteps=num_train_timesteps)
         pipe.fetch_models(model_manager)
-        if use_usp:   # reference :265-273 patches in xfuser USP; here: the native CFG-parallel x sequence-parallel plan
-            from ..distributed.sequence_parallel import get_sp_group
-            pipe.sp_size = get_sp_group().world
-            pipe.use_unified_sequence_parallel = True
-            if pipe.vae is not None and hasattr(pipe.vae, "enable_spatial_sharding"):
-                pipe.vae.enable_spatial_sharding()        # VAE: row bands over ALL ranks, halo exchange per conv
+        if use_usp:
+            pipe.enable_usp()
         return pipe
+
+    def enable_usp(self):
+        """`use_usp=True` (reference :265-273 patches in xfuser USP): install the native multi-GPU plan — the two guidance branches
+        on two halves of the ranks x token-axis sequence parallelism inside a branch for the denoise loop, row bands over ALL
+        ranks with a halo exchange per convolution for the VAE.  Shared by every pipeline of this package."""
+        from ..distributed.sequence_parallel import get_sp_group
+        self.sp_size = get_sp_group().world
+        self.use_unified_sequence_parallel = True
+        if self.vae is not None and hasattr(self.vae, "enable_spatial_sharding"):
+            self.vae.enable_spatial_sharding()
 
     def sp_group(self):
         """The multi-GPU plan of this pipeline (None on one GPU)."""

@@ -41,9 +41,7 @@ class SVIDanceVideoPipeline(SVIVideoPipeline):
         pipe = SVIDanceVideoPipeline(device=device, torch_dtype=torch_dtype, is_test=is_test)
         pipe.fetch_models(model_manager)
         if use_usp:
-            from ..distributed.sequence_parallel import get_sp_group
-            pipe.sp_size = get_sp_group().world
-            pipe.use_unified_sequence_parallel = True
+            pipe.enable_usp()
         return pipe
 
     def encode_pose(self, humanpose_data):

@@ -61,9 +61,7 @@ class SVITalkVideoPipeline(SVIVideoPipeline):
         pipe = SVITalkVideoPipeline(device=device, torch_dtype=torch_dtype, wav2vec_path=wav2vec_path, is_test=is_test)
         pipe.fetch_models(model_manager)
         if use_usp:
-            from ..distributed.sequence_parallel import get_sp_group
-            pipe.sp_size = get_sp_group().world
-            pipe.use_unified_sequence_parallel = True
+            pipe.enable_usp()
         return pipe
 
     def get_audio_embedding(self, audio_path, num_frames, audio_start_idx=0):

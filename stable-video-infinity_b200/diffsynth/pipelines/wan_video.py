@@ -18,9 +18,7 @@ class WanVideoPipeline(SVIVideoPipeline):
         pipe = WanVideoPipeline(device=device, torch_dtype=torch_dtype)
         pipe.fetch_models(model_manager)
         if use_usp:
-            from ..distributed.sequence_parallel import get_sp_group
-            pipe.sp_size = get_sp_group().world
-            pipe.use_unified_sequence_parallel = True
+            pipe.enable_usp()
         return pipe
 
     def encode_image(self, image, num_frames, height, width):

@@ -67,6 +67,30 @@ def _call_dance(pipe, img, seed):
                 humanpose_data=D._pose(FRAMES, H, W, seed=3), cond_wo_pose=False, args=args, progress_bar_cmd=lambda x: x)
 
 
+def _build_t2v(use_usp=False):
+    import test_pipeline_gpu as P
+    from diffsynth import ModelManager, WanVideoPipeline
+    from diffsynth.models.wan_video_dit import WanModel
+    from diffsynth.models.wan_video_vae import WanVideoVAE
+    cfg = synth.CFG_TINY_T2V
+    dit = WanModel(**cfg).eval()
+    dit.load_state_dict({k: v.to(torch.bfloat16).float() for k, v in synth.make_dit_state_dict(cfg, seed=4).items()})
+    vae = WanVideoVAE().eval()
+    vae.load_state_dict({k: v.to(torch.bfloat16).float() for k, v in synth_vae.make_vae_state_dict(seed=0).items()})
+    mm = ModelManager(torch_dtype=torch.bfloat16, device="cpu")
+    mm.add_model("wan_video_dit", dit)
+    mm.add_model("wan_video_vae", vae)
+    pipe = WanVideoPipeline.from_model_manager(mm, torch_dtype=torch.bfloat16, device="cpu", use_usp=use_usp)
+    td = cfg["text_dim"]
+    pipe.prompter = lambda prompt, positive=True: torch.randn(1, 24, td, generator=torch.Generator().manual_seed(31 if positive else 32))
+    return pipe
+
+
+def _call_t2v(pipe, seed):
+    return pipe(prompt="p", negative_prompt="n", num_inference_steps=STEPS, cfg_scale=5.0, seed=seed, tiled=False, height=H, width=W,
+                num_frames=FRAMES, progress_bar_cmd=lambda x: x)
+
+
 def _call(pipe, img, seed, steps=STEPS, **extra):
     args = types.SimpleNamespace(ref_pad_cfg=False, ref_pad_num=-1, sequential_cfg="none")
     return pipe(prompt="p", negative_prompt="n", input_image=img, num_inference_steps=steps, cfg_scale={"text": 5.0}, seed=seed,
@@ -118,6 +142,12 @@ def _usp_worker(rank, world, port, q):
         dref = np.stack([np.array(f) for f in _call_dance(_build_dance(), img, seed=9)]).astype(np.int32)
         dgot = np.stack([np.array(f) for f in _call_dance(_build_dance(use_usp=True), img, seed=9)]).astype(np.int32)
         res["dance_max_diff"] = int(np.abs(dgot - dref).max())
+        # the plain Wan text-to-video pipeline (reference pipelines/wan_video.py) takes the same plan
+        wp = _build_t2v(use_usp=True)
+        wref = np.stack([np.array(f) for f in _call_t2v(_build_t2v(), seed=5)]).astype(np.int32)
+        wgot = np.stack([np.array(f) for f in _call_t2v(wp, seed=5)]).astype(np.int32)
+        res["t2v_max_diff"] = int(np.abs(wgot - wref).max())
+        res["t2v_vae_sharded"] = wp.vae.engine("cpu").halo_exchanges > 0
         res["dance_differs_from_svi"] = bool(np.abs(dref - ref).max() > 0)
         # TeaCache under the plan: every rank must take the same skip decisions (they depend on the timestep embedding only) and
         # keep its own rows' residual
@@ -158,3 +188,4 @@ def test_pipeline_call_with_use_usp(world):
         assert res["max_diff"] <= 1, res                      # bf16 re-rounding of a token-split forward may flip a grey level
         assert res["dance_max_diff"] <= 1 and res["dance_differs_from_svi"], res
         assert res["tea_max_diff"] <= 1 and res["tea_skips_steps"], res
+        assert res["t2v_max_diff"] <= 1 and res["t2v_vae_sharded"], res
